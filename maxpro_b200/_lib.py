@@ -1,0 +1,112 @@
+"""ctypes binding of libmaxpro_b200.so (include/maxpro_b200.h).
+
+This is the stub a maintainer of the reference's Python package would write to
+swap the pyo3 extension (src/lib.rs:166-176) for the C-ABI engine.  There is no
+CPU fallback: if the shared library is missing the import fails loudly, and if
+no B200 is present every compute call raises MaxproError(MAXPRO_ERR_NO_DEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaxpro_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_UNSUPPORTED = range(6)
+METRIC_NONE, METRIC_MAXPRO, METRIC_MAXIMIN = -1, 0, 1
+
+# every symbol include/maxpro_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "maxpro_last_error", "maxpro_version", "maxpro_device_count", "maxpro_set_device",
+    "maxpro_get_device", "maxpro_kernel_launch_count", "maxpro_generate_lhd",
+    "maxpro_generate_batch", "maxpro_criterion", "maxpro_maximin_criterion",
+    "maxpro_l2_distance", "maxpro_score_batch", "maxpro_build_lhd", "maxpro_build_lhd_ex",
+    "maxpro_search_range", "maxpro_reduce_best", "maxpro_anneal_lhd", "maxpro_order_design",
+    "maxpro_search_workspace_bytes", "maxpro_search_range_device",
+    "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe",
+]
+
+
+class MaxproError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[maxpro_b200 status {code}] {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C maxpro_b200/csrc`. maxpro_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    dp, u64, i32, dbl, u32 = C.POINTER(C.c_double), C.c_uint64, C.c_int, C.c_double, C.c_uint32
+    u64p, vp, szp = C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_size_t)
+    sig = {
+        "maxpro_last_error": (C.c_char_p, []),
+        "maxpro_version": (C.c_char_p, []),
+        "maxpro_device_count": (i32, [C.POINTER(i32)]),
+        "maxpro_set_device": (i32, [i32]),
+        "maxpro_get_device": (i32, [C.POINTER(i32)]),
+        "maxpro_kernel_launch_count": (u64, []),
+        "maxpro_generate_lhd": (i32, [u64, u64, u64, dp]),
+        "maxpro_generate_batch": (i32, [u64, u64, u64, u64, u64, dp]),
+        "maxpro_criterion": (i32, [dp, u64, u64, dp]),
+        "maxpro_maximin_criterion": (i32, [dp, u64, u64, dp]),
+        "maxpro_l2_distance": (i32, [dp, dp, u64, dp]),
+        "maxpro_score_batch": (i32, [dp, u64, u64, u64, i32, dp, u64p]),
+        "maxpro_build_lhd": (i32, [u64, u64, u64, i32, u64, dp, dp, u64p]),
+        "maxpro_build_lhd_ex": (i32, [u64, u64, u64, i32, u64, u32, dp, dp, u64p]),
+        "maxpro_search_range": (i32, [u64, u64, i32, u64, u64, u64, dp, u64p]),
+        "maxpro_reduce_best": (i32, [i32, dp, u64p, u64, dp, u64p]),
+        "maxpro_anneal_lhd": (i32, [dp, u64, u64, u64, dbl, dbl, i32, i32, u64, i32, u64, dp, dp, u64p]),
+        "maxpro_order_design": (i32, [dp, u64, u64, i32, i32, dp, u64p]),
+        "maxpro_search_workspace_bytes": (i32, [u64, u64, szp]),
+        "maxpro_search_range_device": (i32, [u64, u64, i32, u64, u64, u64, u32, vp, vp, C.c_size_t, vp]),
+        "maxpro_score_workspace_bytes": (i32, [u64, u64, u64, szp]),
+        "maxpro_score_batch_device": (i32, [vp, u64, u64, u64, i32, vp, vp, vp, C.c_size_t, vp]),
+        "maxpro_fp64_peak_probe": (i32, [i32, dp, dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise MaxproError(rc, lib().maxpro_last_error().decode("utf-8", "replace"))
+
+
+def dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def u64ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def device_count() -> int:
+    c = C.c_int(0)
+    check(lib().maxpro_device_count(C.byref(c)))
+    return c.value
+
+
+def set_device(device: int) -> None:
+    check(lib().maxpro_set_device(device))
+
+
+def kernel_launch_count() -> int:
+    return int(lib().maxpro_kernel_launch_count())

@@ -1,0 +1,590 @@
+// C ABI of the engine (include/maxpro_b200.h).  Host-side orchestration only:
+// validation with the reference's messages, device buffers, kernel dispatch.
+// There is no CPU implementation of any criterion here by design: without a
+// usable sm_100 device every compute entry point fails with MAXPRO_ERR_NO_DEVICE.
+#include "../../include/maxpro_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mp {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+}  // namespace mp
+
+namespace {
+
+using mp::BestRec;
+
+thread_local std::string g_err;
+thread_local int g_device = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    cudaGetLastError();  // clear the sticky-less error state
+    int code = (e == cudaErrorMemoryAllocation) ? MAXPRO_ERR_OOM : MAXPRO_ERR_CUDA;
+    return fail(code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                      \
+    do {                                                    \
+        cudaError_t e_ = (expr);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+int sm_count_cached[64];
+
+int ensure_device(int* sms = nullptr) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(MAXPRO_ERR_NO_DEVICE,
+                    std::string("no CUDA device available; maxpro_b200 has no CPU path (") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + ")");
+    }
+    if (g_device < 0 || g_device >= count) return fail(MAXPRO_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(g_device));
+    if (g_device < 64 && sm_count_cached[g_device] == 0) {
+        int major = 0, n_sm = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, g_device));
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device));
+        if (major != 10)
+            return fail(MAXPRO_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); the kernels are built for sm_100a only");
+        sm_count_cached[g_device] = n_sm;
+    }
+    if (sms) *sms = g_device < 64 ? sm_count_cached[g_device] : 148;
+    return MAXPRO_OK;
+}
+
+bool metric_ok(int m) { return m == MAXPRO_METRIC_MAXPRO || m == MAXPRO_METRIC_MAXIMIN; }
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// ---- small device kernels local to the API -----------------------------------
+
+__global__ void set_result_kernel(BestRec* r, double score, unsigned long long index) {
+    r->score = score;
+    r->index = index;
+}
+
+// total = fold(total, chunk) with chunk-local indices rebased (src/lib.rs:85-97)
+__global__ void fold_result_kernel(BestRec* total, const BestRec* chunk, unsigned long long base,
+                                   int first, int minimize) {
+    double s = chunk->score;
+    unsigned long long i = chunk->index == mp::kNoIndex ? mp::kNoIndex : chunk->index + base;
+    if (first) { total->score = s; total->index = i; return; }
+    bool take = minimize ? mp::better<true>(s, i, total->score, total->index)
+                         : mp::better<false>(s, i, total->score, total->index);
+    if (take) { total->score = s; total->index = i; }
+}
+
+__global__ void init_counter_kernel(unsigned int* c) { *c = 0u; }
+
+// ---- search dispatch -----------------------------------------------------------
+
+constexpr size_t kMaxBlockRecs = 4096;
+constexpr size_t kGenericChunkBytes = 128ull << 20;
+
+unsigned long long generic_chunk(unsigned long long n, unsigned long long d) {
+    unsigned long long per = n * d * sizeof(double);
+    unsigned long long b = kGenericChunkBytes / (per ? per : 1);
+    if (b < 1) b = 1;
+    if (b > (1ull << 16)) b = 1ull << 16;
+    return b;
+}
+
+struct SearchWs {
+    unsigned int* counter;
+    BestRec* block_best;
+    BestRec* chunk_result;
+    double* designs;
+    double* partial;
+    double* scores;
+    size_t total;
+};
+
+SearchWs carve_search_ws(void* base, unsigned long long n, unsigned long long d) {
+    SearchWs w{};
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align_up(bytes); return p; };
+    w.counter = reinterpret_cast<unsigned int*>(take(256));
+    w.block_best = reinterpret_cast<BestRec*>(take(kMaxBlockRecs * sizeof(BestRec)));
+    w.chunk_result = reinterpret_cast<BestRec*>(take(256));
+    if (!(mp::search_small_supported(n, d))) {
+        unsigned long long bc = generic_chunk(n, d);
+        w.designs = reinterpret_cast<double*>(take(bc * n * d * sizeof(double)));
+        w.partial = reinterpret_cast<double*>(take(bc * mp::score_items(n) * sizeof(double)));
+        w.scores = reinterpret_cast<double*>(take(bc * sizeof(double)));
+    }
+    w.total = off;
+    return w;
+}
+
+int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi,
+                             uint32_t flags, void* d_result, void* d_ws, size_t ws_bytes, cudaStream_t stream,
+                             int sms) {
+    (void)flags;
+    if (n == 0) return fail(MAXPRO_ERR_INVALID, "n_samples must be positive and nonzero");
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
+    if (hi < lo) return fail(MAXPRO_ERR_INVALID, "search range is inverted");
+    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the LHD-Philox v1 stratum-exactness bound");
+    SearchWs w = carve_search_ws(d_ws, n, d);
+    if (ws_bytes < w.total) return fail(MAXPRO_ERR_INVALID, "workspace smaller than maxpro_search_workspace_bytes");
+    BestRec* result = static_cast<BestRec*>(d_result);
+    const bool minimize = metric == MAXPRO_METRIC_MAXPRO;
+
+    if (hi == lo) {  // identity of the fold (src/lib.rs:77-83)
+        set_result_kernel<<<1, 1, 0, stream>>>(result, minimize ? INFINITY : -INFINITY, mp::kNoIndex);
+        mp::count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return MAXPRO_OK;
+    }
+    if (n < 2) {
+        // one point: maxpro == 0.0 (maxpro_utils.rs:75-77), maximin == +INF (maximin_utils.rs:57)
+        // for every candidate, so the fold keeps the last index.
+        set_result_kernel<<<1, 1, 0, stream>>>(result, minimize ? 0.0 : INFINITY, hi - 1);
+        mp::count_launch();
+        CUDA_TRY(cudaGetLastError());
+        return MAXPRO_OK;
+    }
+    init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
+    mp::count_launch();
+    if (mp::search_small_supported(n, d)) {
+        mp::SearchLaunch L{};
+        L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
+        L.block_best = w.block_best; L.done_counter = w.counter; L.result = result;
+        L.threads = mp::search_small_pick_threads(n, d);
+        unsigned long long total = hi - lo;
+        unsigned long long want = (total + L.threads - 1) / L.threads;
+        L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
+        L.stream = stream;
+        CUDA_TRY(mp::launch_search_small(L));
+        mp::count_launch();
+        return MAXPRO_OK;
+    }
+    // Any other shape: materialise candidates chunk by chunk in HBM and score them with
+    // the tiled pair kernel.  Same stream definition, same fold; GPU only.
+    const unsigned long long bc = generic_chunk(n, d);
+    int first = 1;
+    for (unsigned long long c0 = lo; c0 < hi; c0 += bc) {
+        unsigned long long cnt = hi - c0 < bc ? hi - c0 : bc;
+        CUDA_TRY(mp::launch_generate(n, d, seed, c0, cnt, w.designs, stream));
+        mp::ScoreLaunch S{};
+        S.designs = w.designs; S.b = cnt; S.n = n; S.d = d; S.metric = metric;
+        S.scores = w.scores; S.partial = w.partial; S.block_best = w.block_best;
+        S.done_counter = w.counter; S.result = w.chunk_result; S.stream = stream;
+        CUDA_TRY(mp::launch_score_batch(S));
+        fold_result_kernel<<<1, 1, 0, stream>>>(result, w.chunk_result, c0, first, minimize ? 1 : 0);
+        mp::count_launch();
+        CUDA_TRY(cudaGetLastError());
+        first = 0;
+    }
+    return MAXPRO_OK;
+}
+
+struct ScoreWs {
+    unsigned int* counter;
+    BestRec* block_best;
+    double* partial;
+    size_t total;
+};
+
+ScoreWs carve_score_ws(void* base, unsigned long long b, unsigned long long n) {
+    ScoreWs w{};
+    size_t off = 0;
+    char* p0 = static_cast<char*>(base);
+    auto take = [&](size_t bytes) { char* p = p0 ? p0 + off : nullptr; off += align_up(bytes); return p; };
+    w.counter = reinterpret_cast<unsigned int*>(take(256));
+    w.block_best = reinterpret_cast<BestRec*>(take(kMaxBlockRecs * sizeof(BestRec)));
+    w.partial = reinterpret_cast<double*>(take(b * mp::score_items(n) * sizeof(double)));
+    w.total = off;
+    return w;
+}
+
+int score_batch_device_impl(const double* d_designs, uint64_t b, uint64_t n, uint64_t d, int metric,
+                            double* d_scores, void* d_result, void* d_ws, size_t ws_bytes, cudaStream_t stream) {
+    if (n == 0) return fail(MAXPRO_ERR_INVALID, "Cannot pass an empty design");
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "Must have finite, positive number of dimensions");
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
+    if (!d_scores) return fail(MAXPRO_ERR_INVALID, "d_scores must not be NULL");
+    ScoreWs w = carve_score_ws(d_ws, b, n);
+    if (ws_bytes < w.total) return fail(MAXPRO_ERR_INVALID, "workspace smaller than maxpro_score_workspace_bytes");
+    if (b == 0) {
+        if (d_result) {
+            set_result_kernel<<<1, 1, 0, stream>>>(static_cast<BestRec*>(d_result),
+                                                  metric == MAXPRO_METRIC_MAXPRO ? INFINITY : -INFINITY, mp::kNoIndex);
+            mp::count_launch();
+        }
+        return MAXPRO_OK;
+    }
+    init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
+    mp::count_launch();
+    mp::ScoreLaunch S{};
+    S.designs = d_designs; S.b = b; S.n = n; S.d = d; S.metric = metric; S.scores = d_scores;
+    S.partial = w.partial; S.block_best = w.block_best; S.done_counter = w.counter;
+    S.result = static_cast<BestRec*>(d_result); S.stream = stream;
+    CUDA_TRY(mp::launch_score_batch(S));
+    return MAXPRO_OK;
+}
+
+int criterion_host(const double* design, uint64_t n, uint64_t d, int metric, double* out) {
+    if (!design || !out) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n == 0) return fail(MAXPRO_ERR_INVALID, "Cannot pass an empty design");  // maxpro_utils.rs:74, maximin_utils.rs:56
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "Must have finite, positive number of dimensions");  // maxpro_utils.rs:79
+    return maxpro_score_batch(design, 1, n, d, metric, out, nullptr);
+}
+
+}  // namespace
+
+// =============================== exported ======================================
+
+extern "C" {
+
+const char* maxpro_last_error(void) { return g_err.c_str(); }
+const char* maxpro_version(void) { return "maxpro_b200 0.1.0 (sm_100a; LHD-Philox v1)"; }
+uint64_t maxpro_kernel_launch_count(void) { return mp::g_launches.load(std::memory_order_relaxed); }
+
+int maxpro_device_count(int* count) {
+    if (!count) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *count = c;
+    return MAXPRO_OK;
+}
+
+int maxpro_set_device(int device) {
+    if (device < 0) return fail(MAXPRO_ERR_INVALID, "device index out of range");
+    g_device = device;
+    return MAXPRO_OK;
+}
+
+int maxpro_get_device(int* device) {
+    if (!device) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    *device = g_device;
+    return MAXPRO_OK;
+}
+
+int maxpro_generate_lhd(uint64_t n, uint64_t d, uint64_t seed, double* out) {
+    if (n == 0) return MAXPRO_OK;  // lhd.rs:98-101
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be a positive, nonzero integer");  // lhd.rs:106
+    if (!out) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the LHD-Philox v1 stratum-exactness bound");
+    if (int rc = ensure_device()) return rc;
+    DevBuf buf;
+    CUDA_TRY(buf.alloc(n * d * sizeof(double)));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(mp::launch_generate(n, d, seed, 0, 1, buf.as<double>(), st));
+    CUDA_TRY(cudaMemcpyAsync(out, buf.p, n * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MAXPRO_OK;
+}
+
+// Test / tooling helper: candidates lo..lo+count-1 of the search seeded `seed`.
+int maxpro_generate_batch(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, uint64_t count, double* out) {
+    if (n == 0 || count == 0) return MAXPRO_OK;
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be a positive, nonzero integer");
+    if (!out) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the LHD-Philox v1 stratum-exactness bound");
+    if (int rc = ensure_device()) return rc;
+    DevBuf buf;
+    size_t bytes = count * n * d * sizeof(double);
+    CUDA_TRY(buf.alloc(bytes));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(mp::launch_generate(n, d, seed, lo, count, buf.as<double>(), st));
+    CUDA_TRY(cudaMemcpyAsync(out, buf.p, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MAXPRO_OK;
+}
+
+int maxpro_criterion(const double* design, uint64_t n, uint64_t d, double* out) {
+    return criterion_host(design, n, d, MAXPRO_METRIC_MAXPRO, out);
+}
+
+int maxpro_maximin_criterion(const double* design, uint64_t n, uint64_t d, double* out) {
+    return criterion_host(design, n, d, MAXPRO_METRIC_MAXIMIN, out);
+}
+
+int maxpro_l2_distance(const double* a, const double* b, uint64_t d, double* out) {
+    if (!a || !b || !out) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "Points must have nonzero length");  // maximin_utils.rs:32
+    double acc = 0.0;
+    for (uint64_t k = 0; k < d; ++k) {
+        volatile double diff = a[k] - b[k];  // volatile: no FMA contraction, Rust never fuses
+        volatile double sq = diff * diff;
+        acc += sq;
+    }
+    *out = std::sqrt(acc);
+    return MAXPRO_OK;
+}
+
+int maxpro_score_batch(const double* designs, uint64_t b, uint64_t n, uint64_t d, int metric,
+                       double* scores, uint64_t* argbest) {
+    if (n == 0) return fail(MAXPRO_ERR_INVALID, "Cannot pass an empty design");
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "Must have finite, positive number of dimensions");
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
+    if (b == 0) { if (argbest) *argbest = UINT64_MAX; return MAXPRO_OK; }
+    if (!designs) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (int rc = ensure_device()) return rc;
+    const size_t bytes = b * n * d * sizeof(double);
+    size_t ws_bytes = 0;
+    if (int rc = maxpro_score_workspace_bytes(b, n, d, &ws_bytes)) return rc;
+    DevBuf dd, ds, dr, dw;
+    CUDA_TRY(dd.alloc(bytes));
+    CUDA_TRY(ds.alloc(b * sizeof(double)));
+    CUDA_TRY(dr.alloc(sizeof(BestRec)));
+    CUDA_TRY(dw.alloc(ws_bytes));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(cudaMemcpyAsync(dd.p, designs, bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = score_batch_device_impl(dd.as<double>(), b, n, d, metric, ds.as<double>(), dr.p, dw.p, ws_bytes, st)) return rc;
+    BestRec rec;
+    if (scores) CUDA_TRY(cudaMemcpyAsync(scores, ds.p, b * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&rec, dr.p, sizeof(rec), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (argbest) *argbest = rec.index;
+    return MAXPRO_OK;
+}
+
+int maxpro_search_range(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi,
+                        double* best_score, uint64_t* best_index) {
+    if (n == 0) return fail(MAXPRO_ERR_INVALID, "n_samples must be positive and nonzero");
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    size_t ws_bytes = 0;
+    if (int rc = maxpro_search_workspace_bytes(n, d, &ws_bytes)) return rc;
+    DevBuf dr, dw;
+    CUDA_TRY(dr.alloc(sizeof(BestRec)));
+    CUDA_TRY(dw.alloc(ws_bytes));
+    cudaStream_t st = cudaStreamPerThread;
+    if (int rc = search_range_device_impl(n, d, metric, seed, lo, hi, 0, dr.p, dw.p, ws_bytes, st, sms)) return rc;
+    BestRec rec;
+    CUDA_TRY(cudaMemcpyAsync(&rec, dr.p, sizeof(rec), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (best_score) *best_score = rec.score;
+    if (best_index) *best_index = rec.index;
+    return MAXPRO_OK;
+}
+
+int maxpro_reduce_best(int metric, const double* scores, const uint64_t* indices, uint64_t count,
+                       double* best_score, uint64_t* best_index) {
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
+    if (count && (!scores || !indices)) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    const bool minimize = metric == MAXPRO_METRIC_MAXPRO;
+    double bs = minimize ? INFINITY : -INFINITY;  // lib.rs:77-83
+    unsigned long long bi = mp::kNoIndex;
+    for (uint64_t r = 0; r < count; ++r) {
+        bool take = minimize ? mp::better<true>(scores[r], indices[r], bs, bi)
+                             : mp::better<false>(scores[r], indices[r], bs, bi);
+        if (take) { bs = scores[r]; bi = indices[r]; }
+    }
+    if (best_score) *best_score = bs;
+    if (best_index) *best_index = bi;
+    return MAXPRO_OK;
+}
+
+int maxpro_build_lhd_ex(uint64_t n, uint64_t d, uint64_t n_iterations, int metric, uint64_t seed,
+                        uint32_t flags, double* out_design, double* out_score, uint64_t* out_index) {
+    if (n == 0) return fail(MAXPRO_ERR_INVALID, "n_samples must be positive and nonzero");        // lib.rs:37
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");            // lib.rs:38
+    if (n_iterations == 0) return fail(MAXPRO_ERR_INVALID, "n_iterations must be positive and nonzero");  // lib.rs:39-42
+    if (metric != MAXPRO_METRIC_NONE && !metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
+    if (!out_design) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (metric == MAXPRO_METRIC_NONE) {  // lib.rs:46-50
+        if (out_score) *out_score = NAN;
+        if (out_index) *out_index = 0;
+        return maxpro_generate_lhd(n, d, seed, out_design);
+    }
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    size_t ws_bytes = 0;
+    if (int rc = maxpro_search_workspace_bytes(n, d, &ws_bytes)) return rc;
+    DevBuf dr, dw, dx;
+    CUDA_TRY(dr.alloc(sizeof(BestRec)));
+    CUDA_TRY(dw.alloc(ws_bytes));
+    CUDA_TRY(dx.alloc(n * d * sizeof(double)));
+    cudaStream_t st = cudaStreamPerThread;
+    if (int rc = search_range_device_impl(n, d, metric, seed, 0, n_iterations, flags, dr.p, dw.p, ws_bytes, st, sms)) return rc;
+    BestRec rec;
+    CUDA_TRY(cudaMemcpyAsync(&rec, dr.p, sizeof(rec), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (rec.index == mp::kNoIndex) return fail(MAXPRO_ERR_CUDA, "search produced no winner (all scores NaN?)");
+    // only (score, index) left the chip: rebuild the winner from its index (lib.rs:70)
+    CUDA_TRY(mp::launch_generate(n, d, seed, rec.index, 1, dx.as<double>(), st));
+    CUDA_TRY(cudaMemcpyAsync(out_design, dx.p, n * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (out_score) *out_score = rec.score;
+    if (out_index) *out_index = rec.index;
+    return MAXPRO_OK;
+}
+
+int maxpro_build_lhd(uint64_t n, uint64_t d, uint64_t n_iterations, int metric, uint64_t seed,
+                     double* out_design, double* out_score, uint64_t* out_index) {
+    return maxpro_build_lhd_ex(n, d, n_iterations, metric, seed, MAXPRO_FLAG_DEFAULT, out_design, out_score, out_index);
+}
+
+int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_iterations,
+                      double initial_temp, double cooling_rate, int metric, int minimize, uint64_t seed,
+                      int swap, uint64_t n_chains, double* out_design, double* out_metric, uint64_t* out_chain) {
+    if (n == 0) return MAXPRO_OK;  // anneal.rs:69-71
+    if (n_iterations == 0) return fail(MAXPRO_ERR_INVALID, "n_iterations must be positive and nonzero");  // anneal.rs:72-75
+    if (!(initial_temp > 0.0)) return fail(MAXPRO_ERR_INVALID, "initial_temp must be positive and nonzero");  // anneal.rs:76-79
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Unknown metric. Available metrics are 'maxpro' and 'maximin'.");
+    if (d == 0) return fail(MAXPRO_ERR_INVALID, "Must have finite, positive number of dimensions");
+    if (n_chains == 0) return fail(MAXPRO_ERR_INVALID, "n_chains must be positive and nonzero");
+    if (!design || !out_design) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (int rc = ensure_device()) return rc;
+    if (!mp::anneal_supported(n, d, swap))
+        return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the shared-memory annealer (n*d*8 bytes, doubled for jitter, must fit 227 KB)");
+    const size_t nd = n * d;
+    DevBuf dx, db, dm, di;
+    CUDA_TRY(dx.alloc(nd * sizeof(double)));
+    CUDA_TRY(db.alloc(n_chains * nd * sizeof(double)));
+    CUDA_TRY(dm.alloc(n_chains * sizeof(double)));
+    CUDA_TRY(di.alloc(n_chains * sizeof(unsigned int)));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(cudaMemcpyAsync(dx.p, design, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    mp::AnnealLaunch L{};
+    L.design = dx.as<double>(); L.n = n; L.d = d; L.iters = n_iterations; L.seed = seed; L.n_chains = n_chains;
+    L.t0 = initial_temp; L.cooling = cooling_rate; L.metric = metric; L.minimize = minimize ? 1 : 0; L.swap = swap ? 1 : 0;
+    L.best_design = db.as<double>(); L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.stream = st;
+    CUDA_TRY(mp::launch_anneal(L));
+    std::vector<double> metrics(n_chains);
+    std::vector<unsigned int> improved(n_chains);
+    CUDA_TRY(cudaMemcpyAsync(metrics.data(), dm.p, n_chains * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(improved.data(), di.p, n_chains * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // best chain: strictly better metric wins, the lowest chain index on ties
+    uint64_t best = 0;
+    for (uint64_t c = 1; c < n_chains; ++c)
+        if (minimize ? (metrics[c] < metrics[best]) : (metrics[c] > metrics[best])) best = c;
+    if (improved[best]) {
+        CUDA_TRY(cudaMemcpyAsync(out_design, db.as<double>() + best * nd, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        std::memcpy(out_design, design, nd * sizeof(double));  // never improved: the input is the global best (anneal.rs:93)
+    }
+    if (out_metric) *out_metric = metrics[best];
+    if (out_chain) *out_chain = best;
+    return MAXPRO_OK;
+}
+
+int maxpro_order_design(const double* design, uint64_t n, uint64_t d, int metric, int minimize,
+                        double* out_design, uint64_t* perm) {
+    if (n == 0 || d == 0) return MAXPRO_OK;  // order.rs:38-46
+    if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Unknown metric. Available metrics are 'maxpro' and 'maximin'.");
+    if (!design || !out_design) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n >= (1ull << 32) - 1) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples too large to index");
+    if (int rc = ensure_device()) return rc;
+    DevBuf dx, dp, da, dpool;
+    CUDA_TRY(dx.alloc(n * d * sizeof(double)));
+    CUDA_TRY(dp.alloc(n * sizeof(unsigned long long)));
+    CUDA_TRY(da.alloc(n * sizeof(double)));
+    CUDA_TRY(dpool.alloc(n * sizeof(unsigned int)));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(cudaMemcpyAsync(dx.p, design, n * d * sizeof(double), cudaMemcpyHostToDevice, st));
+    mp::OrderLaunch L{};
+    L.design = dx.as<double>(); L.n = n; L.d = d; L.metric = metric; L.minimize = minimize ? 1 : 0;
+    L.perm = dp.as<unsigned long long>(); L.acc = da.as<double>(); L.pool = dpool.as<unsigned int>(); L.stream = st;
+    CUDA_TRY(mp::launch_order(L));
+    std::vector<unsigned long long> hp(n);
+    CUDA_TRY(cudaMemcpyAsync(hp.data(), dp.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<double> tmp;
+    const double* src = design;
+    if (out_design == design) { tmp.assign(design, design + n * d); src = tmp.data(); }
+    for (uint64_t m = 0; m < n; ++m) {
+        std::memcpy(out_design + m * d, src + hp[m] * d, d * sizeof(double));
+        if (perm) perm[m] = hp[m];
+    }
+    return MAXPRO_OK;
+}
+
+int maxpro_search_workspace_bytes(uint64_t n, uint64_t d, size_t* bytes) {
+    if (!bytes) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n == 0 || d == 0) return fail(MAXPRO_ERR_INVALID, "n_samples and n_dim must be positive and nonzero");
+    *bytes = carve_search_ws(nullptr, n, d).total;
+    return MAXPRO_OK;
+}
+
+int maxpro_search_range_device(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi,
+                               uint32_t flags, void* d_result, void* d_workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!d_result || !d_workspace) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    return search_range_device_impl(n, d, metric, seed, lo, hi, flags, d_result, d_workspace, workspace_bytes,
+                                    static_cast<cudaStream_t>(stream), sms);
+}
+
+int maxpro_score_workspace_bytes(uint64_t b, uint64_t n, uint64_t d, size_t* bytes) {
+    if (!bytes) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n == 0 || d == 0) return fail(MAXPRO_ERR_INVALID, "Cannot pass an empty design");
+    *bytes = carve_score_ws(nullptr, b, n).total;
+    return MAXPRO_OK;
+}
+
+int maxpro_score_batch_device(const double* d_designs, uint64_t b, uint64_t n, uint64_t d, int metric,
+                              double* d_scores, void* d_result, void* d_workspace, size_t workspace_bytes,
+                              void* stream) {
+    if (b && !d_designs) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (!d_workspace) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (int rc = ensure_device()) return rc;
+    return score_batch_device_impl(d_designs, b, n, d, metric, d_scores, d_result, d_workspace, workspace_bytes,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int maxpro_fp64_peak_probe(int repeats, double* tflops, double* kernel_ms) {
+    if (!tflops) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    if (repeats < 1) repeats = 1;
+    DevBuf sink;
+    CUDA_TRY(sink.alloc(sizeof(double)));
+    cudaStream_t st = cudaStreamPerThread;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int threads = 256, grid = sms * 8, iters = 1 << 16;
+    double best_ms = 1e30;
+    for (int r = 0; r < repeats + 1; ++r) {  // first launch is warm-up
+        cudaEventRecord(e0, st);
+        cudaError_t e = mp::launch_dfma_probe(sink.as<double>(), grid, threads, iters, st);
+        cudaEventRecord(e1, st);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(e, "dfma probe"); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)grid;
+    *tflops = flops / (best_ms * 1e-3) / 1e12;
+    if (kernel_ms) *kernel_ms = best_ms;
+    return MAXPRO_OK;
+}
+
+}  // extern "C"

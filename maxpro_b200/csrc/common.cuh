@@ -1,0 +1,78 @@
+// Shared device/host helpers for the maxpro B200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace mp {
+
+constexpr double kEps = 1e-12;  // src/maxpro_utils.rs:35
+
+// Winner record that leaves the chip: 16 bytes.
+struct __align__(16) BestRec {
+    double score;
+    unsigned long long index;
+};
+
+constexpr unsigned long long kNoIndex = 0xFFFFFFFFFFFFFFFFull;
+
+// Fold of src/lib.rs:85-97 with `a` the earlier (left) element: the left one
+// survives only on a strict win, so equal scores keep the LATER index.  Records
+// carry global indices, so "later" is simply the larger index and the fold is
+// order-free.  kNoIndex marks the identity (lib.rs:77-83).
+template <bool MINIMIZE>
+__host__ __device__ __forceinline__ bool better(double sa, unsigned long long ia,
+                                                double sb, unsigned long long ib) {
+    if (ib == kNoIndex) return true;
+    if (ia == kNoIndex) return false;
+    if (sa == sb) return ia > ib;
+    return MINIMIZE ? (sa < sb) : (sa > sb);
+}
+
+template <bool MINIMIZE>
+__device__ __forceinline__ void warp_reduce_best(double& s, unsigned long long& i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double so = __shfl_xor_sync(0xffffffffu, s, off);
+        unsigned long long io = __shfl_xor_sync(0xffffffffu, i, off);
+        if (better<MINIMIZE>(so, io, s, i)) { s = so; i = io; }
+    }
+}
+
+__device__ __forceinline__ double warp_reduce_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__device__ __forceinline__ double warp_reduce_min(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// 1/x for normal, positive x: MUFU.RCP64H seed (>= 20 good bits) + two Newton
+// steps (20 -> 40 -> 80 bits).  Relative error ~1 ulp; no special-case branch.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Running sum of reciprocals without a divide per term:
+//   num/den + 1/p = (num*p + den) / (den*p)
+// Two FP64 ops per pushed term; one reciprocal per flush.  Safe while the
+// product of pushed terms stays in range: every p is in [1e-12, ~1] for
+// designs in the unit cube, so <= 16 terms keep den >= 1e-192.
+struct RecipChain {
+    double num, den;
+    __device__ __forceinline__ void reset() { num = 0.0; den = 1.0; }
+    __device__ __forceinline__ void push(double p) { num = fma(num, p, den); den *= p; }
+    __device__ __forceinline__ double flush() { double v = num * fast_rcp(den); reset(); return v; }
+};
+
+}  // namespace mp

@@ -1,0 +1,75 @@
+// K1 alone: materialise designs of the LHD-Philox v1 stream in device memory.
+//
+// Replaces lhd::generate_lhd (src/lhd.rs:97-132) for the cases where a design
+// has to exist outside a search kernel: maxpro_generate_lhd, build_lhd with
+// metric None (src/lib.rs:46-50) and regeneration of a search winner from its
+// (seed, index).  One CTA per (design, column); the inside-out Fisher-Yates is a
+// chain of n dependent steps, so a single lane walks it in shared memory and the
+// whole CTA writes the column out.  Not a throughput path: the search kernels
+// generate their candidates in place and never call this.
+#include "common.cuh"
+#include "philox.cuh"
+#include "kernels.h"
+
+namespace mp {
+
+__device__ __forceinline__ void fy_column(double* col, size_t stride, unsigned long long n, uint32_t k,
+                                          uint32_t s_lo, uint32_t s_hi, double c1, double c0) {
+    for (unsigned long long i = 0; i < n; i += 2) {
+        Philox4 w = philox4x32_10((uint32_t)(i >> 1), k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+        {
+            uint32_t j = mulhi_bound(w.y, (uint32_t)i + 1u);
+            unsigned long long m = (i << 32) | w.x;
+            double v = fma((double)m, c1, c0);
+            col[i * stride] = col[j * stride];
+            col[j * stride] = v;
+        }
+        if (i + 1 < n) {
+            uint32_t j = mulhi_bound(w.w, (uint32_t)i + 2u);
+            unsigned long long m = ((i + 1) << 32) | w.z;
+            double v = fma((double)m, c1, c0);
+            col[(i + 1) * stride] = col[j * stride];
+            col[j * stride] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) generate_kernel(unsigned long long n, unsigned long long d,
+                                                       unsigned long long seed, unsigned long long lo,
+                                                       unsigned long long count, double* out, double c1,
+                                                       double c0, int use_smem) {
+    extern __shared__ double col_s[];
+    for (unsigned long long item = blockIdx.x; item < count * d; item += gridDim.x) {
+        const unsigned long long c = item / d, k = item % d;
+        const unsigned long long stream = seed + lo + c;  // src/lib.rs:70
+        double* dst = out + c * n * d + k;                 // lhd[i][k], row-major
+        if (use_smem) {
+            if (threadIdx.x == 0)
+                fy_column(col_s, 1, n, (uint32_t)k, (uint32_t)stream, (uint32_t)(stream >> 32), c1, c0);
+            __syncthreads();
+            for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) dst[i * d] = col_s[i];
+            __syncthreads();
+        } else if (threadIdx.x == 0) {
+            fy_column(dst, d, n, (uint32_t)k, (uint32_t)stream, (uint32_t)(stream >> 32), c1, c0);
+        }
+    }
+}
+
+cudaError_t launch_generate(unsigned long long n, unsigned long long d, unsigned long long seed,
+                            unsigned long long lo, unsigned long long count, double* d_out,
+                            cudaStream_t stream) {
+    if (n == 0 || d == 0 || count == 0) return cudaSuccess;
+    const double c1 = ldexp(1.0 / (double)n, -32), c0 = 0.5 * c1;
+    size_t smem = n * sizeof(double);
+    int use_smem = smem <= 200 * 1024;
+    if (!use_smem) smem = 0;
+    cudaError_t e = cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    if (e != cudaSuccess) return e;
+    unsigned long long items = count * d;
+    int grid = (int)(items < 148ull * 64 ? items : 148ull * 64);
+    generate_kernel<<<grid, 128, smem, stream>>>(n, d, seed, lo, count, d_out, c1, c0, use_smem);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace mp

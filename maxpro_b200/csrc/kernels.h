@@ -1,0 +1,86 @@
+// Host-side launchers of the engine's kernels (internal; the public surface is
+// include/maxpro_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace mp {
+
+constexpr size_t kSmemBudget = 227 * 1024;  // usable dynamic shared memory per CTA on sm_100
+constexpr int kSmallMaxD = 8;               // thread-per-candidate kernels are instantiated for d <= 8
+
+// ---- K1+K2: generate-and-score search ---------------------------------------
+struct SearchLaunch {
+    unsigned long long n, d;
+    int metric;  // 0 maxpro, 1 maximin
+    unsigned long long seed, lo, hi;
+    uint32_t flags;
+    BestRec* block_best;         // [grid]
+    unsigned int* done_counter;  // zero before first use; the kernel re-arms it
+    BestRec* result;
+    int grid, threads;
+    cudaStream_t stream;
+};
+bool search_small_supported(unsigned long long n, unsigned long long d);
+int search_small_pick_threads(unsigned long long n, unsigned long long d);
+cudaError_t launch_search_small(const SearchLaunch& L);
+
+bool search_cta_supported(unsigned long long n, unsigned long long d);
+cudaError_t launch_search_cta(const SearchLaunch& L);
+
+// ---- K1 alone: materialise designs (winner regeneration, generate_lhd) -------
+// out: count designs, row-major n*d each; design c uses stream seed + lo + c.
+cudaError_t launch_generate(unsigned long long n, unsigned long long d, unsigned long long seed,
+                            unsigned long long lo, unsigned long long count, double* d_out,
+                            cudaStream_t stream);
+
+// ---- K2 on supplied designs ---------------------------------------------------
+struct ScoreLaunch {
+    const double* designs;  // [b][n][d] device
+    unsigned long long b, n, d;
+    int metric;
+    double* scores;          // [b] device (required)
+    double* partial;         // [b * items] device scratch
+    BestRec* block_best;     // [finalize grid]
+    unsigned int* done_counter;
+    BestRec* result;         // may be null
+    cudaStream_t stream;
+};
+unsigned long long score_items(unsigned long long n);  // tile pairs per design
+int score_finalize_grid(unsigned long long b);
+cudaError_t launch_score_batch(const ScoreLaunch& L);
+
+// ---- K3: annealing chains ---------------------------------------------------------
+struct AnnealLaunch {
+    const double* design;  // device, [n][d]
+    unsigned long long n, d, iters, seed, n_chains;
+    double t0, cooling;
+    int metric, minimize, swap;
+    double* best_design;     // [n_chains][n*d]
+    double* best_metric;     // [n_chains]
+    unsigned int* improved;  // [n_chains]
+    cudaStream_t stream;
+};
+bool anneal_supported(unsigned long long n, unsigned long long d, int swap);
+cudaError_t launch_anneal(const AnnealLaunch& L);
+
+// ---- K4: greedy ordering ------------------------------------------------------------
+struct OrderLaunch {
+    const double* design;     // device, [n][d]
+    unsigned long long n, d;
+    int metric, minimize;
+    unsigned long long* perm; // device, [n]
+    double* acc;              // device scratch, [n]
+    unsigned int* pool;       // device scratch, [n]
+    cudaStream_t stream;
+};
+cudaError_t launch_order(const OrderLaunch& L);
+
+// ---- FP64 pipe peak probe -------------------------------------------------------
+cudaError_t launch_dfma_probe(double* d_sink, int grid, int threads, int iters, cudaStream_t stream);
+
+void count_launch(int k = 1);
+
+}  // namespace mp

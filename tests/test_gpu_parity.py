@@ -1,0 +1,303 @@
+"""GPU (-m gpu): parity of the CUDA path against the CPU oracle, through the C ABI.
+
+Tolerances (BASELINE.json north_star): criterion within 1e-9 relative in fp64; LHD validity
+and generated designs bit-exact; argbest over an identical supplied candidate set identical;
+maximin (min/sqrt of exactly-rounded terms) bit-exact.
+Nothing here reads /root/reference: fixtures live in tests/golden/.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import lhd_bins_ok, random_lhd
+from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, METRIC_NONE, MaxproError, _lib, engine, maxpro
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9  # north_star tolerance for the fp64 criterion
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert _lib.device_count() > 0, "no CUDA device: the -m gpu tests must run on a B200"
+
+
+# ---------------------------------------------------------------- criteria
+
+def test_known_answers():
+    a, b = [[0.0, 1.0], [1.0, 0.0]], [[0.0, 2.0], [1.0, 0.0]]
+    assert abs(engine.maxpro_criterion(a) - 1.0) < 1e-9        # maxpro_utils.rs:117-124
+    assert abs(engine.maxpro_criterion(b) - 0.5) < 1e-9        # maxpro_utils.rs:126-133
+    assert abs(engine.maximin_criterion(a) - 2.0 ** 0.5) < 1e-9  # maximin_utils.rs:85-92
+    assert abs(engine.maximin_criterion(b) - 5.0 ** 0.5) < 1e-9  # maximin_utils.rs:94-101
+    assert engine.maxpro_criterion([[0.3, 0.4]]) == 0.0        # n < 2, maxpro_utils.rs:75-77
+    assert engine.maximin_criterion([[0.3, 0.4]]) == math.inf  # n == 1, maximin_utils.rs:57
+
+
+def test_r_golden_design(r_golden):
+    v = engine.maxpro_criterion(r_golden["design"])
+    assert math.isclose(v, r_golden["r_measure"], rel_tol=1e-7)          # comparison_r.py:131
+    assert math.isclose(v, r_golden["rust_value_readme"], rel_tol=REL)   # README.md:90
+    assert engine.maximin_criterion(r_golden["design"]) == oracle.maximin_criterion(r_golden["design"])
+
+
+def test_pymaxpro_vectors(pymaxpro_golden):
+    for c in pymaxpro_golden["cases"]:
+        assert math.isclose(engine.maxpro_criterion(c["design"]), c["maxpro_criterion"], rel_tol=REL), (c["n"], c["d"])
+
+
+@pytest.mark.parametrize("n,d", [(2, 1), (2, 2), (3, 5), (10, 4), (50, 2), (50, 3), (64, 3), (65, 2), (100, 5),
+                                 (129, 17), (130, 10), (500, 10), (1000, 20), (700, 33)])
+def test_criterion_shapes(n, d):
+    rng = np.random.default_rng(n * 1000 + d)
+    x = random_lhd(rng, n, d)
+    assert math.isclose(engine.maxpro_criterion(x), oracle.maxpro_criterion(x), rel_tol=REL)
+    assert engine.maximin_criterion(x) == oracle.maximin_criterion(x)  # bit-exact
+
+
+def test_criterion_outside_unit_cube_and_duplicates():
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(40, 3)) * 50.0
+    assert math.isclose(engine.maxpro_criterion(x), oracle.maxpro_criterion(x), rel_tol=REL)
+    assert engine.maximin_criterion(x) == oracle.maximin_criterion(x)
+    x[7] = x[3]  # coincident points: product 0 -> term 1/eps
+    assert math.isclose(engine.maxpro_criterion(x), oracle.maxpro_criterion(x), rel_tol=REL)
+    assert engine.maximin_criterion(x) == 0.0
+    x[11, 1] = x[3, 1]  # one shared coordinate
+    assert math.isclose(engine.maxpro_criterion(x), oracle.maxpro_criterion(x), rel_tol=REL)
+
+
+def test_criterion_large_single_design():
+    rng = np.random.default_rng(8)
+    x = random_lhd(rng, 5000, 8)  # C5-sized design: 12.5M pairs over many tile items
+    assert math.isclose(engine.maxpro_criterion(x), oracle.maxpro_criterion(x), rel_tol=REL)
+    assert engine.maximin_criterion(x) == oracle.maximin_criterion(x)
+
+
+# ---------------------------------------------------------------- score_batch (parity entry point)
+
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+def test_score_batch_parity_4096(metric):
+    """B = 4096 host-supplied designs -> per-score tolerance and identical argbest."""
+    designs = np.stack([oracle.generate_lhd(50, 3, 10_000 + i) for i in range(4096)])
+    ref, ref_arg = oracle.score_batch(designs, metric)
+    got, arg = engine.score_batch(designs, metric)
+    if metric == METRIC_MAXPRO:
+        assert rel_err(got, ref) < REL
+    else:
+        assert np.array_equal(got, ref)
+    assert arg == ref_arg
+
+
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+def test_score_batch_tie_rule(metric):
+    rng = np.random.default_rng(11)
+    base = np.stack([random_lhd(rng, 20, 3) for _ in range(300)])
+    scores, arg = engine.score_batch(base, metric)
+    other = (arg + 1) % 300
+    dup = np.concatenate([base, base[arg:arg + 1], base[other:other + 1]])
+    scores2, arg2 = engine.score_batch(dup, metric)
+    assert scores2[300] == scores2[arg]      # identical inputs -> identical bits
+    assert arg2 == 300                       # later index wins (lib.rs:85-97)
+    assert oracle.score_batch(dup, metric)[1] == 300
+    front = np.concatenate([base[arg:arg + 1], base])
+    assert engine.score_batch(front, metric)[1] == arg + 1
+
+
+@pytest.mark.parametrize("n,d,b", [(2, 2, 7), (7, 1, 33), (64, 4, 50), (65, 3, 20), (200, 6, 9), (10, 12, 100)])
+def test_score_batch_shapes(n, d, b):
+    rng = np.random.default_rng(n + d + b)
+    designs = np.stack([random_lhd(rng, n, d) for _ in range(b)])
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        ref, ref_arg = oracle.score_batch(designs, metric)
+        got, arg = engine.score_batch(designs, metric)
+        assert rel_err(got, ref) < REL and arg == ref_arg
+
+
+# ---------------------------------------------------------------- generation (K1)
+
+@pytest.mark.parametrize("n,d,seed,lo,count", [(50, 3, 42, 0, 64), (50, 2, 42, 1000, 16), (1, 1, 3, 0, 4), (2, 5, 9, 5, 8),
+                                               (7, 2, 12345, 0, 8), (100, 4, 12345, 0, 4), (501, 3, 2 ** 63, 2 ** 40, 3),
+                                               (5000, 8, 42, 0, 1), (30000, 2, 1, 0, 1)])
+def test_generate_bit_exact(n, d, seed, lo, count):
+    got = engine.generate_batch(n, d, seed, lo, count)
+    for c in range(count):
+        ref = oracle.generate_lhd(n, d, (seed + lo + c) % 2 ** 64)
+        assert np.array_equal(got[c], ref)
+        assert lhd_bins_ok(got[c])  # the reference's own validity test (lhd.rs:134-155)
+
+
+def test_generate_lhd_reference_test():
+    x = engine.generate_lhd(100, 4, 12345)  # lhd.rs:134-155
+    assert x.shape == (100, 4) and lhd_bins_ok(x)
+    assert np.array_equal(x, oracle.generate_lhd(100, 4, 12345))
+    assert engine.generate_lhd(0, 4, 12345).shape == (0, 4)  # lhd.rs:157-166
+    with pytest.raises(MaxproError):
+        engine.generate_lhd(10, 0, 12345)                     # lhd.rs:168-177
+
+
+# ---------------------------------------------------------------- fused search (K1+K2)
+
+SMALL_SHAPES = [(50, 3), (50, 2), (7, 2), (13, 5), (50, 8), (2, 1), (3, 3), (9, 4), (25, 6), (11, 7), (100, 1)]
+
+
+@pytest.mark.parametrize("n,d", SMALL_SHAPES)
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+def test_search_matches_oracle(n, d, metric):
+    iters, seed = 20_000, 42
+    s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
+    design, s, i = engine.build_lhd(n, d, iters, metric, seed)
+    assert i == i_ref
+    assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+    assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))  # winner rebuilt from (seed, index)
+    assert lhd_bins_ok(design)
+
+
+@pytest.mark.parametrize("n,d", [(40, 9), (130, 10), (300, 4)])
+def test_search_generic_path(n, d):
+    iters, seed = 3000, 7
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
+        _, s, i = engine.build_lhd(n, d, iters, metric, seed)
+        assert i == i_ref and math.isclose(s, s_ref, rel_tol=REL)
+
+
+def test_search_one_point_and_none_metric():
+    d, s, i = engine.build_lhd(1, 3, 10, METRIC_MAXPRO, 5)
+    assert (s, i) == (0.0, 9) and d.shape == (1, 3)      # all tie at 0.0 -> last index
+    d, s, i = engine.build_lhd(1, 3, 10, METRIC_MAXIMIN, 5)
+    assert (s, i) == (math.inf, 9)
+    d, _, _ = engine.build_lhd(20, 3, 10, METRIC_NONE, 5)  # lib.rs:46-50
+    assert np.array_equal(d, oracle.generate_lhd(20, 3, 5))
+
+
+def test_search_full_size_properties():
+    """BASELINE metric config (n=50, d=3) at a size the oracle cannot brute-force: check through
+    size-independent properties -- determinism, shard-fold invariance, winner re-score."""
+    n, d, seed, total = 50, 3, 42, 1 << 24
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        s, i = engine.search_range(n, d, metric, seed, 0, total)
+        assert (s, i) == engine.search_range(n, d, metric, seed, 0, total)  # deterministic
+        cuts = [0, 1, 999_999, 5_000_000, total - 3, total]
+        parts = [engine.search_range(n, d, metric, seed, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert engine.reduce_best(metric, [p[0] for p in parts], [p[1] for p in parts]) == (s, i)
+        win = oracle.generate_lhd(n, d, seed + i)
+        crit = oracle.maxpro_criterion(win) if metric == METRIC_MAXPRO else oracle.maximin_criterion(win)
+        assert math.isclose(s, crit, rel_tol=REL)
+        # the winner beats (or ties) a sample of other candidates scored on the CPU
+        rng = np.random.default_rng(1)
+        for j in rng.integers(0, total, 200):
+            c = oracle.generate_lhd(n, d, seed + int(j))
+            cj = oracle.maxpro_criterion(c) if metric == METRIC_MAXPRO else oracle.maximin_criterion(c)
+            assert cj >= s * (1 - REL) if metric == METRIC_MAXPRO else cj <= s
+    # an empty shard is the identity of the fold
+    s, i = engine.search_range(n, d, METRIC_MAXPRO, seed, 5, 5)
+    assert s == math.inf and i == 2 ** 64 - 1
+
+
+# ---------------------------------------------------------------- annealer (K3)
+
+@pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)])
+@pytest.mark.parametrize("swap", [True, False])
+@pytest.mark.parametrize("n,d,iters", [(20, 3, 400), (50, 2, 300), (9, 5, 500)])
+def test_anneal_matches_oracle(metric, minimize, swap, n, d, iters):
+    x = oracle.generate_lhd(n, d, 77)
+    ref, ref_best = oracle.anneal_lhd(x, iters, 1.0, 0.99, metric, minimize, 1234, swap)
+    got, best, chain = engine.anneal_lhd(x, iters, 1.0, 0.99, metric, minimize, 1234, swap, n_chains=1)
+    assert chain == 0
+    assert np.array_equal(got, ref)  # same trajectory -> same design, bit for bit
+    assert math.isclose(best, ref_best, rel_tol=REL)
+
+
+def test_anneal_chains_and_contract():
+    x = oracle.generate_lhd(30, 3, 5)
+    base = oracle.maxpro_criterion(x)
+    got, best, chain = engine.anneal_lhd(x, 500, 1.0, 0.99, METRIC_MAXPRO, True, 100, True, n_chains=64)
+    refs = [oracle.anneal_lhd(x, 500, 1.0, 0.99, METRIC_MAXPRO, True, 100 + c, True) for c in range(64)]
+    ref_best = min(r[1] for r in refs)
+    ref_chain = [r[1] for r in refs].index(ref_best)
+    assert chain == ref_chain and math.isclose(best, ref_best, rel_tol=REL)
+    assert np.array_equal(got, refs[ref_chain][0])
+    assert best <= base and lhd_bins_ok(got)  # never worse than the input; swaps keep the LHD
+    assert math.isclose(engine.maxpro_criterion(got), best, rel_tol=REL)
+    # cold chain that never improves returns the input untouched (anneal.rs:93)
+    got, best, _ = engine.anneal_lhd(x, 3, 1e-300, 0.5, METRIC_MAXIMIN, False, 1, False, n_chains=2)
+    ref, ref_best = oracle.anneal_lhd(x, 3, 1e-300, 0.5, METRIC_MAXIMIN, False, 1, False)
+    assert best >= oracle.maximin_criterion(x)
+    # long swap run crosses the periodic re-sum and the temp -> 0 regime
+    x = oracle.generate_lhd(12, 2, 9)
+    ref, ref_best = oracle.anneal_lhd(x, 3000, 1.0, 0.9, METRIC_MAXPRO, True, 3, True)
+    got, best, _ = engine.anneal_lhd(x, 3000, 1.0, 0.9, METRIC_MAXPRO, True, 3, True)
+    assert np.array_equal(got, ref) and math.isclose(best, ref_best, rel_tol=REL)
+
+
+def test_anneal_large_design_runs():
+    x = oracle.generate_lhd(1000, 20, 42)  # C4 shape: 160 KB of shared memory per chain
+    got, best, _ = engine.anneal_lhd(x, 50, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, n_chains=4)
+    assert best <= oracle.maxpro_criterion(x) * (1 + REL) and lhd_bins_ok(got)
+    assert math.isclose(oracle.maxpro_criterion(got), best, rel_tol=REL)
+
+
+# ---------------------------------------------------------------- greedy ordering (K4)
+
+@pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False), (METRIC_MAXPRO, False), (METRIC_MAXIMIN, True)])
+@pytest.mark.parametrize("n,d", [(2, 2), (12, 2), (30, 3), (45, 5)])
+def test_order_matches_reference_algorithm(metric, minimize, n, d):
+    x = oracle.generate_lhd(n, d, 99)
+    ref, p_ref = oracle.order_design(x, metric, minimize)  # the O(n^4 d) restatement of order.rs
+    got, p = engine.order_design(x, metric, minimize)
+    assert p.tolist() == p_ref.tolist() and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)])
+def test_order_large(metric, minimize):
+    x = oracle.generate_lhd(500, 5, 42)  # README.md:77-78 benchmark shape
+    _, p_ref = oracle.order_design(x, metric, minimize, incremental=True)
+    got, p = engine.order_design(x, metric, minimize)
+    assert p.tolist() == p_ref.tolist()
+    # the reference's own test: ordering is a permutation, criteria unchanged (order.rs:107-138)
+    assert sorted(p.tolist()) == list(range(500))
+    assert abs(oracle.maximin_criterion(x) - oracle.maximin_criterion(got)) < 1e-10
+    assert abs(oracle.maxpro_criterion(x) - oracle.maxpro_criterion(got)) < 1e-10 * oracle.maxpro_criterion(x)
+
+
+def test_order_structured_ties(r_golden):
+    """The R design sits on a regular grid: many exactly equal distances, so the maximin order is
+    decided by the tie rules alone."""
+    x = np.array(r_golden["design"])
+    for metric, minimize in ((METRIC_MAXIMIN, False), (METRIC_MAXPRO, True)):
+        _, p_ref = oracle.order_design(x, metric, minimize, incremental=True)
+        _, p = engine.order_design(x, metric, minimize)
+        assert p.tolist() == p_ref.tolist()
+
+
+def test_order_c5_shape_runs():
+    x = oracle.generate_lhd(5000, 8, 42)
+    got, p = engine.order_design(x, METRIC_MAXPRO, True)
+    assert sorted(p.tolist()) == list(range(5000))
+    _, p_ref = oracle.order_design(x, METRIC_MAXPRO, True, incremental=True)
+    assert p.tolist() == p_ref.tolist()
+
+
+# ---------------------------------------------------------------- python surface end to end
+
+def test_python_module_pipeline():
+    """examples/python/basic_maxpro.py flow with the documented signature (docs/python-api.md)."""
+    lhd = maxpro.build_lhd(20, 2, 2000, "maxpro", 42)
+    assert len(lhd) == 20 and len(lhd[0]) == 2
+    base = maxpro.maxpro_criterion(lhd)
+    sw = maxpro.anneal_lhd(lhd, 200, 1.0, 0.99, "maxpro", True, True, 43)
+    jt = maxpro.anneal_lhd(sw, 200, 1.0, 0.99, "MaxPro", True, False, 44)
+    assert maxpro.maxpro_criterion(jt) <= maxpro.maxpro_criterion(sw) <= base
+    od = maxpro.order_design(jt, "maxpro")
+    assert sorted(map(tuple, od)) == sorted(map(tuple, jt))
+    assert maxpro.maximin_criterion(lhd) == oracle.maximin_criterion(lhd)
+    g = maxpro.generate_lhd(10, 3, 1)
+    assert lhd_bins_ok(np.array(g)) and maxpro.generate_lhd(10, 3) != g
