@@ -170,13 +170,28 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     }
     init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
     mp::count_launch();
+    int cyc_cands = 0;
+    if (mp::search_cyclic_supported(n, d, &cyc_cands)) {
+        mp::SearchLaunch L{};
+        L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
+        L.block_best = w.block_best; L.done_counter = w.counter; L.result = result;
+        L.group = 2; L.threads = 2 * cyc_cands;
+        unsigned long long total = hi - lo;
+        unsigned long long want = (total + cyc_cands - 1) / cyc_cands;
+        L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
+        L.stream = stream;
+        CUDA_TRY(mp::launch_search_cyclic(L));
+        mp::count_launch();
+        return MAXPRO_OK;
+    }
     if (mp::search_small_supported(n, d)) {
         mp::SearchLaunch L{};
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
         L.block_best = w.block_best; L.done_counter = w.counter; L.result = result;
-        L.threads = mp::search_small_pick_threads(n, d);
+        mp::search_small_pick_config(n, d, &L.group, &L.threads);
         unsigned long long total = hi - lo;
-        unsigned long long want = (total + L.threads - 1) / L.threads;
+        unsigned long long per_cta = (unsigned long long)(L.threads / L.group);
+        unsigned long long want = (total + per_cta - 1) / per_cta;
         L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
         L.stream = stream;
         CUDA_TRY(mp::launch_search_small(L));
@@ -562,12 +577,16 @@ int maxpro_fp64_peak_probe(int repeats, double* tflops, double* kernel_ms) {
     if (int rc = ensure_device(&sms)) return rc;
     if (repeats < 1) repeats = 1;
     DevBuf sink;
-    CUDA_TRY(sink.alloc(sizeof(double)));
+    CUDA_TRY(sink.alloc(17 * sizeof(double)));
     cudaStream_t st = cudaStreamPerThread;
+    double vals[17];
+    vals[0] = 0.0;
+    for (int i = 0; i < 16; ++i) vals[i + 1] = 0.999999 + 1e-7 * i;
+    CUDA_TRY(cudaMemcpyAsync(sink.p, vals, sizeof(vals), cudaMemcpyHostToDevice, st));
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    const int threads = 256, grid = sms * 8, iters = 1 << 16;
+    const int threads = 256, grid = sms * 4, iters = 1 << 16;
     double best_ms = 1e30;
     for (int r = 0; r < repeats + 1; ++r) {  // first launch is warm-up
         cudaEventRecord(e0, st);

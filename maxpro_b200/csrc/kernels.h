@@ -21,14 +21,16 @@ struct SearchLaunch {
     unsigned int* done_counter;  // zero before first use; the kernel re-arms it
     BestRec* result;
     int grid, threads;
+    int group;  // lanes per candidate (1 or 2)
     cudaStream_t stream;
 };
 bool search_small_supported(unsigned long long n, unsigned long long d);
-int search_small_pick_threads(unsigned long long n, unsigned long long d);
+void search_small_pick_config(unsigned long long n, unsigned long long d, int* group, int* threads);
 cudaError_t launch_search_small(const SearchLaunch& L);
 
-bool search_cta_supported(unsigned long long n, unsigned long long d);
-cudaError_t launch_search_cta(const SearchLaunch& L);
+// shape-specialised cyclic schedule (search_cyclic.cu); *cands = candidates per CTA
+bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* cands);
+cudaError_t launch_search_cyclic(const SearchLaunch& L);
 
 // ---- K1 alone: materialise designs (winner regeneration, generate_lhd) -------
 // out: count designs, row-major n*d each; design c uses stream seed + lo + c.

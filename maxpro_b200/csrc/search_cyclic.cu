@@ -1,0 +1,271 @@
+// K1+K2 fused, shape-specialised variant of search_small.cu for the headline shapes
+// (n = 50, d = 2 or 3): same thread-group-per-candidate layout, but the pair schedule is
+// CYCLIC and every loop bound and shared-memory stride is a compile-time constant.
+//
+// Replaces the same reference code as search_small.cu: generate_lhd (src/lhd.rs:97-132) ->
+// criterion (src/maxpro_utils.rs:28-83 / src/maximin_utils.rs:54-67) -> fold (src/lib.rs:76-98).
+//
+// Why a second kernel.  ncu on the triangular schedule of search_small.cu (profiles/) showed
+// one warp alone reaching only ~45% of the FP64 pipe: 18% of the pairs live in remainder
+// loops, tile prologues and the in-tile triangle, and those took 42% of the time.  The
+// cyclic schedule has ONE block shape and nothing else:
+//     pair {i, (i+s) mod n},  s = 1 .. (n-1)/2,  every row i          (+ the n/2 diameters)
+// The two lanes of a candidate split the s range in halves (s = 1..12 and 13..24 at n = 50),
+// walk the rows in register tiles of R = 5, and for S = 4 consecutive shifts load the
+// R+S-1 = 8 partner rows once: 20 pairs per block, 24 LDS.64, fully unrolled, no triangle,
+// no remainder, identical trip counts in both lanes (no divergence).  Row wrap-around costs
+// one add and one unsigned min per loaded row.  With N and C constant every shared-memory
+// address is base + immediate.
+#include "common.cuh"
+#include "philox.cuh"
+#include "reduce.cuh"
+#include "kernels.h"
+
+#include <cstdlib>
+
+namespace mp {
+
+struct CyclicParams {
+    int ring;  // warps per sub-partition that take turns on the FP64 pipe (0 = no turn-taking)
+    unsigned long long seed, lo, hi;
+    double c1, c0;
+    double n_pairs, inv_d;
+    BestRec* block_best;
+    unsigned int* done_counter;
+    BestRec* result;
+};
+
+template <int D>
+__device__ __forceinline__ double cyc_maxpro_term(const double (&a)[D], const double (&b)[D]) {
+    double q = a[0] - b[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) q *= (a[k] - b[k]);
+    return fma(q, q, kEps);
+}
+
+template <int D>
+__device__ __forceinline__ double cyc_sqdist_term(const double (&a)[D], const double (&b)[D]) {
+    double df = __dsub_rn(a[0], b[0]);
+    double s = __dmul_rn(df, df);
+#pragma unroll
+    for (int k = 1; k < D; ++k) {
+        df = __dsub_rn(a[k], b[k]);
+        s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    return s;
+}
+
+// Byte offsets inside one candidate's slice: element (k, i) at (k*N + i) * C * 8.
+template <int N, int D, int C>
+struct Layout {
+    static constexpr unsigned kRowBytes = C * 8u;        // i -> i+1
+    static constexpr unsigned kDimBytes = N * C * 8u;    // k -> k+1
+};
+
+template <int N, int D, int C>
+__device__ __forceinline__ void load_row_at(double (&dst)[D], const unsigned char* cand, unsigned row_off) {
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        dst[k] = *reinterpret_cast<const double*>(cand + row_off + k * Layout<N, D, C>::kDimBytes);
+}
+
+// One column of generate_lhd (inside-out Fisher-Yates), strides as immediates.
+template <int N, int D, int C>
+__device__ __forceinline__ void cyc_generate_column(unsigned char* col, uint32_t k, uint32_t s_lo, uint32_t s_hi,
+                                                    double c1, double c0) {
+    constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
+#pragma unroll 2
+    for (int i = 0; i < N; i += 2) {
+        Philox4 w = philox4x32_10((uint32_t)(i >> 1), k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+        {
+            uint32_t j = mulhi_bound(w.y, (uint32_t)i + 1u);
+            unsigned long long m = ((unsigned long long)(uint32_t)i << 32) | w.x;
+            double v = fma((double)m, c1, c0);
+            *reinterpret_cast<double*>(col + i * RB) = *reinterpret_cast<double*>(col + j * RB);
+            *reinterpret_cast<double*>(col + j * RB) = v;
+        }
+        if (i + 1 < N) {
+            uint32_t j = mulhi_bound(w.w, (uint32_t)i + 2u);
+            unsigned long long m = ((unsigned long long)(uint32_t)(i + 1) << 32) | w.z;
+            double v = fma((double)m, c1, c0);
+            *reinterpret_cast<double*>(col + (i + 1) * RB) = *reinterpret_cast<double*>(col + j * RB);
+            *reinterpret_cast<double*>(col + j * RB) = v;
+        }
+    }
+}
+
+template <int N, int D, int C, bool MAXPRO>
+__device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
+    constexpr int R = 5, S = 4, G = 2;
+    constexpr int kHalf = (N - 1) / 2;       // shifts 1..kHalf pair every row once
+    constexpr int kPerLane = kHalf / G;      // shifts per lane
+    constexpr int kBlocks = kPerLane / S;    // blocks of S shifts per tile
+    static_assert(N % R == 0, "row tiles must divide n");
+    static_assert(kHalf % (G * S) == 0, "shift range must split into whole blocks");
+    static_assert(kPerLane <= 16, "one flush per tile keeps every chain within 16 terms");
+    constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
+    constexpr unsigned NB = N * RB;          // wrap modulus in bytes
+
+    RecipChain ch[R];
+    double mins[R];
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { ch[r].reset(); mins[r] = CUDART_INF; }
+
+    const unsigned s_first = 1u + (unsigned)g * kPerLane;  // this lane's first shift
+#pragma unroll 1
+    for (int t = 0; t < N / R; ++t) {
+        const unsigned i0_off = (unsigned)t * R * RB;
+        double xi[R][D];
+#pragma unroll
+        for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xi[r], cand, i0_off + r * RB);
+#pragma unroll
+        for (int b = 0; b < kBlocks; ++b) {
+            // partner rows (i0 + s0 + u) mod N, u = 0 .. R+S-2
+            const unsigned base = i0_off + (s_first + (unsigned)b * S) * RB;
+            double xj[R + S - 1][D];
+#pragma unroll
+            for (int u = 0; u < R + S - 1; ++u) {
+                unsigned off = base + u * RB;
+                off = min(off, off - NB);  // off >= NB ? off - NB : off   (unsigned wrap)
+                load_row_at<N, D, C>(xj[u], cand, off);
+            }
+#pragma unroll
+            for (int c = 0; c < S; ++c)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (MAXPRO) ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c]));
+                    else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xj[r + c]));
+                }
+        }
+        // diameters {i, i + N/2} (even N): rows of the lower half only, tiles dealt to the lanes
+        if (N % 2 == 0 && t < N / (2 * R) && (t & 1) == g) {
+            double xd[R][D];
+#pragma unroll
+            for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xd[r], cand, i0_off + (N / 2 + r) * RB);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (MAXPRO) ch[r].push(cyc_maxpro_term<D>(xi[r], xd[r]));
+                else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xd[r]));
+            }
+        }
+        if (MAXPRO) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc += ch[r].flush();  // <= kPerLane + 1 terms per chain
+        }
+    }
+    if (MAXPRO) return acc;
+    double m = mins[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) m = fmin(m, mins[r]);
+    return m;
+}
+
+// Named-barrier token between two warps (64 threads): bar.arrive hands it on, bar.sync takes it.
+__device__ __forceinline__ void cyc_token_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void cyc_token_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+// Turn-taking on the FP64 pipe.  Each warp alternates an integer-only, latency-bound phase
+// (Philox + Fisher-Yates, ~17k cycles) and an FP64-bound phase (the pair loop, ~10k pipe
+// cycles).  The warps of a sub-partition (warp id mod 4) share the pipe fairly, so left alone
+// they finish scoring together and then all generate together while the pipe idles (measured:
+// 60% pipe utilisation).  With p.ring = 2 the first two warps of every sub-partition pass a
+// token (strict alternation: one of them is always scoring) and the third runs free, which
+// keeps one or two warps on the pipe at all times.
+template <int N, int D, int C, bool MAXPRO>
+__global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int G = 2, kPerWarp = 16;
+    static_assert(N % 2 == 0 ? (N / 2) % 5 == 0 : true, "diameter tiles");
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = wid * kPerWarp + (lane & 15), g = lane >> 4;
+    const unsigned int group_mask = (1u << (lane & 15)) | (1u << ((lane & 15) + 16));
+    unsigned char* cand = smem_raw + (size_t)c * 8;
+    BestRec* warp_best = reinterpret_cast<BestRec*>(smem_raw + (size_t)N * D * C * sizeof(double));
+
+    const unsigned long long gcid = (unsigned long long)blockIdx.x * C + c;
+    const unsigned long long gstep = (unsigned long long)gridDim.x * C;
+    const unsigned long long total = p.hi - p.lo;
+    const unsigned long long rounds = (total + gstep - 1) / gstep;
+
+    double best = MAXPRO ? CUDART_INF : -CUDART_INF;
+    unsigned long long best_idx = kNoIndex;
+
+    // token ring: barrier 1 + smsp*ring + q is the token INTO ring position q
+    const int ring = p.ring, smsp = wid & 3, q = wid >> 2;
+    const bool in_ring = q < ring;
+    const int tok_in = 1 + smsp * ring + q, tok_out = 1 + smsp * ring + (q + 1 == ring ? 0 : q + 1);
+    if (in_ring && q == ring - 1) cyc_token_pass(tok_out);  // position 0 scores first
+
+    for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
+        const unsigned long long off = gcid + rnd * gstep;
+        const bool active = off < total;
+        const unsigned long long idx = p.lo + off;
+        const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
+        const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
+        if (active) {
+#pragma unroll 1
+            for (int k = g; k < D; k += G)
+                cyc_generate_column<N, D, C>(cand + (size_t)k * Layout<N, D, C>::kDimBytes, (uint32_t)k, s_lo, s_hi, p.c1, p.c0);
+        }
+        __syncwarp(group_mask);
+        if (in_ring) cyc_token_wait(tok_in);
+        double s = 0.0;
+        if (active) s = cyc_score<N, D, C, MAXPRO>(cand, g);
+        if (in_ring) cyc_token_pass(tok_out);
+        const double other = __shfl_xor_sync(group_mask, s, 16);
+        if (MAXPRO) s = (g == 0) ? s + other : other + s;  // same bits in both lanes
+        else s = fmin(s, other);
+        __syncwarp(group_mask);
+        if (!MAXPRO) s = sqrt(s);
+        if (active && (MAXPRO ? (s <= best) : (s >= best))) { best = s; best_idx = idx; }
+    }
+    if (in_ring && q == 0) cyc_token_wait(tok_in);  // take the last token so no arrival is left pending
+    if (MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
+    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+}
+
+template <int N, int D, int C>
+static cudaError_t launch_cyclic_nd(const SearchLaunch& L, const CyclicParams& p) {
+    constexpr size_t smem = (size_t)N * D * C * sizeof(double) + 32 * sizeof(BestRec);
+    static_assert(smem <= kSmemBudget, "candidates per CTA do not fit shared memory");
+    cudaError_t e;
+    if (L.metric == 0) {
+        e = cudaFuncSetAttribute(search_cyclic_kernel<N, D, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        search_cyclic_kernel<N, D, C, true><<<L.grid, 2 * C, smem, L.stream>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(search_cyclic_kernel<N, D, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        search_cyclic_kernel<N, D, C, false><<<L.grid, 2 * C, smem, L.stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// Shapes with a specialised instantiation; *cands = candidates per CTA.
+bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* cands) {
+    if (const char* e = getenv("MAXPRO_NO_CYCLIC")) if (atoi(e) != 0) return false;
+    int c = 0;
+    if (n == 50 && d == 3) c = 192;
+    else if (n == 50 && d == 2) c = 256;
+    if (cands) *cands = c;
+    return c != 0;
+}
+
+cudaError_t launch_search_cyclic(const SearchLaunch& L) {
+    CyclicParams p;
+    p.ring = 2;
+    if (const char* e = getenv("MAXPRO_CYCLIC_RING")) { int v = atoi(e); if (v == 0 || v == 2 || v == 3) p.ring = v; }
+    if (p.ring > (L.threads / 32) / 4) p.ring = 0;
+    p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
+    p.c1 = ldexp(1.0 / (double)L.n, -32);
+    p.c0 = 0.5 * p.c1;
+    p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
+    p.inv_d = 1.0 / (double)L.d;
+    p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;
+    if (L.n == 50 && L.d == 3) return launch_cyclic_nd<50, 3, 192>(L, p);
+    if (L.n == 50 && L.d == 2) return launch_cyclic_nd<50, 2, 256>(L, p);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace mp

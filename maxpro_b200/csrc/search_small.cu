@@ -28,6 +28,8 @@
 #include "reduce.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace mp {
 
 struct SearchParams {
@@ -86,13 +88,20 @@ __device__ __forceinline__ void generate_column(double* col, int stride, int n, 
 }
 
 constexpr int kMaxChain = 16;  // terms per RecipChain before a flush (den >= 1e-192)
-constexpr int kJUnroll = 4;    // j iterations per unrolled body
 
-// Score the thread's design.  MAXPRO: returns S = sum_{i<j} 1/(prod diff^2 + eps)
-// (src/maxpro_utils.rs:38-58).  !MAXPRO: returns min_{i<j} squared distance.
-template <int D, int R, bool MAXPRO>
-__device__ __forceinline__ double score_thread_design(const double* xs, int stride, int n) {
-    const int kstride = n * stride;  // distance between dimensions
+// Score one design held in shared memory by a group of G lanes (G = 1 or 2).
+// MAXPRO: returns this lane's share of S = sum_{i<j} 1/(prod diff^2 + eps)
+// (src/maxpro_utils.rs:38-58); !MAXPRO: this lane's min_{i<j} squared distance.
+// Work split (uniform control flow, so lanes never diverge):
+//   phase A  every lane loads the same R-row tile into registers and the rows after
+//            the tile are dealt round-robin to the G lanes (R pairs per loaded row);
+//   phase B  the R(R-1)/2 pairs inside a tile are taken tile-by-tile, tiles dealt
+//            round-robin to the lanes;
+//   phase C  pairs among the < R rows left over when R does not divide n.
+template <int D, int R, int G, bool MAXPRO>
+__device__ __forceinline__ double score_group_design(const double* xs, int stride, int n, int g) {
+    constexpr int U = (D >= 5) ? 2 : ((R == 5) ? 5 : 4);  // rows per unrolled body (register budget)
+    const int kstride = n * stride;      // distance between dimensions
     RecipChain ch[R];
     double mins[R];
     double acc = 0.0;
@@ -105,16 +114,52 @@ __device__ __forceinline__ double score_thread_design(const double* xs, int stri
         for (int r = 0; r < R; ++r) acc += ch[r].flush();
         pushed = 0;
     };
+    auto load_row = [&](double (&dst)[D], int row) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) dst[k] = xs[k * kstride + row * stride];
+    };
 
-    int i0 = 0;
-    for (; i0 + R <= n; i0 += R) {
+    const int full = (n / R) * R;
+    // ---- phase A
+    for (int i0 = 0; i0 < full; i0 += R) {
         double xi[R][D];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r) load_row(xi[r], i0 + r);
+        int jb = i0 + R;
+        for (; jb + G * U <= n; jb += G * U) {
+            if (MAXPRO && pushed + U > kMaxChain) flush_all();
+            double xj[U][D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) xi[r][k] = xs[k * kstride + (i0 + r) * stride];
-
-        // pairs inside the row tile, spread over the chains
+            for (int u = 0; u < U; ++u) load_row(xj[u], jb + g + G * u);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (MAXPRO) ch[r].push(maxpro_term<D>(xi[r], xj[u]));
+                    else mins[r] = fmin(mins[r], sqdist_term<D>(xi[r], xj[u]));
+                }
+            if (MAXPRO) pushed += U;
+        }
+        for (; jb < n; jb += G) {
+            if (MAXPRO && pushed + 1 > kMaxChain) flush_all();
+            const int j = jb + g;
+            if (G == 1 || j < n) {
+                double xj[D];
+                load_row(xj, j);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (MAXPRO) ch[r].push(maxpro_term<D>(xi[r], xj));
+                    else mins[r] = fmin(mins[r], sqdist_term<D>(xi[r], xj));
+                }
+            }
+            if (MAXPRO) pushed += 1;
+        }
+    }
+    // ---- phase B
+    for (int i0 = g * R; i0 < full; i0 += G * R) {
+        double xi[R][D];
+#pragma unroll
+        for (int r = 0; r < R; ++r) load_row(xi[r], i0 + r);
         if (MAXPRO && pushed + R > kMaxChain) flush_all();
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -124,50 +169,21 @@ __device__ __forceinline__ double score_thread_design(const double* xs, int stri
                 else mins[(r + r2) % R] = fmin(mins[(r + r2) % R], sqdist_term<D>(xi[r], xi[r2]));
             }
         if (MAXPRO) pushed += R / 2 + 1;
-
-        // the tile against every later row: R pairs per loaded row
-        int j = i0 + R;
-        for (; j + kJUnroll <= n; j += kJUnroll) {
-            if (MAXPRO && pushed + kJUnroll > kMaxChain) flush_all();
-            double xj[kJUnroll][D];
-#pragma unroll
-            for (int u = 0; u < kJUnroll; ++u)
-#pragma unroll
-                for (int k = 0; k < D; ++k) xj[u][k] = xs[k * kstride + (j + u) * stride];
-#pragma unroll
-            for (int u = 0; u < kJUnroll; ++u)
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (MAXPRO) ch[r].push(maxpro_term<D>(xi[r], xj[u]));
-                    else mins[r] = fmin(mins[r], sqdist_term<D>(xi[r], xj[u]));
-                }
-            if (MAXPRO) pushed += kJUnroll;
-        }
-        for (; j < n; ++j) {
+    }
+    // ---- phase C
+    int turn = 0;
+    for (int i = full; i < n; ++i) {
+        double xi[D];
+        load_row(xi, i);
+        for (int j = i + 1; j < n; ++j, ++turn) {
             if (MAXPRO && pushed + 1 > kMaxChain) flush_all();
-            double xj[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) xj[k] = xs[k * kstride + j * stride];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (MAXPRO) ch[r].push(maxpro_term<D>(xi[r], xj));
-                else mins[r] = fmin(mins[r], sqdist_term<D>(xi[r], xj));
+            if (G == 1 || (turn % G) == g) {
+                double xj[D];
+                load_row(xj, j);
+                if (MAXPRO) ch[0].push(maxpro_term<D>(xi, xj));
+                else mins[0] = fmin(mins[0], sqdist_term<D>(xi, xj));
             }
             if (MAXPRO) pushed += 1;
-        }
-    }
-    // rows left over when R does not divide n
-    for (int i = i0; i < n; ++i) {
-        double xi[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) xi[k] = xs[k * kstride + i * stride];
-        for (int j = i + 1; j < n; ++j) {
-            if (MAXPRO && pushed + 1 > kMaxChain) flush_all();
-            double xj[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) xj[k] = xs[k * kstride + j * stride];
-            if (MAXPRO) { ch[0].push(maxpro_term<D>(xi, xj)); pushed += 1; }
-            else mins[0] = fmin(mins[0], sqdist_term<D>(xi, xj));
         }
     }
     if (MAXPRO) {
@@ -180,71 +196,139 @@ __device__ __forceinline__ double score_thread_design(const double* xs, int stri
     return m;
 }
 
-template <int D, int R, bool MAXPRO>
-__global__ void __launch_bounds__(256, 1) search_small_kernel(SearchParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x;
-    const int n = p.n;
-    double* xs = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
-    BestRec* warp_best = reinterpret_cast<BestRec*>(smem_raw + (size_t)n * D * T * sizeof(double));
+// Named-barrier helpers: a producer/consumer token between two warps (64 threads).
+__device__ __forceinline__ void token_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-    const unsigned long long gtid = (unsigned long long)blockIdx.x * T + threadIdx.x;
-    const unsigned long long gsize = (unsigned long long)gridDim.x * T;
+// G lanes per candidate: lane g generates columns g, g+G, ... and scores its share of
+// the pairs.  G = 2 doubles the resident warps for the same shared memory (12 warps per
+// SM at n=50, d=3).
+//
+// LOCK: the warps of one SM sub-partition (warp id mod 4) take turns on the FP64 pipe.
+// Every warp alternates an integer-only, latency-bound phase (Philox + Fisher-Yates) and an
+// FP64-bound phase (the pair loop).  Left alone, the warps of a sub-partition share the pipe
+// fairly, therefore finish scoring together, therefore all generate together while the FP64
+// pipe idles -- measured 56% pipe utilisation.  Passing a token round the 2-3 warps of each
+// sub-partition (named barriers, bar.arrive / bar.sync on 64 threads) makes the scoring phases
+// strictly consecutive, so one warp's generation always overlaps another warp's scoring.
+template <int D, int R, int G, bool MAXPRO, bool LOCK>
+__global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = blockDim.x / G;  // candidates resident in this CTA
+    const int n = p.n;
+    // Lane layout inside a warp: lanes [0, 32/G) are lane-role 0 of 32/G consecutive
+    // candidates, lanes [32/G, 2*32/G) lane-role 1 of the same candidates.  Each half-warp
+    // (the unit a 64-bit shared-memory access is split into) then touches 16 different
+    // candidates = 16 different bank pairs: no conflicts for any per-lane element index.
+    constexpr int kPerWarp = 32 / G;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = wid * kPerWarp + (lane % kPerWarp), g = lane / kPerWarp;
+    const unsigned int group_mask = (G == 1) ? (1u << lane) : ((1u << (lane % kPerWarp)) | (1u << (lane % kPerWarp + kPerWarp)));
+    double* xs = reinterpret_cast<double*>(smem_raw) + c;
+    BestRec* warp_best = reinterpret_cast<BestRec*>(smem_raw + (size_t)n * D * C * sizeof(double));
+
+    const unsigned long long gcid = (unsigned long long)blockIdx.x * C + c;
+    const unsigned long long gstep = (unsigned long long)gridDim.x * C;
+    const unsigned long long total = p.hi - p.lo;
+    const unsigned long long rounds = (total + gstep - 1) / gstep;  // same trip count for every thread
+
+    // token ring of the warps sharing this warp's sub-partition: barrier 1 + smsp*ring + q is
+    // the token INTO ring position q
+    const int ring = (blockDim.x >> 5) >> 2, smsp = wid & 3, q = wid >> 2;
+    const int tok_in = 1 + smsp * ring + q, tok_out = 1 + smsp * ring + (q + 1 == ring ? 0 : q + 1);
+    if (LOCK && q == ring - 1) token_pass(tok_out);  // position 0 scores first
 
     // MAXPRO minimises S (psi is monotone in S); maximin maximises the distance.
     double best = MAXPRO ? CUDART_INF : -CUDART_INF;
     unsigned long long best_idx = kNoIndex;
 
-    for (unsigned long long idx = p.lo + gtid; idx < p.hi; idx += gsize) {
+    for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
+        const unsigned long long off = gcid + rnd * gstep;
+        const bool active = off < total;
+        const unsigned long long idx = p.lo + off;
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
+        if (active) {
 #pragma unroll 1
-        for (int k = 0; k < D; ++k)
-            generate_column(xs + (size_t)k * n * T, T, n, (uint32_t)k, s_lo, s_hi, p.c1, p.c0);
-        double s = score_thread_design<D, R, MAXPRO>(xs, T, n);
+            for (int k = g; k < D; k += G)
+                generate_column(xs + (size_t)k * n * C, C, n, (uint32_t)k, s_lo, s_hi, p.c1, p.c0);
+        }
+        if (G > 1) __syncwarp(group_mask);
+        if (LOCK) token_wait(tok_in);
+        double s = 0.0;
+        if (active) s = score_group_design<D, R, G, MAXPRO>(xs, C, n, g);
+        if (LOCK) token_pass(tok_out);
+        if (G > 1) {
+            // fixed order (even lane + odd lane) so both lanes hold the same bits
+            const double other = __shfl_xor_sync(group_mask, s, kPerWarp);
+            if (MAXPRO) s = (g == 0) ? s + other : other + s;
+            else s = fmin(s, other);
+            __syncwarp(group_mask);  // partner is done reading before the design is overwritten
+        }
         if (!MAXPRO) s = sqrt(s);  // reference compares distances, not squares (ties)
         // idx grows along the loop, so ">= / <=" keeps the later index on ties
-        if (MAXPRO ? (s <= best) : (s >= best)) { best = s; best_idx = idx; }
+        if (active && (MAXPRO ? (s <= best) : (s >= best))) { best = s; best_idx = idx; }
     }
+    if (LOCK && q == 0) token_wait(tok_in);  // consume the last token so no arrival is left pending
     if (MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
     block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
 // ---- host side -------------------------------------------------------------
 
-template <int D, int R>
-static cudaError_t launch_dr(const SearchLaunch& L, const SearchParams& p) {
-    size_t smem = (size_t)p.n * D * L.threads * sizeof(double) + 32 * sizeof(BestRec);
-    cudaError_t e;
-    if (L.metric == 0) {
-        e = cudaFuncSetAttribute(search_small_kernel<D, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        search_small_kernel<D, R, true><<<L.grid, L.threads, smem, L.stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(search_small_kernel<D, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        search_small_kernel<D, R, false><<<L.grid, L.threads, smem, L.stream>>>(p);
-    }
+template <int D, int R, int G, bool MAXPRO, bool LOCK>
+static cudaError_t launch_one(const SearchLaunch& L, const SearchParams& p, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(search_small_kernel<D, R, G, MAXPRO, LOCK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    search_small_kernel<D, R, G, MAXPRO, LOCK><<<L.grid, L.threads, smem, L.stream>>>(p);
     return cudaGetLastError();
 }
 
+template <int D, int R, int G>
+static cudaError_t launch_drg(const SearchLaunch& L, const SearchParams& p) {
+    size_t smem = (size_t)p.n * D * (L.threads / G) * sizeof(double) + 32 * sizeof(BestRec);
+    // the token ring needs whole rings: warps a multiple of 4, 2 or 3 warps per sub-partition
+    const int warps = L.threads / 32;
+    bool lock = (L.threads % 128 == 0) && (warps / 4 == 2 || warps / 4 == 3);
+    if (const char* e = getenv("MAXPRO_SMALL_LOCK")) lock = lock && atoi(e) != 0;
+    if (L.metric == 0) return lock ? launch_one<D, R, G, true, true>(L, p, smem) : launch_one<D, R, G, true, false>(L, p, smem);
+    return lock ? launch_one<D, R, G, false, true>(L, p, smem) : launch_one<D, R, G, false, false>(L, p, smem);
+}
+
+// Register tile height R by dimension count: the tile (R*D doubles) plus the unrolled rows
+// must stay inside the 128-register budget of a 512-thread CTA.
 template <int D>
 static cudaError_t launch_d(const SearchLaunch& L, const SearchParams& p) {
-    if (p.n % 5 == 0 && D <= 4) return launch_dr<D, 5>(L, p);
-    return launch_dr<D, 4>(L, p);
+    if constexpr (D <= 4) {
+        const bool r5 = (p.n % 5 == 0);
+        if (L.group == 2) return r5 ? launch_drg<D, 5, 2>(L, p) : launch_drg<D, 4, 2>(L, p);
+        return r5 ? launch_drg<D, 5, 1>(L, p) : launch_drg<D, 4, 1>(L, p);
+    } else if constexpr (D <= 6) {
+        return L.group == 2 ? launch_drg<D, 4, 2>(L, p) : launch_drg<D, 4, 1>(L, p);
+    } else {
+        return L.group == 2 ? launch_drg<D, 3, 2>(L, p) : launch_drg<D, 3, 1>(L, p);
+    }
 }
 
 bool search_small_supported(unsigned long long n, unsigned long long d) {
     return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * 64 + 32 * sizeof(BestRec) <= kSmemBudget;
 }
 
-int search_small_pick_threads(unsigned long long n, unsigned long long d) {
-    // Largest warp multiple (<= 256) whose designs fit in one SM's shared memory.
-    size_t per_thread = (size_t)n * d * sizeof(double);
-    size_t t = (kSmemBudget - 32 * sizeof(BestRec)) / per_thread;
-    t = (t / 32) * 32;
-    if (t > 256) t = 256;
-    return (int)t;
+// Lanes per candidate and CTA size.  Two lanes per candidate whenever there are at least two
+// columns to generate; as many candidates as fit one SM's shared memory (multiple of 16 so
+// every lane of a half-warp hits its own bank pair), at most 512 threads.
+void search_small_pick_config(unsigned long long n, unsigned long long d, int* group, int* threads) {
+    int G = d >= 2 ? 2 : 1;
+    if (const char* e = getenv("MAXPRO_SMALL_GROUP")) { int v = atoi(e); if (v == 1 || v == 2) G = v; }
+    size_t per = (size_t)n * d * sizeof(double);
+    size_t c = (kSmemBudget - 32 * sizeof(BestRec)) / per;
+    c = (c / 16) * 16;
+    if (c * G > 512) c = 512 / G;
+    if (const char* e = getenv("MAXPRO_SMALL_CANDS")) { size_t v = (size_t)atoi(e); if (v >= 16 && v <= c && v % 16 == 0) c = v; }
+    if (G == 1) c = (c / 32) * 32;
+    *group = G;
+    *threads = (int)(c * G);
 }
 
 cudaError_t launch_search_small(const SearchLaunch& L) {
