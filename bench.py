@@ -68,15 +68,18 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, lines):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
-        for ln in self.lines:
+        for ln in lines:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -221,22 +224,33 @@ def main():
     peak_tflops, _ = engine.fp64_peak_probe(5)
 
     # ---------------- value: device-resident, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~1 s to come up: start it before the warm-up steps
     for s in range(args.warmup):
         device_step(s)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.lines.clear()  # keep only samples taken inside the timed region
     launches0 = _lib.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record(stream)
     for s in range(args.steps):
         device_step(args.warmup + s)
+        marks[s].record(stream)
     e1.record(stream)
     barrier()
+    if rank == 0:
+        prev, per = e0, []
+        for m in marks:
+            per.append(prev.elapsed_time(m)); prev = m
+        print("device per-step ms: " + " ".join(f"{v:.1f}" for v in per), file=sys.stderr)
     launches = _lib.kernel_launch_count() - launches0
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    timed_lines = list(sampler.lines)
+    # stop polling before the host-facing leg: NVML queries and cudaMalloc/cudaFree contend for
+    # driver locks, which showed up as 100+ ms stalls in e2e steps
+    sampler.stop()
     value = per_gpu * world * args.steps / (dev_ms * 1e-3)
     per_gpu_rate = per_gpu * args.steps / (dev_ms * 1e-3)
     kernel_ms = dev_ms / args.steps  # one criterion-kernel launch per step (+ a 1-thread counter reset)
@@ -260,11 +274,20 @@ def main():
         host_step(base + s)
     barrier()
     t0 = time.perf_counter()
+    step_ms = []
     for s in range(args.steps):
+        t1 = time.perf_counter()
         host_step(base + 2 + s)
+        step_ms.append((time.perf_counter() - t1) * 1e3)
     barrier()
+    if rank == 0:
+        print("e2e per-step ms: " + " ".join(f"{v:.1f}" for v in step_ms), file=sys.stderr)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = per_gpu * world * args.steps / e2e_s
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(timed_lines)  # clocks seen during the device-timed region
 
     line = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -280,7 +303,7 @@ def main():
                      "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": None,
                      "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
                                     f"nominal 148 SM x 64 lanes x 2 x 1.965 GHz = {NOMINAL_FP64_TFLOPS:.1f}",
-                     "flops_per_candidate": FLOPS_PER_CANDIDATE, "kernel": "search_small_kernel<3,5,true>",
+                     "flops_per_candidate": FLOPS_PER_CANDIDATE, "kernel": "search_cyclic_kernel<50,3,192,true>",
                      "kernel_ms_per_launch": kernel_ms, "candidates_per_launch": per_gpu,
                      "note": "algorithmic flops; the kernel issues ~8.4 FP64-pipe instructions per pair for 12 "
                              "algorithmic flops, see profiles/ for pipe utilisation"},

@@ -43,10 +43,51 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
     } while (0)
 
+// Device scratch with a small per-thread cache: the host-facing calls are made in tight
+// loops (bench.py's e2e leg, the CLI pipeline) and cudaMalloc/cudaFree take driver-wide
+// locks, so blocks up to 64 MB are kept for the next call on the same thread and device.
+// Every call synchronises its stream before returning, so a cached block is never in use.
+struct CachedBlock { void* p; size_t bytes; int device; };
+struct BlockCache {
+    std::vector<CachedBlock> free_blocks;
+    size_t cached_bytes = 0;
+    ~BlockCache() { for (auto& b : free_blocks) cudaFree(b.p); }
+};
+thread_local BlockCache g_cache;
+constexpr size_t kCacheBlockMax = 64ull << 20, kCacheTotalMax = 512ull << 20;
+
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    size_t bytes = 0;
+    int device = 0;
+    ~DevBuf() {
+        if (!p) return;
+        if (bytes <= kCacheBlockMax && g_cache.cached_bytes + bytes <= kCacheTotalMax) {
+            g_cache.free_blocks.push_back({p, bytes, device});
+            g_cache.cached_bytes += bytes;
+        } else {
+            cudaFree(p);
+        }
+    }
+    cudaError_t alloc(size_t want) {
+        if (want == 0) want = 1;
+        cudaGetDevice(&device);
+        auto& fb = g_cache.free_blocks;
+        size_t best = fb.size();
+        for (size_t i = 0; i < fb.size(); ++i)
+            if (fb[i].device == device && fb[i].bytes >= want && fb[i].bytes <= 4 * want + 4096 &&
+                (best == fb.size() || fb[i].bytes < fb[best].bytes)) best = i;
+        if (best != fb.size()) {
+            p = fb[best].p; bytes = fb[best].bytes;
+            g_cache.cached_bytes -= bytes;
+            fb.erase(fb.begin() + best);
+            return cudaSuccess;
+        }
+        bytes = want;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; bytes = 0; }
+        return e;
+    }
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
