@@ -1,0 +1,93 @@
+"""Times the BASELINE.json configs C1-C5 on one B200 next to the CPU oracle (scaled samples).
+Prints one JSON line per config; run under gpurun and keep the output under profiles/.
+usage: python tools/bench_configs.py [c1 c2 c3 c4 c5 ...]"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import oracle
+from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, _lib, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+which = set(a.lower() for a in sys.argv[1:]) or {"c1", "c2", "c3", "c4", "c5"}
+
+
+def timed(fn, *a, **k):
+    t0 = time.perf_counter()
+    out = fn(*a, **k)
+    return out, time.perf_counter() - t0
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+engine.search_range(50, 3, METRIC_MAXPRO, 1, 0, 1000)  # context + module load
+
+if "c1" in which:
+    # cargo run --release -- --iterations 100000 --samples 50 --ndims 2 --metric max-pro
+    n, d, N = 50, 2, 100_000
+    _, t_gpu = timed(engine.build_lhd, n, d, N, METRIC_MAXPRO, 42)
+    (_, s, i), t_gpu2 = timed(engine.build_lhd, n, d, 1 << 26, METRIC_MAXPRO, 42)
+    _, t_cpu = timed(oracle.search_range, n, d, oracle.MAXPRO, 42, 0, 2_000_000)
+    cli = os.path.join(ROOT, "maxpro_b200", "bin", "maxpro")
+    r, t_cli = timed(subprocess.run, [cli, "--iterations", "100000", "--samples", "50", "--ndims", "2", "--metric", "max-pro", "--seed", "42"],
+                     capture_output=True, text=True)
+    lines = r.stdout.strip().splitlines()
+    emit(config="C1", n=n, d=d, search_100k_s=t_gpu, search_rate_steady=(1 << 26) / t_gpu2, cpu_rate=2_000_000 / t_cpu,
+         cpu_cores=oracle.num_threads(), cli_wall_s=t_cli, cli_rc=r.returncode, cli_metrics=lines[2:5] if len(lines) >= 5 else lines[-3:])
+
+if "c2" in which:
+    n, d, N = 50, 3, 1_000_000
+    (s, i), t_gpu = timed(engine.search_range, n, d, METRIC_MAXIMIN, 42, 0, N)
+    (s2, i2), t_cpu = timed(oracle.search_range, n, d, oracle.MAXIMIN, 42, 0, N)
+    _, t_big = timed(engine.search_range, n, d, METRIC_MAXIMIN, 42, 0, 1 << 27)
+    emit(config="C2", n=n, d=d, N=N, gpu_s=t_gpu, cpu_s=t_cpu, same_winner=(s, i) == (s2, i2), score=s, index=i,
+         gpu_rate_steady=(1 << 27) / t_big, cpu_rate=N / t_cpu, cpu_cores=oracle.num_threads())
+
+if "c3" in which:
+    n, d = 500, 10
+    N = 200_000  # one GPU's share is 1.25e6; a bounded sample here
+    (s, i), t_gpu = timed(engine.search_range, n, d, METRIC_MAXPRO, 42, 0, N)
+    Nc = 4000
+    (s2, i2), t_cpu = timed(oracle.search_range, n, d, oracle.MAXPRO, 42, 0, Nc)
+    (s3, i3), _ = timed(engine.search_range, n, d, METRIC_MAXPRO, 42, 0, Nc)
+    flops = (3 * d + 3) * n * (n - 1) // 2 + 2
+    emit(config="C3", n=n, d=d, N=N, gpu_s=t_gpu, gpu_rate=N / t_gpu, algorithmic_tflops=N / t_gpu * flops / 1e12,
+         cpu_rate=Nc / t_cpu, cpu_cores=oracle.num_threads(), parity_on_4000=(i3 == i2 and abs(s3 - s2) <= 1e-9 * s2), score=s, index=i)
+
+if "c4" in which:
+    n, d = 1000, 20
+    x = engine.generate_lhd(n, d, 42)
+    chains, steps = 1184, 200  # 8 chains per SM; the full config is 65,536 chains per GPU
+    (out, best, ch), t_gpu = timed(engine.anneal_lhd, x, steps, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, chains)
+    (o2, b2), t_cpu = timed(oracle.anneal_lhd, x, 20, 1.0, 0.99, oracle.MAXPRO, True, 43, True)
+    emit(config="C4", n=n, d=d, chains=chains, steps=steps, gpu_s=t_gpu, gpu_chain_steps_per_s=chains * steps / t_gpu,
+         algorithmic_tflops=chains * steps / t_gpu * 4 * (n - 2) * (3 * d + 3) / 1e12,
+         cpu_chain_steps_per_s_1core_full_rescore=20 / t_cpu, start_metric=oracle.maxpro_criterion(x), best_metric=best)
+    (out, best, ch), t_gpu = timed(engine.anneal_lhd, x, steps, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, chains)
+    emit(config="C4-second-call", gpu_s=t_gpu, gpu_chain_steps_per_s=chains * steps / t_gpu)
+    # jitter moves need the proposal beside the current design in shared memory: n*d*16 B <= 227 KB
+    xj = engine.generate_lhd(500, 10, 42)
+    (out, best, ch), t_j = timed(engine.anneal_lhd, xj, 100, 1.0, 0.99, METRIC_MAXPRO, True, 43, False, 1184)
+    emit(config="C4-jitter-n500-d10", chains=1184, steps=100, gpu_s=t_j, gpu_chain_steps_per_s=1184 * 100 / t_j,
+         algorithmic_tflops=1184 * 100 / t_j * ((3 * 10 + 3) * 500 * 499 / 2) / 1e12)
+
+if "c5" in which:
+    n, d = 5000, 8
+    x = engine.generate_lhd(n, d, 42)
+    (out, perm), t_gpu = timed(engine.order_design, x, METRIC_MAXPRO, True)
+    (out, perm), t_gpu2 = timed(engine.order_design, x, METRIC_MAXPRO, True)
+    (o2, p2), t_cpu = timed(oracle.order_design, x, oracle.MAXPRO, True, True)
+    (_, pm), t_mm = timed(engine.order_design, x, METRIC_MAXIMIN, False)
+    emit(config="C5", n=n, d=d, gpu_s=t_gpu2, gpu_first_call_s=t_gpu, cpu_incremental_1core_s=t_cpu,
+         same_order=perm.tolist() == p2.tolist(), maximin_gpu_s=t_mm,
+         reference_algorithm_flops=7e14, note="the reference's O(n^4 d) order_design is infeasible at this size (README: 5.13 s at n=500,d=5)")
+    x5 = engine.generate_lhd(500, 5, 42)
+    (_, p), t500 = timed(engine.order_design, x5, METRIC_MAXPRO, True)
+    emit(config="C5-readme-shape", n=500, d=5, gpu_s=t500, reference_published_s=5.129)
