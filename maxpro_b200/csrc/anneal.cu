@@ -260,11 +260,11 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
     cudaError_t e;
     if (L.metric == 0) {
-        e = cudaFuncSetAttribute(anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        e = cudaFuncSetAttribute(anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         anneal_kernel<true><<<(unsigned int)grid, threads, smem, L.stream>>>(p);
     } else {
-        e = cudaFuncSetAttribute(anneal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        e = cudaFuncSetAttribute(anneal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         anneal_kernel<false><<<(unsigned int)grid, threads, smem, L.stream>>>(p);
     }

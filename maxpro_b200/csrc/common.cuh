@@ -7,6 +7,7 @@
 namespace mp {
 
 constexpr double kEps = 1e-12;  // src/maxpro_utils.rs:35
+constexpr int kMaxChainTerms = 16;  // terms a RecipChain may hold before a flush (den >= 1e-192)
 
 // Winner record that leaves the chip: 16 bytes.
 struct __align__(16) BestRec {

@@ -32,6 +32,11 @@ cudaError_t launch_search_small(const SearchLaunch& L);
 bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* cands);
 cudaError_t launch_search_cyclic(const SearchLaunch& L);
 
+// CTA-per-candidate kernel for designs that do not fit the thread-group kernels (search_cta.cu)
+bool search_cta_supported(unsigned long long n, unsigned long long d);
+int search_cta_grid(unsigned long long n, unsigned long long d, int sms);
+cudaError_t launch_search_cta(const SearchLaunch& L);
+
 // ---- K1 alone: materialise designs (winner regeneration, generate_lhd) -------
 // out: count designs, row-major n*d each; design c uses stream seed + lo + c.
 cudaError_t launch_generate(unsigned long long n, unsigned long long d, unsigned long long seed,

@@ -160,8 +160,23 @@ def test_search_matches_oracle(n, d, metric):
     assert lhd_bins_ok(design)
 
 
+@pytest.mark.parametrize("n,d,iters", [(40, 9, 3000), (130, 10, 3000), (300, 4, 3000), (301, 7, 1500), (500, 10, 1500),
+                                       (1000, 20, 300), (1999, 2, 400), (63, 12, 2000), (2, 9, 50), (9, 33, 500)])
+def test_search_cta_path(n, d, iters):
+    """CTA-per-candidate kernel (designs too large for the thread-group kernels)."""
+    seed = 7
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
+        design, s, i = engine.build_lhd(n, d, iters, metric, seed)
+        assert i == i_ref
+        assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+        assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
+
+
 @pytest.mark.parametrize("n,d", [(40, 9), (130, 10), (300, 4)])
-def test_search_generic_path(n, d):
+def test_search_generic_path(n, d, monkeypatch):
+    """Chunked generate -> tiled score path (what remains for shapes no fused kernel covers)."""
+    monkeypatch.setenv("MAXPRO_NO_CTA", "1")
     iters, seed = 3000, 7
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
