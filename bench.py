@@ -109,6 +109,7 @@ def host_info():
 def cpu_rate(seconds_target: float, lo0: int):
     """Oracle port of build_lhd's map+reduce on the host cores; bounded sample."""
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     probe = 100_000
     oracle.search_range(N_POINTS, N_DIMS, oracle.MAXPRO, SEED, lo0, lo0 + probe)
@@ -125,6 +126,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     cores = oracle.num_threads()
     probe = 200_000
     t0 = time.perf_counter()

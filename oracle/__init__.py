@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         L.oracle_order_design_incremental.restype = i32
         L.oracle_order_design_incremental.argtypes = [dp, u64, u64, i32, i32, dp, u64p]
         L.oracle_num_threads.restype = i32
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -177,3 +179,8 @@ def order_design(design, metric, minimize, incremental=False):
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """Use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().oracle_set_num_threads(int(n))

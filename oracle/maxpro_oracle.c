@@ -436,6 +436,16 @@ int oracle_order_design_incremental(const double *design, uint64_t n, uint64_t d
     return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every host core. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP
