@@ -74,6 +74,18 @@ struct RecipChain {
     __device__ __forceinline__ void reset() { num = 0.0; den = 1.0; }
     __device__ __forceinline__ void push(double p) { num = fma(num, p, den); den *= p; }
     __device__ __forceinline__ double flush() { double v = num * fast_rcp(den); reset(); return v; }
+    // acc + num/den with the quotient good to ~2^-40 (one Newton step on the 20-bit MUFU seed,
+    // the residual folded into the final FMA): every partial sum is then within 1e-12 relative,
+    // three orders inside the 1e-9 parity bar, for 3 FP64 instructions instead of 5.
+    __device__ __forceinline__ double flush_into(double acc) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+        const double e = fma(-den, r, 1.0);
+        const double nr = num * r;
+        const double v = fma(nr, e, nr);  // num * r * (1 + e)
+        reset();
+        return acc + v;
+    }
 };
 
 }  // namespace mp
