@@ -60,6 +60,15 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
+// v_i = (i + (jit + 1/2) 2^-32) / n = fma((double)(i*2^32 + jit), c1, c0): the stratum value of
+// the LHD-Philox stream.  The 64-bit integer is assembled by register pairing (mov.b64), not by
+// shift/or arithmetic, which nvcc otherwise expands into carry chains.
+__device__ __forceinline__ double stratum_value(uint32_t i, uint32_t jit, double c1, double c0) {
+    unsigned long long m;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "r"(jit), "r"(i));
+    return fma(__ull2double_rn(m), c1, c0);
+}
+
 // (w * bound) >> 32 : multiply-shift map of a 32-bit word onto [0, bound).
 __host__ __device__ __forceinline__ uint32_t mulhi_bound(uint32_t w, uint32_t bound) {
     return (uint32_t)(((uint64_t)w * (uint64_t)bound) >> 32);

@@ -73,9 +73,8 @@ __device__ __forceinline__ void load_row_at(double (&dst)[D], const unsigned cha
 template <int N, int D, int C>
 __device__ __forceinline__ void cyc_fy_step(unsigned char* col, int i, uint32_t jit, uint32_t idx, double c1, double c0) {
     constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
-    const uint32_t j = mulhi_bound(idx, (uint32_t)i + 1u);
-    const unsigned long long m = ((unsigned long long)(uint32_t)i << 32) | jit;
-    const double v = fma((double)m, c1, c0);
+    const uint32_t j = __umulhi(idx, (uint32_t)i + 1u);
+    const double v = stratum_value((uint32_t)i, jit, c1, c0);
     *reinterpret_cast<double*>(col + i * RB) = *reinterpret_cast<double*>(col + j * RB);
     *reinterpret_cast<double*>(col + j * RB) = v;
 }
