@@ -216,9 +216,9 @@ def main():
         lo = (step * world + rank) * per_gpu  # global candidate indices, disjoint per (step, rank)
         return lo, lo + per_gpu
 
-    def device_step(step: int):
+    def device_step(step: int, flags: int = 0):
         lo, hi = block(step)
-        _lib.check(L.maxpro_search_range_device(N_POINTS, N_DIMS, METRIC_MAXPRO, SEED, lo, hi, 0,
+        _lib.check(L.maxpro_search_range_device(N_POINTS, N_DIMS, METRIC_MAXPRO, SEED, lo, hi, flags,
                                                 result.data_ptr(), ws.data_ptr(), ws_bytes.value,
                                                 stream.cuda_stream))
 
@@ -259,6 +259,29 @@ def main():
     achieved_tflops = per_gpu_rate * FLOPS_PER_CANDIDATE / 1e12
     rec = result.cpu().numpy()
     last_score, last_index = float(rec[:1].view(np.float64)[0]), int(rec[1:].view(np.uint64)[0])
+
+    # ---------------- reported separately: fp32-product screening + fp64 re-score (not a parity path)
+    def read_result():
+        r = result.cpu().numpy()
+        return float(r[:1].view(np.float64)[0]), int(r[1:].view(np.uint64)[0])
+    device_step(0, flags=1)
+    torch.cuda.synchronize()
+    screen_winner = read_result()
+    device_step(0, flags=0)
+    torch.cuda.synchronize()
+    exact_winner = read_result()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for s in range(args.steps):
+        device_step(args.warmup + s, flags=1)
+    s1.record(stream)
+    barrier()
+    screen_ms = max_over_ranks(s0.elapsed_time(s1))
+    fp32_screen = {"value": per_gpu * world * args.steps / (screen_ms * 1e-3), "unit": UNIT,
+                   "same_winner_as_fp64_search": screen_winner == exact_winner,
+                   "note": "MAXPRO_FLAG_FP32_SCREEN: fp32 products/reciprocals, one survivor per warp re-scored in fp64; "
+                           "the returned score is exact, which near-tied candidate wins is not guaranteed"}
 
     # ---------------- e2e: the host-facing call, winner design back in host memory
     base = args.warmup + args.steps
@@ -315,6 +338,7 @@ def main():
                         "the winner record and the regenerated design are copied to host every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "fp32_screen": fp32_screen,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, sample, dt, cores = cpu_rate(15.0, 1 << 40)

@@ -163,6 +163,7 @@ struct SearchWs {
     unsigned int* counter;
     BestRec* block_best;
     BestRec* chunk_result;
+    unsigned long long* survivors;  // fp32 screening: one index per warp
     double* designs;
     double* partial;
     double* scores;
@@ -177,6 +178,7 @@ SearchWs carve_search_ws(void* base, unsigned long long n, unsigned long long d)
     w.counter = reinterpret_cast<unsigned int*>(take(256));
     w.block_best = reinterpret_cast<BestRec*>(take(kMaxBlockRecs * sizeof(BestRec)));
     w.chunk_result = reinterpret_cast<BestRec*>(take(256));
+    w.survivors = reinterpret_cast<unsigned long long*>(take(kMaxBlockRecs * 16 * sizeof(unsigned long long)));
     if (!mp::search_small_supported(n, d) && !use_cta_kernel(n, d)) {
         unsigned long long bc = generic_chunk(n, d);
         w.designs = reinterpret_cast<double*>(take(bc * n * d * sizeof(double)));
@@ -217,7 +219,32 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     }
     init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
     mp::count_launch();
-    int cyc_cands = 0;
+    int cyc_cands = 0, scr_cands = 0;
+    if ((flags & MAXPRO_FLAG_FP32_SCREEN) && mp::search_screen_supported(n, d, &scr_cands) &&
+        mp::search_cyclic_supported(n, d, &cyc_cands)) {
+        // stage 1: fp32 screening, one survivor per warp
+        mp::SearchLaunch L{};
+        L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
+        L.threads = scr_cands; L.group = 1;
+        unsigned long long total = hi - lo;
+        unsigned long long want = (total + scr_cands - 1) / scr_cands;
+        L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
+        L.stream = stream;
+        CUDA_TRY(mp::launch_search_screen(L, w.survivors));
+        mp::count_launch();
+        // stage 2: exact fp64 re-score of the survivors, usual fold
+        mp::SearchLaunch E{};
+        E.n = n; E.d = d; E.metric = metric; E.seed = seed; E.lo = 0; E.hi = 0; E.flags = flags;
+        E.block_best = w.block_best; E.done_counter = w.counter; E.result = result;
+        E.group = 2; E.threads = 2 * cyc_cands;
+        E.list = w.survivors; E.list_count = (unsigned long long)L.grid * (unsigned long long)(scr_cands / 32);
+        unsigned long long want2 = (E.list_count + cyc_cands - 1) / cyc_cands;
+        E.grid = (int)(want2 < (unsigned long long)sms ? want2 : (unsigned long long)sms);
+        E.stream = stream;
+        CUDA_TRY(mp::launch_search_cyclic(E));
+        mp::count_launch();
+        return MAXPRO_OK;
+    }
     if (mp::search_cyclic_supported(n, d, &cyc_cands)) {
         mp::SearchLaunch L{};
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;

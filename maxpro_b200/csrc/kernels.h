@@ -22,6 +22,8 @@ struct SearchLaunch {
     BestRec* result;
     int grid, threads;
     int group;  // lanes per candidate (1 or 2)
+    const unsigned long long* list;  // optional explicit candidate list (cyclic kernel, stage 2 of the screened search)
+    unsigned long long list_count;
     cudaStream_t stream;
 };
 bool search_small_supported(unsigned long long n, unsigned long long d);
@@ -31,6 +33,10 @@ cudaError_t launch_search_small(const SearchLaunch& L);
 // shape-specialised cyclic schedule (search_cyclic.cu); *cands = candidates per CTA
 bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* cands);
 cudaError_t launch_search_cyclic(const SearchLaunch& L);
+
+// fp32 screening pass (search_screen.cu): one surviving candidate index per warp
+bool search_screen_supported(unsigned long long n, unsigned long long d, int* cands);
+cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* survivors);
 
 // CTA-per-candidate kernel for designs that do not fit the thread-group kernels (search_cta.cu)
 bool search_cta_supported(unsigned long long n, unsigned long long d);

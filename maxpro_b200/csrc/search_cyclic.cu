@@ -28,6 +28,9 @@ namespace mp {
 struct CyclicParams {
     int ring;  // warps per sub-partition that take turns on the FP64 pipe (0 = no turn-taking)
     unsigned long long seed, lo, hi;
+    // list mode (stage 2 of the fp32-screened search): score list[0..list_count) instead of lo..hi
+    const unsigned long long* list;
+    unsigned long long list_count;
     double c1, c0;
     double n_pairs, inv_d;
     BestRec* block_best;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
 
     const unsigned long long gcid = (unsigned long long)blockIdx.x * C + c;
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
-    const unsigned long long total = p.hi - p.lo;
+    const unsigned long long total = p.list ? p.list_count : p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
 
     double best = MAXPRO ? CUDART_INF : -CUDART_INF;
@@ -222,8 +225,12 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
 
     for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
         const unsigned long long off = gcid + rnd * gstep;
-        const bool active = off < total;
-        const unsigned long long idx = p.lo + off;
+        bool active = off < total;
+        unsigned long long idx = p.lo + off;
+        if (p.list) {
+            idx = active ? p.list[off] : kNoIndex;
+            active = idx != kNoIndex;
+        }
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         if (active) {
@@ -285,6 +292,7 @@ cudaError_t launch_search_cyclic(const SearchLaunch& L) {
     if (const char* e = getenv("MAXPRO_CYCLIC_RING")) { int v = atoi(e); if (v == 0 || v == 2 || v == 3) p.ring = v; }
     if (p.ring > (L.threads / 32) / 4) p.ring = 0;
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
+    p.list = L.list; p.list_count = L.list_count;
     p.c1 = ldexp(1.0 / (double)L.n, -32);
     p.c0 = 0.5 * p.c1;
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;

@@ -184,6 +184,23 @@ def test_search_generic_path(n, d, monkeypatch):
         assert i == i_ref and math.isclose(s, s_ref, rel_tol=REL)
 
 
+@pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+def test_search_fp32_screen_two_stage(n, d, metric):
+    """MAXPRO_FLAG_FP32_SCREEN: fp32 screening + exact fp64 re-score of one survivor per warp.
+    The returned score is always the exact criterion of the returned design; the winner equals
+    the exact search's unless two of the best lie within fp32 noise (not the case for these seeds)."""
+    for iters, seed in ((20_000, 42), (1 << 21, 7)):
+        design, s, i = engine.build_lhd(n, d, iters, metric, seed, flags=1)
+        _, s_exact, i_exact = engine.build_lhd(n, d, iters, metric, seed)
+        assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
+        crit = oracle.maxpro_criterion(design) if metric == METRIC_MAXPRO else oracle.maximin_criterion(design)
+        assert math.isclose(s, crit, rel_tol=REL)
+        assert (i, s) == (i_exact, s_exact)
+    # shapes without a screening kernel fall back to the exact path
+    assert engine.build_lhd(13, 5, 5000, metric, 3, flags=1)[1:] == engine.build_lhd(13, 5, 5000, metric, 3)[1:]
+
+
 def test_search_one_point_and_none_metric():
     d, s, i = engine.build_lhd(1, 3, 10, METRIC_MAXPRO, 5)
     assert (s, i) == (0.0, 9) and d.shape == (1, 3)      # all tie at 0.0 -> last index

@@ -14,7 +14,7 @@ L = _lib.lib()
 dev = torch.device("cuda", 0)
 
 
-def dev_search(n, d, metric, total, reps=3):
+def dev_search(n, d, metric, total, reps=3, flags=0):
     ws_bytes = C.c_size_t(0)
     _lib.check(L.maxpro_search_workspace_bytes(n, d, C.byref(ws_bytes)))
     ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
@@ -24,7 +24,7 @@ def dev_search(n, d, metric, total, reps=3):
     for r in range(reps + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        _lib.check(L.maxpro_search_range_device(n, d, metric, 42, r * total, (r + 1) * total, 0, res.data_ptr(),
+        _lib.check(L.maxpro_search_range_device(n, d, metric, 42, r * total, (r + 1) * total, flags, res.data_ptr(),
                                                 ws.data_ptr(), ws_bytes.value, st.cuda_stream))
         e1.record(st)
         torch.cuda.synchronize()
@@ -37,6 +37,15 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "search"
 if mode == "ncu":
     total = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 192 * 16
     print(engine.search_range(50, 3, METRIC_MAXPRO, 42, 0, total))
+    sys.exit(0)
+
+if mode == "screen":
+    total = 1 << 26
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        for (n, d) in ((50, 3), (50, 2)):
+            ms0 = dev_search(n, d, metric, total)
+            ms1 = dev_search(n, d, metric, total, flags=1)
+            print(f"n={n} d={d} metric={metric}: exact {total/ms0/1e6:.3f} Gcand/s | fp32 screen + fp64 rescore {total/ms1/1e6:.3f} Gcand/s", flush=True)
     sys.exit(0)
 
 if mode == "sweep":
