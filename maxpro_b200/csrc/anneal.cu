@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
         bool materialized = false, synced = true;  // HBM copy exists / equals the current design
         double temp = p.t0;                                                             // :81
         double* best_out = p.best_design + chain * (unsigned long long)nd;
+        unsigned long long until_resync = p.resync;  // iterations until the next full re-sum of S
 
         for (unsigned long long t = 0; t < p.iters; ++t) {
             double raw_new, u;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 r2 = (int)mulhi_bound(w.y, (uint32_t)n);  // :30
                 c = (int)mulhi_bound(w.z, (uint32_t)d);   // :31
                 u = (double)w.w * 0x1p-32;
-                if (MAXPRO && (t % p.resync) != p.resync - 1) {
+                if (MAXPRO && --until_resync != 0) {
                     // incremental: only pairs (r1,j), (r2,j), j not in {r1,r2}, change
                     double delta = 0.0;
                     if (r1 != r2) {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                     delta = block_reduce(delta, scratch, true);
                     raw_new = raw_cur + delta;
                 } else {
+                    until_resync = p.resync;
                     // maximin, or the periodic full re-sum: apply, score, (maybe) undo
                     __syncthreads();
                     if (threadIdx.x == 0) {
