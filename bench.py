@@ -121,7 +121,7 @@ def cpu_rate(seconds_target: float, lo0: int):
     return sample / dt, sample, dt, oracle.num_threads()
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference algorithm on the host CPU, rank 0 only."""
     if rank != 0:
         return
@@ -154,7 +154,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -171,8 +171,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE line (the JSON).  Libraries write there too (NCCL prints its
+    # version banner on fd 1), so everything else goes to stderr and the line is written to the
+    # saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import ctypes as C
@@ -346,7 +356,7 @@ def main():
                                 "sample": f"{sample} candidates (n=50, d=3, MaxPro) in {dt:.1f} s, OpenMP over candidates, "
                                           f"{host_info()['cpu_model']}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
