@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -341,6 +342,24 @@ int score_batch_device_impl(const double* d_designs, uint64_t b, uint64_t n, uin
     }
     init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
     mp::count_launch();
+    int cyc_cands = 0;
+    if (mp::search_cyclic_supported(n, d, &cyc_cands) && (reinterpret_cast<uintptr_t>(d_designs) & 15u) == 0 &&
+        !getenv("MAXPRO_NO_FAST_SCORE")) {
+        // headline shapes: the thread-group kernel of the fused search, fed from HBM instead of Philox
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
+        BestRec* scratch_result = d_result ? static_cast<BestRec*>(d_result) : w.block_best + (kMaxBlockRecs - 1);
+        mp::SearchLaunch L{};
+        L.n = n; L.d = d; L.metric = metric; L.seed = 0; L.lo = 0; L.hi = b;
+        L.block_best = w.block_best; L.done_counter = w.counter; L.result = scratch_result;
+        L.group = 2; L.threads = 2 * cyc_cands;
+        unsigned long long want = (b + cyc_cands - 1) / cyc_cands;
+        L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
+        L.designs = d_designs; L.scores = d_scores; L.stream = stream;
+        CUDA_TRY(mp::launch_search_cyclic(L));
+        mp::count_launch();
+        return MAXPRO_OK;
+    }
     mp::ScoreLaunch S{};
     S.designs = d_designs; S.b = b; S.n = n; S.d = d; S.metric = metric; S.scores = d_scores;
     S.partial = w.partial; S.block_best = w.block_best; S.done_counter = w.counter;

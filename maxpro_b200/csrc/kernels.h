@@ -24,6 +24,8 @@ struct SearchLaunch {
     int group;  // lanes per candidate (1 or 2)
     const unsigned long long* list;  // optional explicit candidate list (cyclic kernel, stage 2 of the screened search)
     unsigned long long list_count;
+    const double* designs;           // supplied mode (cyclic kernel): score designs[lo..hi) instead of generating
+    double* scores;
     cudaStream_t stream;
 };
 bool search_small_supported(unsigned long long n, unsigned long long d);

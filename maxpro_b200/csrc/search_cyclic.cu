@@ -31,6 +31,10 @@ struct CyclicParams {
     // list mode (stage 2 of the fp32-screened search): score list[0..list_count) instead of lo..hi
     const unsigned long long* list;
     unsigned long long list_count;
+    // supplied mode (score_batch): candidate idx is the design designs[idx*N*D ...], row-major
+    // [i][k] in HBM; scores[idx] receives its criterion.  lo..hi index the batch.
+    const double* designs;
+    double* scores;
     double c1, c0;
     double n_pairs, inv_d;
     BestRec* block_best;
@@ -118,7 +122,9 @@ __device__ __forceinline__ void cyc_generate_three(unsigned char* cand, uint32_t
     cyc_generate_blocks<N, D, C>(cand + (g ? 2u : 0u) * DB, g ? 2u : 0u, g ? H : NB - H, H, s_lo, s_hi, c1, c0);
 }
 
-template <int N, int D, int C, bool MAXPRO>
+// SAFE: designs a caller supplied may lie outside the unit cube, where the reciprocal chains
+// are not range-safe; then every term takes an IEEE divide (src/maxpro_utils.rs:54 literally).
+template <int N, int D, int C, bool MAXPRO, bool SAFE = false>
 __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
     constexpr int R = 5, S = 4, G = 2;
     constexpr int kHalf = (N - 1) / 2;       // shifts 1..kHalf pair every row once
@@ -158,7 +164,7 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
             for (int c = 0; c < S; ++c)
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (MAXPRO) ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c]));
+                    if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xj[r + c]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c])); }
                     else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xj[r + c]));
                 }
         }
@@ -169,11 +175,11 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
             for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xd[r], cand, i0_off + (N / 2 + r) * RB);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (MAXPRO) ch[r].push(cyc_maxpro_term<D>(xi[r], xd[r]));
+                if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xd[r]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xd[r])); }
                 else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xd[r]));
             }
         }
-        if (MAXPRO) {
+        if (MAXPRO && !SAFE) {
 #pragma unroll
             for (int r = 0; r < R; ++r) acc = ch[r].flush_into(acc);  // <= kPerLane + 1 terms per chain
         }
@@ -183,6 +189,36 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
 #pragma unroll
     for (int r = 1; r < R; ++r) m = fmin(m, mins[r]);
     return m;
+}
+
+// Supplied designs: HBM row-major [i][k] -> shared [k][i][c].  Lane 0 takes the first kRows0 rows,
+// lane 1 the rest, as 16-byte vectors (LDG.128: a 32-byte sector is fetched for every 16 bytes
+// used, the best a lane-per-design access can do without staging).  Returns false if a value
+// lies outside [0, 1] (sign bit set or high word above that of 1.0): the caller then scores
+// the design with IEEE divides.
+template <int N, int D, int C>
+__device__ __forceinline__ bool cyc_load_design(unsigned char* cand, const double* src, int g) {
+    constexpr int kElems = N * D;
+    static_assert(kElems % 2 == 0, "16-byte vectors");
+    constexpr int kRows0 = ((N / 2 + 1) / 2) * 2;  // lane 0's rows: even, so both lanes start on a 16-byte boundary
+    constexpr int kVec0 = kRows0 * D / 2, kVec1 = (kElems - kRows0 * D) / 2;
+    static_assert((kRows0 * D) % 2 == 0 && kVec1 >= 0 && kVec1 <= kVec0, "split");
+    constexpr unsigned RB = Layout<N, D, C>::kRowBytes, DB = Layout<N, D, C>::kDimBytes;
+    const double2* v = reinterpret_cast<const double2*>(src) + g * kVec0;
+    unsigned char* dst = cand + (unsigned)g * kRows0 * RB;
+    unsigned int worst = 0u;
+#pragma unroll
+    for (int t = 0; t < kVec0; ++t) {
+        if (t < kVec1 || g == 0) {
+            const double2 x = __ldg(v + t);
+            const int e0 = 2 * t, e1 = 2 * t + 1;
+            *reinterpret_cast<double*>(dst + (e0 / D) * RB + (e0 % D) * DB) = x.x;
+            *reinterpret_cast<double*>(dst + (e1 / D) * RB + (e1 % D) * DB) = x.y;
+            worst = max(worst, max((unsigned int)__double2hiint(x.x), (unsigned int)__double2hiint(x.y)));
+            // exactly-1.0 passes (hi == 0x3FF00000, lo == 0); anything in (1, 1+2^-20) also passes and is harmless
+        }
+    }
+    return worst <= 0x3FF00000u;
 }
 
 // Named-barrier token between two warps (64 threads): bar.arrive hands it on, bar.sync takes it.
@@ -198,7 +234,7 @@ __device__ __forceinline__ void cyc_token_pass(int id) { asm volatile("bar.arriv
 // vs 1.08 Gcand/s without -- because an FP64 instruction holds the sub-partition's issue port
 // for 2 cycles, so time ~ 2*N_fp64 + N_other whatever the interleaving.  Kept as an
 // experiment switch (MAXPRO_CYCLIC_RING), off by default.
-template <int N, int D, int C, bool MAXPRO>
+template <int N, int D, int C, bool MAXPRO, bool SUPPLIED = false>
 __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int G = 2, kPerWarp = 16;
@@ -233,7 +269,10 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
         }
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
-        if (active) {
+        bool in_cube = true;
+        if (active && SUPPLIED) {
+            in_cube = cyc_load_design<N, D, C>(cand, p.designs + idx * (unsigned long long)(N * D), g);
+        } else if (active) {
             if (D == 3) {
                 cyc_generate_three<N, C>(cand, s_lo, s_hi, p.c1, p.c0, g, group_mask);
             } else {
@@ -245,17 +284,28 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
         __syncwarp(group_mask);
         if (in_ring) cyc_token_wait(tok_in);
         double s = 0.0;
-        if (active) s = cyc_score<N, D, C, MAXPRO>(cand, g);
+        if (SUPPLIED && MAXPRO) {
+            in_cube = __shfl_xor_sync(group_mask, (int)in_cube, 16) && in_cube;  // both halves of the design
+            if (active && in_cube) s = cyc_score<N, D, C, MAXPRO, false>(cand, g);
+            else if (active) s = cyc_score<N, D, C, MAXPRO, true>(cand, g);
+        } else if (active) {
+            s = cyc_score<N, D, C, MAXPRO>(cand, g);
+        }
         if (in_ring) cyc_token_pass(tok_out);
         const double other = __shfl_xor_sync(group_mask, s, 16);
         if (MAXPRO) s = (g == 0) ? s + other : other + s;  // same bits in both lanes
         else s = fmin(s, other);
         __syncwarp(group_mask);
         if (!MAXPRO) s = sqrt(s);
+        if (SUPPLIED) {
+            // every score leaves the chip, and the fold compares criteria exactly as lib.rs:85-97 does
+            if (MAXPRO) s = pow(s / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
+            if (active && g == 0) p.scores[idx] = s;
+        }
         if (active && (MAXPRO ? (s <= best) : (s >= best))) { best = s; best_idx = idx; }
     }
     if (in_ring && q == 0) cyc_token_wait(tok_in);  // take the last token so no arrival is left pending
-    if (MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
+    if (!SUPPLIED && MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
     block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
@@ -264,16 +314,14 @@ static cudaError_t launch_cyclic_nd(const SearchLaunch& L, const CyclicParams& p
     constexpr size_t smem = (size_t)N * D * C * sizeof(double) + 32 * sizeof(BestRec);
     static_assert(smem <= kSmemBudget, "candidates per CTA do not fit shared memory");
     cudaError_t e;
-    if (L.metric == 0) {
-        e = cudaFuncSetAttribute(search_cyclic_kernel<N, D, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto go = [&](auto kernel) -> cudaError_t {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        search_cyclic_kernel<N, D, C, true><<<L.grid, 2 * C, smem, L.stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(search_cyclic_kernel<N, D, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        search_cyclic_kernel<N, D, C, false><<<L.grid, 2 * C, smem, L.stream>>>(p);
-    }
-    return cudaGetLastError();
+        kernel<<<L.grid, 2 * C, smem, L.stream>>>(p);
+        return cudaGetLastError();
+    };
+    if (p.designs) return L.metric == 0 ? go(search_cyclic_kernel<N, D, C, true, true>) : go(search_cyclic_kernel<N, D, C, false, true>);
+    return L.metric == 0 ? go(search_cyclic_kernel<N, D, C, true, false>) : go(search_cyclic_kernel<N, D, C, false, false>);
 }
 
 // Shapes with a specialised instantiation; *cands = candidates per CTA.
@@ -293,6 +341,7 @@ cudaError_t launch_search_cyclic(const SearchLaunch& L) {
     if (p.ring > (L.threads / 32) / 4) p.ring = 0;
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.list = L.list; p.list_count = L.list_count;
+    p.designs = L.designs; p.scores = L.scores;
     p.c1 = ldexp(1.0 / (double)L.n, -32);
     p.c0 = 0.5 * p.c1;
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;

@@ -111,6 +111,32 @@ def test_score_batch_tie_rule(metric):
     assert engine.score_batch(front, metric)[1] == arg + 1
 
 
+@pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+def test_score_batch_headline_shapes_fast_path(n, d, metric, monkeypatch):
+    """n=50 batches take the thread-group kernel fed from HBM: odd batch sizes, designs outside
+    the unit cube (IEEE-divide fallback), boundary coordinates, coincident points, ties; and the
+    same batch through the generic tiled kernel must give the same argbest."""
+    rng = np.random.default_rng(d)
+    for b in (1, 5, 191, 193, 1000):
+        designs = np.stack([random_lhd(rng, n, d) for _ in range(b)])
+        if b >= 5:
+            designs[1] = designs[1] * 7.0 - 3.0      # outside the unit cube
+            designs[2, 3] = designs[2, 9]             # coincident points
+            designs[3, 0, 0], designs[3, 1, 0] = 0.0, 1.0  # boundary values stay on the fast path
+            designs[4] = -designs[4]                  # negative coordinates
+        ref, ref_arg = oracle.score_batch(designs, metric)
+        got, arg = engine.score_batch(designs, metric)
+        assert arg == ref_arg
+        assert rel_err(got, ref) < REL if metric == METRIC_MAXPRO else np.array_equal(got, ref)
+        monkeypatch.setenv("MAXPRO_NO_FAST_SCORE", "1")
+        got2, arg2 = engine.score_batch(designs, metric)
+        monkeypatch.delenv("MAXPRO_NO_FAST_SCORE")
+        assert arg2 == arg and rel_err(got2, got) < REL
+    dup = np.concatenate([designs, designs[arg:arg + 1]])
+    assert engine.score_batch(dup, metric)[1] == len(designs)  # later index on ties
+
+
 @pytest.mark.parametrize("n,d,b", [(2, 2, 7), (7, 1, 33), (64, 4, 50), (65, 3, 20), (200, 6, 9), (10, 12, 100)])
 def test_score_batch_shapes(n, d, b):
     rng = np.random.default_rng(n + d + b)
