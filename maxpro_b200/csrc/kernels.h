@@ -92,6 +92,9 @@ struct OrderLaunch {
     cudaStream_t stream;
 };
 cudaError_t launch_order(const OrderLaunch& L);
+// cluster / distributed-shared-memory version (order_cluster.cu): pool spread over 8 SMs
+bool order_cluster_supported(unsigned long long n, unsigned long long d);
+cudaError_t launch_order_cluster(const OrderLaunch& L);
 
 // ---- FP64 pipe peak probe -------------------------------------------------------
 cudaError_t launch_dfma_probe(double* d_sink, int grid, int threads, int iters, cudaStream_t stream);

@@ -11,7 +11,7 @@
 //   maximin: acc[c] = min_{i in prefix} dist(i, c); value(prefix + c) =
 //            min(cur_min, acc[c]) -- exact, so ties (which are the common case
 //            once cur_min is small) resolve exactly as in the reference.
-// Each step adds ONE point, so every acc[c] takes one O(d) update: O(n^2 d)
+// Each step adds ONE point, so every running value takes one O(d) update: O(n^2 d)
 // total.  The pool keeps Vec::swap_remove order (order.rs:63,101): the last
 // element moves into the hole, and scan position decides ties.
 // The n-1 steps are strictly sequential (argbest, then update), hence one CTA:
@@ -42,15 +42,25 @@ __device__ __forceinline__ bool cand_better(double va, unsigned int pa, double v
     return MINIMIZE ? (va < vb) : (va > vb);
 }
 
-template <bool MAXPRO, bool MINIMIZE>
-__global__ void __launch_bounds__(1024, 1) order_kernel(OrderParams p) {
-    extern __shared__ __align__(16) double last_s[];  // [d] coordinates of the point just placed
+// Pool state lives in shared memory, indexed by scan POSITION: pool_s[pos] = point id,
+// acc_s[pos] = that point's running value.  swap_remove moves the last position into the hole
+// (both arrays), so position order is exactly the reference's Vec order.  Coordinates stay in
+// HBM/L2 (row-major, one 8*d-byte row per point): each thread issues the loads of all its
+// positions before using any of them.  SMEM: n*12 bytes (+ d doubles), i.e. n <= ~18,000.
+constexpr int kOrderMaxPerThread = 8;
+
+template <bool MAXPRO, bool MINIMIZE, bool SMEM_STATE>
+__global__ void __launch_bounds__(512, 1) order_kernel(OrderParams p) {
+    extern __shared__ __align__(16) unsigned char order_smem[];
     __shared__ double red_v[32];
     __shared__ unsigned int red_p[32];
     __shared__ unsigned int pick_s;
     __shared__ double cur_min_s;
     const unsigned int n = (unsigned int)p.n, d = (unsigned int)p.d;
     const unsigned int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    double* last_s = reinterpret_cast<double*>(order_smem);                        // [d]
+    double* acc = SMEM_STATE ? last_s + d : p.acc;                                  // [n] by position
+    unsigned int* pool = SMEM_STATE ? reinterpret_cast<unsigned int*>(acc + n) : p.pool;  // [n] by position
 
     // first point: closest to the centre [0.5; d], strict <, first index wins (order.rs:49-59)
     double bv = CUDART_INF;
@@ -65,10 +75,12 @@ __global__ void __launch_bounds__(1024, 1) order_kernel(OrderParams p) {
         }
         double dist = sqrt(sq);
         if (cand_better<true>(dist, i, bv, bp)) { bv = dist; bp = i; }
-        p.pool[i] = i;
-        p.acc[i] = MAXPRO ? 0.0 : CUDART_INF;
+        pool[i] = i;
+        acc[i] = MAXPRO ? 0.0 : CUDART_INF;
     }
     unsigned int pool_n = n, m = 0;
+    // 16-byte loads need 16-byte aligned rows: even d and an aligned base
+    const bool vec_ok = (d % 2 == 0) && ((reinterpret_cast<unsigned long long>(p.x) & 15ull) == 0);
 
     auto block_argbest = [&](bool minimize_centre) {
 #pragma unroll
@@ -90,11 +102,12 @@ __global__ void __launch_bounds__(1024, 1) order_kernel(OrderParams p) {
                 if (q == 0xFFFFFFFFu || take) { v = red_v[w]; q = red_p[w]; }
             }
             // swap_remove(q): the last pool entry fills the hole (order.rs:63,101)
-            unsigned int pick = p.pool[q];
-            p.pool[q] = p.pool[pool_n - 1];
+            const unsigned int pick = pool[q];
+            if (!MAXPRO && !minimize_centre) cur_min_s = fmin(cur_min_s, acc[q]);
+            pool[q] = pool[pool_n - 1];
+            acc[q] = acc[pool_n - 1];
             p.perm[m] = pick;
             pick_s = pick;
-            if (!MAXPRO && !minimize_centre) cur_min_s = fmin(cur_min_s, p.acc[pick]);
         }
         __syncthreads();
     };
@@ -111,30 +124,65 @@ __global__ void __launch_bounds__(1024, 1) order_kernel(OrderParams p) {
         __syncthreads();
         bv = MINIMIZE ? CUDART_INF : -CUDART_INF;
         bp = 0xFFFFFFFFu;
-        for (unsigned int pos = tid; pos < pool_n; pos += T) {
-            const unsigned int c = p.pool[pos];
-            const double* xc = p.x + (unsigned long long)c * d;
-            double v;
-            if (MAXPRO) {
-                double prod = 1.0;  // src/maxpro_utils.rs:45-54, one pair
-                for (unsigned int k = 0; k < d; ++k) {
-                    double df = __dsub_rn(last_s[k], xc[k]);
-                    prod = __dmul_rn(prod, __dmul_rn(df, df));
-                }
-                v = __dadd_rn(p.acc[c], 1.0 / __dadd_rn(prod, kEps));
-                p.acc[c] = v;
-            } else {
-                double df = __dsub_rn(last_s[0], xc[0]);
-                double sq = __dmul_rn(df, df);
-                for (unsigned int k = 1; k < d; ++k) {
-                    df = __dsub_rn(last_s[k], xc[k]);
-                    sq = __dadd_rn(sq, __dmul_rn(df, df));
-                }
-                double a = fmin(p.acc[c], sqrt(sq));
-                p.acc[c] = a;
-                v = fmin(a, cur_min);  // criterion of prefix + c
+        for (unsigned int pos0 = tid; pos0 < pool_n; pos0 += T * kOrderMaxPerThread) {
+            // issue every row pointer first, then walk the dimensions of all rows together
+            const double* rows[kOrderMaxPerThread];
+            double val[kOrderMaxPerThread];
+#pragma unroll
+            for (int u = 0; u < kOrderMaxPerThread; ++u) {
+                const unsigned int pos = pos0 + u * T;
+                rows[u] = p.x + (unsigned long long)(pos < pool_n ? pool[pos] : 0u) * d;
+                val[u] = MAXPRO ? 1.0 : 0.0;
             }
-            if (cand_better<MINIMIZE>(v, pos, bv, bp) || bp == 0xFFFFFFFFu) { bv = v; bp = pos; }
+            auto fold = [&](int u, unsigned int k, double xk) {
+                const double df = __dsub_rn(last_s[k], xk);
+                if (MAXPRO) val[u] = __dmul_rn(val[u], __dmul_rn(df, df));  // src/maxpro_utils.rs:48-50
+                else val[u] = (k == 0) ? __dmul_rn(df, df) : __dadd_rn(val[u], __dmul_rn(df, df));
+            };
+            // The rows are scattered over HBM/L2 (pool order), so the cost is load latency: fetch
+            // four dimensions of every row of the batch (two 16-byte loads per row, all in
+            // flight together) before touching any of them.
+            unsigned int k = 0;
+            if (vec_ok) {
+                for (; k + 4 <= d; k += 4) {
+                    double2 a[kOrderMaxPerThread], b[kOrderMaxPerThread];
+#pragma unroll
+                    for (int u = 0; u < kOrderMaxPerThread; ++u) {
+                        a[u] = __ldg(reinterpret_cast<const double2*>(rows[u] + k));
+                        b[u] = __ldg(reinterpret_cast<const double2*>(rows[u] + k + 2));
+                    }
+#pragma unroll
+                    for (int u = 0; u < kOrderMaxPerThread; ++u) {
+                        if (pos0 + u * T < pool_n) {
+                            fold(u, k, a[u].x); fold(u, k + 1, a[u].y); fold(u, k + 2, b[u].x); fold(u, k + 3, b[u].y);
+                        }
+                    }
+                }
+            }
+            for (; k < d; ++k) {
+                double xk[kOrderMaxPerThread];
+#pragma unroll
+                for (int u = 0; u < kOrderMaxPerThread; ++u) xk[u] = __ldg(rows[u] + k);
+#pragma unroll
+                for (int u = 0; u < kOrderMaxPerThread; ++u)
+                    if (pos0 + u * T < pool_n) fold(u, k, xk[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kOrderMaxPerThread; ++u) {
+                const unsigned int pos = pos0 + u * T;
+                if (pos < pool_n) {
+                    double v;
+                    if (MAXPRO) {
+                        v = __dadd_rn(acc[pos], 1.0 / __dadd_rn(val[u], kEps));  // :53-54, one pair
+                        acc[pos] = v;
+                    } else {
+                        const double a = fmin(acc[pos], sqrt(val[u]));
+                        acc[pos] = a;
+                        v = fmin(a, cur_min);  // criterion of prefix + this point
+                    }
+                    if (cand_better<MINIMIZE>(v, pos, bv, bp) || bp == 0xFFFFFFFFu) { bv = v; bp = pos; }
+                }
+            }
         }
         block_argbest(false);
         --pool_n; ++m;
@@ -145,17 +193,23 @@ cudaError_t launch_order(const OrderLaunch& L) {
     OrderParams p;
     p.x = L.design; p.n = L.n; p.d = L.d; p.maxpro = L.metric == 0; p.minimize = L.minimize;
     p.perm = L.perm; p.acc = L.acc; p.pool = L.pool;
-    size_t smem = L.d * sizeof(double);
-    int threads = L.n >= 4096 ? 1024 : (L.n >= 1024 ? 512 : 256);
+    size_t smem_state = L.d * sizeof(double) + L.n * (sizeof(double) + sizeof(unsigned int));
+    const bool in_smem = smem_state + 1024 <= kSmemBudget;
+    size_t smem = in_smem ? smem_state : L.d * sizeof(double);
+    int threads = L.n >= 1024 ? 512 : 256;
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<1, threads, smem, L.stream>>>(p);
+        count_launch();
+        return cudaGetLastError();
+    };
     if (L.metric == 0) {
-        if (L.minimize) order_kernel<true, true><<<1, threads, smem, L.stream>>>(p);
-        else order_kernel<true, false><<<1, threads, smem, L.stream>>>(p);
-    } else {
-        if (L.minimize) order_kernel<false, true><<<1, threads, smem, L.stream>>>(p);
-        else order_kernel<false, false><<<1, threads, smem, L.stream>>>(p);
+        if (in_smem) return L.minimize ? go(order_kernel<true, true, true>) : go(order_kernel<true, false, true>);
+        return L.minimize ? go(order_kernel<true, true, false>) : go(order_kernel<true, false, false>);
     }
-    count_launch();
-    return cudaGetLastError();
+    if (in_smem) return L.minimize ? go(order_kernel<false, true, true>) : go(order_kernel<false, false, true>);
+    return L.minimize ? go(order_kernel<false, true, false>) : go(order_kernel<false, false, false>);
 }
 
 }  // namespace mp

@@ -326,6 +326,20 @@ def test_order_large(metric, minimize):
     assert abs(oracle.maxpro_criterion(x) - oracle.maxpro_criterion(got)) < 1e-10 * oracle.maxpro_criterion(x)
 
 
+@pytest.mark.parametrize("n,d", [(64, 2), (65, 3), (71, 1), (200, 6), (1000, 3)])
+def test_order_cluster_path(n, d, monkeypatch):
+    """n >= 64 runs on a thread-block cluster (pool in distributed shared memory); it must pick
+    exactly what the single-CTA kernel and the oracle pick."""
+    x = oracle.generate_lhd(n, d, 5)
+    for metric, minimize in ((METRIC_MAXPRO, True), (METRIC_MAXIMIN, False), (METRIC_MAXIMIN, True)):
+        _, p_ref = oracle.order_design(x, metric, minimize, incremental=True)
+        _, p = engine.order_design(x, metric, minimize)
+        monkeypatch.setenv("MAXPRO_NO_ORDER_CLUSTER", "1")
+        _, p1 = engine.order_design(x, metric, minimize)
+        monkeypatch.delenv("MAXPRO_NO_ORDER_CLUSTER")
+        assert p.tolist() == p_ref.tolist() == p1.tolist()
+
+
 def test_order_structured_ties(r_golden):
     """The R design sits on a regular grid: many exactly equal distances, so the maximin order is
     decided by the tie rules alone."""
