@@ -3,14 +3,20 @@
 // Replaces anneal::anneal_lhd + swap_rows (src/anneal.rs:23-143).  The reference
 // runs ONE chain and re-scores the whole design (O(n^2 d)) every iteration; here
 //   - each chain keeps its current design in shared memory, dimension-major
-//     [k][i], for the whole run (160 KB at n=1000, d=20: one chain per SM);
+//     [k][i] with an even row stride, for the whole run (160 KB at n=1000, d=20:
+//     one chain per SM);
 //   - swap moves on the MaxPro criterion are scored incrementally: exchanging
-//     x[r1][c] and x[r2][c] only changes the 2(n-2) pairs that touch r1 or r2,
-//     and each change is evaluated as (p - p')/(p p') so the update does not
-//     cancel; S is re-summed from scratch every kResync iterations to stop drift;
+//     x[r1][c] and x[r2][c] only changes the 2(n-2) pairs that touch r1 or r2.
+//     A thread takes two neighbouring partner rows j, j+1 (one 16-byte load per
+//     dimension), carries the four products over the d-1 untouched dimensions in
+//     registers, and evaluates each change as (p - p')/(p p') so the update does
+//     not cancel; the four changes of a thread share ONE divide.  S is re-summed
+//     from scratch every kResync iterations to stop drift;
+//   - the swap draws (r1, r2, c, u) of 128 consecutive iterations are produced in
+//     one go, one Philox call per thread, and read back as a broadcast;
 //   - jitter moves (every coordinate changes) and maximin moves are re-scored in
-//     full, with the row pairs dealt cyclically (i, i+s mod n) so every thread
-//     gets the same number of pairs;
+//     full: work items of (row i, 8 consecutive cyclic shifts), the 8 running
+//     products in registers across the dimensions;
 //   - the chain's global best (anneal.rs:92-94,131-136) lives in HBM and is
 //     touched only when it improves; when the current design was already the
 //     best, a swap improvement rewrites two elements instead of the design.
@@ -22,7 +28,12 @@
 #include "philox.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace mp {
+
+constexpr int kDrawBatch = 128;  // swap iterations whose draws are generated together
+constexpr int kShiftBlock = 8;   // cyclic shifts per full-score work item
 
 struct AnnealParams {
     const double* design;  // [n][d] row-major start design (shared by all chains)
@@ -36,50 +47,96 @@ struct AnnealParams {
     unsigned int* improved;     // [n_chains]
 };
 
-__device__ __forceinline__ double block_reduce(double v, double* scratch, bool is_sum) {
-    // deterministic: fixed lane tree, then warp partials folded in warp order
-    v = is_sum ? warp_reduce_sum(v) : warp_reduce_min(v);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    double r = scratch[0];
-    for (int w = 1; w < nw; ++w) r = is_sum ? r + scratch[w] : fmin(r, scratch[w]);
-    return r;
+// Deterministic block reduction in two halves.  Every thread: lane tree, lane 0 publishes the
+// warp's partial.  After a barrier, warp 0 alone folds the partials (a second lane tree) --
+// the chain's scalar state and the Metropolis arithmetic (pow, exp, two divides) live in warp
+// 0 only, so the other warps spend no issue slots on it.
+template <bool IS_SUM>
+__device__ __forceinline__ void publish_partial(double v, double* part) {
+    v = IS_SUM ? warp_reduce_sum(v) : warp_reduce_min(v);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+}
+template <bool IS_SUM>
+__device__ __forceinline__ double warp0_total(const double* part) {
+    const int lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;  // nw <= 16
+    double v = lane < nw ? part[lane] : (IS_SUM ? 0.0 : CUDART_INF);
+    return IS_SUM ? warp_reduce_sum(v) : warp_reduce_min(v);
 }
 
-// Full criterion of the design at xs ([k][i] layout).  MAXPRO: S (maxpro_utils.rs:38-58);
-// else min squared distance, bit-exact per pair (maximin_utils.rs:39-44).
+// Full criterion of the design at xs ([k][i] layout, row stride ns).  MAXPRO: S
+// (maxpro_utils.rs:38-58); else min squared distance, bit-exact per pair
+// (maximin_utils.rs:39-44).  Pairs are enumerated cyclically -- row i meets rows
+// i+1 .. i+half (mod n), and for even n the diameters (i, i+n/2) belong to the lower
+// half -- in items of kShiftBlock consecutive shifts whose partner rows are consecutive
+// addresses across the lanes.  Outside the unit cube (in_cube false) every term takes an
+// IEEE divide instead of the reciprocal chains.
 template <bool MAXPRO>
-__device__ __forceinline__ double block_full_score(const double* xs, int n, int d, double* scratch) {
-    double t = MAXPRO ? 0.0 : CUDART_INF;
+__device__ __forceinline__ double full_score_partial(const double* xs, int n, int d, int ns, bool in_cube) {
+    constexpr int SB = kShiftBlock;
+    double acc = 0.0, mn = CUDART_INF;
+    RecipChain ch[SB];
+#pragma unroll
+    for (int c = 0; c < SB; ++c) ch[c].reset();
+    int pushed = 0;
     const int half = (n - 1) / 2;
+    const bool even = (n & 1) == 0;
+    const int smax = half + (even ? 1 : 0);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        // cyclic pairing: row i meets rows i+1 .. i+half (mod n); for even n the
-        // diameter pairs (i, i+n/2) are taken by the lower half only
-        const int smax = half + ((n % 2 == 0 && i < n / 2) ? 1 : 0);
-        for (int s = 1; s <= smax; ++s) {
-            int j = i + s;
-            if (j >= n) j -= n;
+        const int my_smax = half + ((even && i < n / 2) ? 1 : 0);
+        for (int s0 = 1; s0 <= smax; s0 += SB) {
+            int jj[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                int j = i + s0 + c;
+                if (j >= n) j -= n;
+                jj[c] = (s0 + c <= my_smax) ? j : i;  // masked slots pair the row with itself
+            }
+            double q[SB];
+            {
+                const double xi = xs[i];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) {
+                    if (MAXPRO) q[c] = xi - xs[jj[c]];
+                    else { const double df = __dsub_rn(xi, xs[jj[c]]); q[c] = __dmul_rn(df, df); }
+                }
+            }
+            for (int k = 1; k < d; ++k) {
+                const double* xk = xs + k * ns;
+                const double xi = xk[i];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) {
+                    if (MAXPRO) q[c] *= xi - xk[jj[c]];
+                    else { const double df = __dsub_rn(xi, xk[jj[c]]); q[c] = __dadd_rn(q[c], __dmul_rn(df, df)); }
+                }
+            }
             if (MAXPRO) {
-                double p = 1.0;
-                for (int k = 0; k < d; ++k) {
-                    double df = xs[k * n + i] - xs[k * n + j];
-                    p *= df * df;
+                if (in_cube) {
+                    if (pushed == kMaxChainTerms) {
+#pragma unroll
+                        for (int c = 0; c < SB; ++c) acc += ch[c].flush();
+                        pushed = 0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < SB; ++c)
+                        if (s0 + c <= my_smax) ch[c].push(fma(q[c], q[c], kEps));
+                    ++pushed;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SB; ++c)
+                        if (s0 + c <= my_smax) acc += 1.0 / fma(q[c], q[c], kEps);
                 }
-                t += 1.0 / (p + kEps);
             } else {
-                double df = __dsub_rn(xs[i], xs[j]);
-                double sq = __dmul_rn(df, df);
-                for (int k = 1; k < d; ++k) {
-                    df = __dsub_rn(xs[k * n + i], xs[k * n + j]);
-                    sq = __dadd_rn(sq, __dmul_rn(df, df));
-                }
-                t = fmin(t, sq);
+#pragma unroll
+                for (int c = 0; c < SB; ++c)
+                    if (s0 + c <= my_smax) mn = fmin(mn, q[c]);
             }
         }
     }
-    return block_reduce(t, scratch, MAXPRO);
+    if (MAXPRO) {
+#pragma unroll
+        for (int c = 0; c < SB; ++c) acc += ch[c].flush();
+    }
+    return MAXPRO ? acc : mn;  // this thread's share; the caller reduces
 }
 
 template <bool MAXPRO>
@@ -88,86 +145,162 @@ __device__ __forceinline__ double metric_from_raw(double raw, int n, double n_pa
     return sqrt(raw);                                              // maximin_utils.rs:44
 }
 
+// Change of S when x[r1][c] and x[r2][c] are exchanged: the partial sum of this thread over
+// its partner rows.  Per partner row j (not r1, r2):
+//   A = prod_{k != c} (x[r1][k] - x[j][k]),  B likewise for r2;  u = a_c - x[j][c], v = b_c - x[j][c]
+//   pair (r1, j): p = (A u)^2 + eps -> p' = (A v)^2 + eps;   pair (r2, j): p = (B v)^2 + eps -> p' = (B u)^2 + eps
+//   1/p' - 1/p = (p - p') / (p p')
+__device__ __forceinline__ double swap_delta_partial(const double* cur, const double2* rows, int n, int d, int ns,
+                                                     int r1, int r2, int c, bool in_cube) {
+    // rows[k] = {x[r1][k], x[r2][k]}: staged once per iteration, read as 16-byte broadcasts
+    double delta = 0.0;
+    const double a_c = rows[c].x, b_c = rows[c].y;
+    for (int j0 = 2 * threadIdx.x; j0 < n; j0 += 2 * blockDim.x) {
+        const double* qx = cur + j0;
+        const double2 xc = *reinterpret_cast<const double2*>(qx + c * ns);
+        double A0 = 1.0, B0 = 1.0, A1 = 1.0, B1 = 1.0;
+        const double2* rw = rows;
+#pragma unroll 4
+        for (int k = 0; k < c; ++k, qx += ns, ++rw) {
+            const double2 x = *reinterpret_cast<const double2*>(qx);
+            const double2 ab = *rw;
+            A0 *= ab.x - x.x; B0 *= ab.y - x.x; A1 *= ab.x - x.y; B1 *= ab.y - x.y;
+        }
+        qx += ns; ++rw;
+#pragma unroll 4
+        for (int k = c + 1; k < d; ++k, qx += ns, ++rw) {
+            const double2 x = *reinterpret_cast<const double2*>(qx);
+            const double2 ab = *rw;
+            A0 *= ab.x - x.x; B0 *= ab.y - x.x; A1 *= ab.x - x.y; B1 *= ab.y - x.y;
+        }
+        double nm[2], dn[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = j0 + h;
+            const double A = h ? A1 : A0, B = h ? B1 : B0, xjc = h ? xc.y : xc.x;
+            const double uu = a_c - xjc, vv = b_c - xjc;
+            const double au = A * uu, av = A * vv, bu = B * uu, bv = B * vv;
+            const double p1 = fma(au, au, kEps), p1n = fma(av, av, kEps);
+            const double p2 = fma(bv, bv, kEps), p2n = fma(bu, bu, kEps);
+            const bool live = j != r1 && j != r2 && j < n;
+            if (in_cube) {
+                // both changes over one denominator: (p1-p1')/(p1 p1') + (p2-p2')/(p2 p2')
+                const double d1 = p1 * p1n, d2 = p2 * p2n;
+                nm[h] = live ? fma(p1 - p1n, d2, (p2 - p2n) * d1) : 0.0;
+                dn[h] = live ? d1 * d2 : 1.0;  // >= 1e-48 in the unit cube
+            } else if (live) {
+                delta += (p1 - p1n) / (p1 * p1n) + (p2 - p2n) / (p2 * p2n);
+            }
+        }
+        if (in_cube) delta += fma(nm[0], dn[1], nm[1] * dn[0]) / (dn[0] * dn[1]);  // denominator >= 1e-96
+    }
+    return delta;
+}
+
+// What warp 0 tells the other warps about an iteration.
+struct Decision {
+    int accept;
+    int best_mode;  // 0 none, 1 replay the move log into the HBM best, 2 rewrite the HBM best in full
+    int log_n;      // entries to replay (best_mode 1)
+    int pad;
+};
+constexpr int kLogCap = 256;  // accepted swaps remembered between two global bests
+
 template <bool MAXPRO>
 __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     extern __shared__ __align__(16) double smem_d[];
     const int n = (int)p.n, d = (int)p.d, nd = n * d;
-    double* cur = smem_d;                          // [k][i]
-    double* cand = p.swap ? cur : smem_d + nd;     // jitter needs the proposal beside the current
-    double* scratch = smem_d + (p.swap ? nd : 2 * nd);  // 32 doubles of reduce scratch
+    const int ns = (n + 1) & ~1;                      // even row stride: 16-byte partner loads
+    const int dns = d * ns;
+    double* cur = smem_d;                             // [k][i]
+    double* cand = p.swap ? cur : smem_d + dns;       // jitter needs the proposal beside the current
+    double* part = smem_d + (p.swap ? dns : 2 * dns);   // 32 doubles: warp partials of a reduction
+    Decision* dec = reinterpret_cast<Decision*>(part + 32);
+    uint4* draws = reinterpret_cast<uint4*>(part + 34);   // kDrawBatch swap draws
+    double2* rows = reinterpret_cast<double2*>(draws + kDrawBatch);  // [d] {x[r1][k], x[r2][k]} of the move
+    ushort4* mlog = reinterpret_cast<ushort4*>(rows + d);            // kLogCap accepted moves {r1, r2, c}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (unsigned long long chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
         const unsigned long long stream = p.seed + chain;
         const uint32_t key0 = (uint32_t)stream, key1 = (uint32_t)(stream >> 32);
         __syncthreads();
+        if (ns != n)
+            for (int k = threadIdx.x; k < d; k += blockDim.x) { cur[k * ns + n] = 0.0; cand[k * ns + n] = 0.0; }
+        int ok = 1;
         for (int e = threadIdx.x; e < nd; e += blockDim.x) {
-            int i = e / d, k = e - i * d;
-            cur[k * n + i] = p.design[e];  // anneal.rs:89
+            const int i = e / d, k = e - i * d;
+            const double v = p.design[e];
+            ok &= (v >= 0.0 && v <= 1.0) ? 1 : 0;
+            cur[k * ns + i] = v;  // anneal.rs:89
         }
+        // reciprocal chains and shared denominators are range-safe only in the unit cube
+        const bool in_cube = __syncthreads_and(ok) != 0;
+        publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
         __syncthreads();
-        double raw_cur = block_full_score<MAXPRO>(cur, n, d, scratch);
-        double cur_metric = metric_from_raw<MAXPRO>(raw_cur, n, p.n_pairs, p.inv_d);  // :90
-        double global_best = cur_metric;                                                // :94
-        bool materialized = false, synced = true;  // HBM copy exists / equals the current design
-        double temp = p.t0;                                                             // :81
+        // chain state, kept by warp 0 (every lane holds the same values)
+        double raw_cur = 0.0, cur_metric = 0.0, global_best = 0.0;
+        double temp = p.t0;                                                             // anneal.rs:81
+        bool materialized = false, overflow = false;  // HBM best exists / the move log lost entries
+        int log_n = 0;                                // moves accepted since the HBM best equalled cur
+        if (warp == 0) {
+            raw_cur = warp0_total<MAXPRO>(part);
+            cur_metric = metric_from_raw<MAXPRO>(raw_cur, n, p.n_pairs, p.inv_d);       // :90
+            global_best = cur_metric;                                                   // :94
+        }
+        __syncthreads();  // part[] is free again
         double* best_out = p.best_design + chain * (unsigned long long)nd;
         unsigned long long until_resync = p.resync;  // iterations until the next full re-sum of S
 
         for (unsigned long long t = 0; t < p.iters; ++t) {
-            double raw_new, u;
+            // ---- propose and score: every thread ends up with its share `mine` of the reduction
+            double mine, u = 0.0;
             int r1 = 0, r2 = 0, c = 0;
+            bool incremental = false, applied = false;
             if (p.swap) {
-                Philox4 w = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0u, kDomainSwap, key0, key1);
+                const unsigned int slot = (unsigned int)t & (kDrawBatch - 1);
+                if (slot == 0) {
+                    // every reader of the previous batch is past a barrier of iteration t-1
+                    for (int q = threadIdx.x; q < kDrawBatch; q += blockDim.x) {
+                        const unsigned long long tq = t + (unsigned long long)q;
+                        const Philox4 w = philox4x32_10((uint32_t)tq, (uint32_t)(tq >> 32), 0u, kDomainSwap, key0, key1);
+                        draws[q] = make_uint4(w.x, w.y, w.z, w.w);
+                    }
+                    __syncthreads();
+                }
+                const uint4 w = draws[slot];
                 r1 = (int)mulhi_bound(w.x, (uint32_t)n);  // anneal.rs:29
                 r2 = (int)mulhi_bound(w.y, (uint32_t)n);  // :30
                 c = (int)mulhi_bound(w.z, (uint32_t)d);   // :31
                 u = (double)w.w * 0x1p-32;
                 if (MAXPRO && --until_resync != 0) {
                     // incremental: only pairs (r1,j), (r2,j), j not in {r1,r2}, change
-                    double delta = 0.0;
+                    incremental = true;
+                    mine = 0.0;
                     if (r1 != r2) {
-                        const double a_c = cur[c * n + r1], b_c = cur[c * n + r2];
-                        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                            if (j == r1 || j == r2) continue;
-                            double A = 1.0, B = 1.0;
-                            for (int k = 0; k < d; ++k) {
-                                if (k == c) continue;
-                                const double xj = cur[k * n + j];
-                                A *= cur[k * n + r1] - xj;
-                                B *= cur[k * n + r2] - xj;
-                            }
-                            const double xjc = cur[c * n + j];
-                            const double uu = a_c - xjc, vv = b_c - xjc;
-                            const double au = A * uu, av = A * vv, bu = B * uu, bv = B * vv;
-                            const double p1 = fma(au, au, kEps), p1n = fma(av, av, kEps);
-                            const double p2 = fma(bv, bv, kEps), p2n = fma(bu, bu, kEps);
-                            // 1/p' - 1/p = (p - p')/(p p')
-                            delta += (p1 - p1n) / (p1 * p1n) + (p2 - p2n) / (p2 * p2n);
-                        }
+                        // the previous iteration's readers of rows[] are past its barriers
+                        for (int k = threadIdx.x; k < d; k += blockDim.x) rows[k] = make_double2(cur[k * ns + r1], cur[k * ns + r2]);
+                        __syncthreads();
+                        mine = swap_delta_partial(cur, rows, n, d, ns, r1, r2, c, in_cube);
                     }
-                    delta = block_reduce(delta, scratch, true);
-                    raw_new = raw_cur + delta;
+                    publish_partial<true>(mine, part);
                 } else {
                     until_resync = p.resync;
-                    // maximin, or the periodic full re-sum: apply, score, (maybe) undo
-                    __syncthreads();
+                    // maximin, or the periodic full re-sum: apply the move, score; warp 0 undoes a rejected one
+                    applied = true;
+                    __syncthreads();  // the previous iteration's best write-out still reads cur
                     if (threadIdx.x == 0) {
-                        double v1 = cur[c * n + r1], v2 = cur[c * n + r2];
-                        cur[c * n + r1] = v2; cur[c * n + r2] = v1;  // anneal.rs:34-39
+                        double v1 = cur[c * ns + r1], v2 = cur[c * ns + r2];
+                        cur[c * ns + r1] = v2; cur[c * ns + r2] = v1;  // anneal.rs:34-39
                     }
                     __syncthreads();
-                    raw_new = block_full_score<MAXPRO>(cur, n, d, scratch);
-                    __syncthreads();
-                    if (threadIdx.x == 0) {  // undo; re-applied below on acceptance
-                        double v1 = cur[c * n + r1], v2 = cur[c * n + r2];
-                        cur[c * n + r1] = v2; cur[c * n + r2] = v1;
-                    }
-                    __syncthreads();
+                    publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
                 }
             } else {
                 // jitter: element e = i*d + k (row-major, the reference's iteration order,
                 // anneal.rs:102-107) takes word e%4 of block e/4
                 const double two_step = __dadd_rn(p.step, p.step);
+                int jok = 1;
                 for (int blk = threadIdx.x; blk * 4 < nd; blk += blockDim.x) {
                     Philox4 w = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)blk, kDomainJit, key0, key1);
                     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
@@ -178,59 +311,77 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                             int i = e / d, k = e - i * d;
                             double uu = (double)ws[q] * 0x1p-32;
                             double delta = __dsub_rn(__dmul_rn(uu, two_step), p.step);
-                            double v = __dadd_rn(cur[k * n + i], delta);
+                            double v = __dadd_rn(cur[k * ns + i], delta);
+                            jok &= (v == v) ? 1 : 0;  // clamp passes NaN through
                             v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);  // clamp(0.0, 1.0)
-                            cand[k * n + i] = v;
+                            cand[k * ns + i] = v;
                         }
                     }
                 }
-                Philox4 wa = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0u, kDomainJacc, key0, key1);
-                u = (double)wa.x * 0x1p-32;
-                __syncthreads();
-                raw_new = block_full_score<MAXPRO>(cand, n, d, scratch);
+                if (warp == 0) {
+                    Philox4 wa = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0u, kDomainJacc, key0, key1);
+                    u = (double)wa.x * 0x1p-32;
+                }
+                // every coordinate of the proposal has just been clamped into [0, 1]
+                const bool cand_in_cube = __syncthreads_and(jok) != 0;
+                publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cand, n, d, ns, cand_in_cube), part);
             }
+            __syncthreads();  // partials are in; nobody reads cur / cand for scoring any more
 
-            // Metropolis (anneal.rs:110-128); every thread evaluates the same numbers
-            const double new_metric = metric_from_raw<MAXPRO>(raw_new, n, p.n_pairs, p.inv_d);
-            double diff = new_metric - cur_metric;
-            if (!p.minimize) diff *= -1.0;
-            const double p_acc = diff < 0.0 ? 1.0 : exp(-diff / temp);
-            const bool accept = u < p_acc;
-            __syncthreads();
-            if (accept) {
-                if (p.swap) {
-                    if (threadIdx.x == 0) {
-                        double v1 = cur[c * n + r1], v2 = cur[c * n + r2];
-                        cur[c * n + r1] = v2; cur[c * n + r2] = v1;
-                    }
-                } else {
-                    for (int e = threadIdx.x; e < nd; e += blockDim.x) cur[e] = cand[e];
+            // ---- Metropolis (anneal.rs:110-128) and the global best (:131-136), warp 0 only
+            if (warp == 0) {
+                const double total = warp0_total<MAXPRO>(part);
+                const double raw_new = incremental ? raw_cur + total : total;
+                const double new_metric = metric_from_raw<MAXPRO>(raw_new, n, p.n_pairs, p.inv_d);
+                double diff = new_metric - cur_metric;
+                if (!p.minimize) diff *= -1.0;
+                const double p_acc = diff < 0.0 ? 1.0 : exp(-diff / temp);
+                const bool accept = u < p_acc;
+                if (p.swap && accept != applied && lane == 0) {
+                    // apply an accepted incremental move / undo a rejected applied one
+                    double v1 = cur[c * ns + r1], v2 = cur[c * ns + r2];
+                    cur[c * ns + r1] = v2; cur[c * ns + r2] = v1;
                 }
-                cur_metric = new_metric;
-                raw_cur = raw_new;
+                if (accept) { cur_metric = new_metric; raw_cur = raw_new; }
+                const bool improves = (p.minimize && cur_metric < global_best) || (!p.minimize && cur_metric > global_best);
+                int best_mode = 0;
+                if (accept && p.swap) {
+                    if (log_n < kLogCap) {
+                        if (lane == 0) mlog[log_n] = make_ushort4((unsigned short)r1, (unsigned short)r2, (unsigned short)c, 0);
+                        ++log_n;
+                    } else {
+                        overflow = true;
+                    }
+                }
+                if (improves) {
+                    best_mode = (p.swap && materialized && !overflow) ? 1 : 2;
+                    if (lane == 0) { dec->log_n = log_n; }
+                    global_best = cur_metric;
+                    materialized = true; overflow = false; log_n = 0;
+                }
+                if (lane == 0) { dec->accept = accept ? 1 : 0; dec->best_mode = best_mode; }
+                temp *= p.cooling;  // anneal.rs:139
+            }
+            __syncthreads();
+            const int accept = dec->accept, best_mode = dec->best_mode;
+            if (accept && !p.swap) {
+                for (int e = threadIdx.x; e < dns; e += blockDim.x) cur[e] = cand[e];
                 __syncthreads();
             }
-            // strict-improvement global best (anneal.rs:131-136)
-            const bool improves = (p.minimize && cur_metric < global_best) || (!p.minimize && cur_metric > global_best);
-            if (improves) {
-                if (p.swap && materialized && synced && accept) {
-                    if (threadIdx.x == 0) {
-                        best_out[r1 * d + c] = cur[c * n + r1];
-                        best_out[r2 * d + c] = cur[c * n + r2];
-                    }
-                } else {
-                    for (int e = threadIdx.x; e < nd; e += blockDim.x) {
-                        int i = e / d, k = e - i * d;
-                        best_out[e] = cur[k * n + i];
-                    }
+            if (best_mode == 1) {
+                // the HBM best differs from cur only where a logged move touched it
+                const int ln = dec->log_n;
+                for (int e = threadIdx.x; e < ln; e += blockDim.x) {
+                    const ushort4 m = mlog[e];
+                    best_out[(int)m.x * d + m.z] = cur[(int)m.z * ns + m.x];
+                    best_out[(int)m.y * d + m.z] = cur[(int)m.z * ns + m.y];
                 }
-                global_best = cur_metric;
-                materialized = true;
-                synced = true;
-            } else if (accept) {
-                synced = false;
+            } else if (best_mode == 2) {
+                for (int e = threadIdx.x; e < nd; e += blockDim.x) {
+                    int i = e / d, k = e - i * d;
+                    best_out[e] = cur[k * ns + i];
+                }
             }
-            temp *= p.cooling;  // anneal.rs:139
         }
         if (threadIdx.x == 0) {
             p.best_metric[chain] = global_best;
@@ -240,12 +391,15 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
 }
 
 size_t anneal_smem_bytes(unsigned long long n, unsigned long long d, int swap) {
-    return (size_t)(n * d * (swap ? 1 : 2) + 32 + 2) * sizeof(double);
+    const unsigned long long ns = (n + 1) & ~1ull;
+    return (size_t)(ns * d * (swap ? 1 : 2) + 34 + 2 * d) * sizeof(double) + (size_t)kDrawBatch * sizeof(uint4) + (size_t)kLogCap * sizeof(ushort4);
 }
 
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap) {
-    return n >= 1 && d >= 1 && n < (1ull << 31) / (d ? d : 1) && anneal_smem_bytes(n, d, swap) <= kSmemBudget;
+    return n >= 1 && d >= 1 && n < (1ull << 30) / (d ? d : 1) && n <= 65535 && d <= 65535 && anneal_smem_bytes(n, d, swap) <= kSmemBudget;
 }
+
+static int round_up_32(unsigned long long v) { return (int)((v + 31) / 32 * 32); }
 
 cudaError_t launch_anneal(const AnnealLaunch& L) {
     AnnealParams p;
@@ -258,7 +412,17 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     p.inv_d = 1.0 / (double)L.d;
     p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved;
     size_t smem = anneal_smem_bytes(L.n, L.d, L.swap);
-    int threads = L.n <= 64 ? 64 : (L.n <= 128 ? 128 : (L.n <= 512 ? 256 : 512));
+    int threads;
+    if (L.swap && L.metric == 0) {
+        // incremental steps: one thread per two partner rows
+        threads = round_up_32((L.n + 1) / 2);
+    } else {
+        // full re-score every iteration: one thread per row
+        threads = round_up_32(L.n);
+    }
+    if (threads < 32) threads = 32;
+    if (threads > 512) threads = 512;
+    if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
     cudaError_t e;
     if (L.metric == 0) {
