@@ -1,0 +1,184 @@
+// Device helpers shared by the annealing kernels (anneal.cu: every mode; anneal_pipe.cu: the
+// software-pipelined swap/MaxPro chain).  See anneal.cu for the reference mapping.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+#include "kernels.h"
+
+namespace mp {
+
+constexpr int kDrawBatch = 128;  // swap iterations whose draws are generated together
+constexpr int kShiftBlock = 8;   // cyclic shifts per full-score work item
+
+struct AnnealParams {
+    const double* design;  // [n][d] row-major start design (shared by all chains)
+    unsigned long long n, d, iters, seed, n_chains;
+    double t0, cooling, step;
+    int minimize, swap;
+    unsigned long long resync;
+    double n_pairs, inv_d;
+    double* best_design;        // [n_chains][n*d] row-major, valid where improved[c] != 0
+    double* best_metric;        // [n_chains]
+    unsigned int* improved;     // [n_chains]
+};
+
+// Deterministic block reduction in two halves.  Every thread: lane tree, lane 0 publishes the
+// warp's partial.  After a barrier, warp 0 alone folds the partials (a second lane tree) --
+// the chain's scalar state and the Metropolis arithmetic (pow, exp, two divides) live in warp
+// 0 only, so the other warps spend no issue slots on it.
+template <bool IS_SUM>
+__device__ __forceinline__ void publish_partial(double v, double* part) {
+    v = IS_SUM ? warp_reduce_sum(v) : warp_reduce_min(v);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+}
+template <bool IS_SUM>
+__device__ __forceinline__ double warp_total(const double* part, int nw) {  // nw <= 32 partials
+    const int lane = threadIdx.x & 31;
+    double v = lane < nw ? part[lane] : (IS_SUM ? 0.0 : CUDART_INF);
+    return IS_SUM ? warp_reduce_sum(v) : warp_reduce_min(v);
+}
+
+// Full criterion of the design at xs ([k][i] layout, row stride ns).  MAXPRO: S
+// (maxpro_utils.rs:38-58); else min squared distance, bit-exact per pair
+// (maximin_utils.rs:39-44).  Pairs are enumerated cyclically -- row i meets rows
+// i+1 .. i+half (mod n), and for even n the diameters (i, i+n/2) belong to the lower
+// half -- in items of kShiftBlock consecutive shifts whose partner rows are consecutive
+// addresses across the lanes.  Outside the unit cube (in_cube false) every term takes an
+// IEEE divide instead of the reciprocal chains.
+template <bool MAXPRO, int SB = kShiftBlock>
+__device__ __forceinline__ double full_score_partial(const double* xs, int n, int d, int ns, bool in_cube) {
+    double acc = 0.0, mn = CUDART_INF;
+    RecipChain ch[SB];
+#pragma unroll
+    for (int c = 0; c < SB; ++c) ch[c].reset();
+    int pushed = 0;
+    const int half = (n - 1) / 2;
+    const bool even = (n & 1) == 0;
+    const int smax = half + (even ? 1 : 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int my_smax = half + ((even && i < n / 2) ? 1 : 0);
+        for (int s0 = 1; s0 <= smax; s0 += SB) {
+            int jj[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                int j = i + s0 + c;
+                if (j >= n) j -= n;
+                jj[c] = (s0 + c <= my_smax) ? j : i;  // masked slots pair the row with itself
+            }
+            double q[SB];
+            {
+                const double xi = xs[i];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) {
+                    if (MAXPRO) q[c] = xi - xs[jj[c]];
+                    else { const double df = __dsub_rn(xi, xs[jj[c]]); q[c] = __dmul_rn(df, df); }
+                }
+            }
+            for (int k = 1; k < d; ++k) {
+                const double* xk = xs + k * ns;
+                const double xi = xk[i];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) {
+                    if (MAXPRO) q[c] *= xi - xk[jj[c]];
+                    else { const double df = __dsub_rn(xi, xk[jj[c]]); q[c] = __dadd_rn(q[c], __dmul_rn(df, df)); }
+                }
+            }
+            if (MAXPRO) {
+                if (in_cube) {
+                    if (pushed == kMaxChainTerms) {
+#pragma unroll
+                        for (int c = 0; c < SB; ++c) acc += ch[c].flush();
+                        pushed = 0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < SB; ++c)
+                        if (s0 + c <= my_smax) ch[c].push(fma(q[c], q[c], kEps));
+                    ++pushed;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SB; ++c)
+                        if (s0 + c <= my_smax) acc += 1.0 / fma(q[c], q[c], kEps);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < SB; ++c)
+                    if (s0 + c <= my_smax) mn = fmin(mn, q[c]);
+            }
+        }
+    }
+    if (MAXPRO) {
+#pragma unroll
+        for (int c = 0; c < SB; ++c) acc += ch[c].flush();
+    }
+    return MAXPRO ? acc : mn;  // this thread's share; the caller reduces
+}
+
+template <bool MAXPRO>
+__device__ __forceinline__ double metric_from_raw(double raw, int n, double n_pairs, double inv_d) {
+    if (MAXPRO) return n < 2 ? 0.0 : pow(raw / n_pairs, inv_d);  // maxpro_utils.rs:75-82
+    return sqrt(raw);                                              // maximin_utils.rs:44
+}
+
+// Change of S when x[r1][c] and x[r2][c] are exchanged: the partial sum of this thread over
+// its partner rows.  Per partner row j (not r1, r2):
+//   A = prod_{k != c} (x[r1][k] - x[j][k]),  B likewise for r2;  u = a_c - x[j][c], v = b_c - x[j][c]
+//   pair (r1, j): p = (A u)^2 + eps -> p' = (A v)^2 + eps;   pair (r2, j): p = (B v)^2 + eps -> p' = (B u)^2 + eps
+//   1/p' - 1/p = (p - p') / (p p')
+// e1, e2: two more partner rows to leave out (-1 = none); `workers` threads share the rows.
+__device__ __forceinline__ double swap_delta_partial(const double* cur, const double2* rows, int n, int d, int ns,
+                                                     int r1, int r2, int c, bool in_cube, int e1, int e2, int workers) {
+    // rows[k] = {x[r1][k], x[r2][k]}: staged once per iteration, read as 16-byte broadcasts
+    double delta = 0.0;
+    const double a_c = rows[c].x, b_c = rows[c].y;
+    for (int j0 = 2 * threadIdx.x; j0 < n; j0 += 2 * workers) {
+        const double* qx = cur + j0;
+        const double2 xc = *reinterpret_cast<const double2*>(qx + c * ns);
+        double A0 = 1.0, B0 = 1.0, A1 = 1.0, B1 = 1.0;
+        const double2* rw = rows;
+#pragma unroll 4
+        for (int k = 0; k < c; ++k, qx += ns, ++rw) {
+            const double2 x = *reinterpret_cast<const double2*>(qx);
+            const double2 ab = *rw;
+            A0 *= ab.x - x.x; B0 *= ab.y - x.x; A1 *= ab.x - x.y; B1 *= ab.y - x.y;
+        }
+        qx += ns; ++rw;
+#pragma unroll 4
+        for (int k = c + 1; k < d; ++k, qx += ns, ++rw) {
+            const double2 x = *reinterpret_cast<const double2*>(qx);
+            const double2 ab = *rw;
+            A0 *= ab.x - x.x; B0 *= ab.y - x.x; A1 *= ab.x - x.y; B1 *= ab.y - x.y;
+        }
+        double nm[2], dn[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = j0 + h;
+            const double A = h ? A1 : A0, B = h ? B1 : B0, xjc = h ? xc.y : xc.x;
+            const double uu = a_c - xjc, vv = b_c - xjc;
+            const double au = A * uu, av = A * vv, bu = B * uu, bv = B * vv;
+            const double p1 = fma(au, au, kEps), p1n = fma(av, av, kEps);
+            const double p2 = fma(bv, bv, kEps), p2n = fma(bu, bu, kEps);
+            const bool live = j != r1 && j != r2 && j != e1 && j != e2 && j < n;
+            if (in_cube) {
+                // both changes over one denominator: (p1-p1')/(p1 p1') + (p2-p2')/(p2 p2')
+                const double d1 = p1 * p1n, d2 = p2 * p2n;
+                nm[h] = live ? fma(p1 - p1n, d2, (p2 - p2n) * d1) : 0.0;
+                dn[h] = live ? d1 * d2 : 1.0;  // >= 1e-48 in the unit cube
+            } else if (live) {
+                delta += (p1 - p1n) / (p1 * p1n) + (p2 - p2n) / (p2 * p2n);
+            }
+        }
+        if (in_cube) delta += fma(nm[0], dn[1], nm[1] * dn[0]) / (dn[0] * dn[1]);  // denominator >= 1e-96
+    }
+    return delta;
+}
+
+// What warp 0 tells the other warps about an iteration.
+struct Decision {
+    int accept;
+    int best_mode;  // 0 none, 1 replay the move log into the HBM best, 2 rewrite the HBM best in full
+    int log_n;      // entries to replay (best_mode 1)
+    int pad;
+};
+constexpr int kLogCap = 256;  // accepted swaps remembered between two global bests
+
+}  // namespace mp

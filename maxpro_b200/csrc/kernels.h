@@ -80,6 +80,9 @@ struct AnnealLaunch {
 };
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap);
 cudaError_t launch_anneal(const AnnealLaunch& L);
+// swap moves on MaxPro as a two-stage pipeline (anneal_pipe.cu); launch_anneal dispatches to it
+bool anneal_pipe_supported(unsigned long long n, unsigned long long d, int metric, int swap);
+cudaError_t launch_anneal_pipe(const AnnealLaunch& L);
 
 // ---- K4: greedy ordering ------------------------------------------------------------
 struct OrderLaunch {
