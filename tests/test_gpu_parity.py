@@ -296,6 +296,21 @@ def test_anneal_chains_and_contract():
     assert np.array_equal(got, ref) and math.isclose(best, ref_best, rel_tol=REL)
 
 
+@pytest.mark.parametrize("n,d,iters,cooling", [(200, 4, 600, 0.99), (120, 6, 500, 0.97), (64, 3, 2500, 0.995)])
+def test_anneal_swap_pipeline_matches_oracle(n, d, iters, cooling, monkeypatch):
+    """Swap moves on MaxPro run as a two-stage pipeline (anneal_pipe.cu): speculative wide half,
+    special terms for the rows of the previous move, log-threshold acceptance, series for small
+    changes of S.  The trajectory must still be the oracle's (full re-score + pow + exp), and
+    the plain kernel (MAXPRO_NO_ANNEAL_PIPE=1) must agree too."""
+    x = oracle.generate_lhd(n, d, 2024)
+    ref, ref_best = oracle.anneal_lhd(x, iters, 1.0, cooling, METRIC_MAXPRO, True, 99, True)
+    got, best, _ = engine.anneal_lhd(x, iters, 1.0, cooling, METRIC_MAXPRO, True, 99, True, n_chains=1)
+    assert np.array_equal(got, ref) and math.isclose(best, ref_best, rel_tol=REL)
+    monkeypatch.setenv("MAXPRO_NO_ANNEAL_PIPE", "1")
+    got2, best2, _ = engine.anneal_lhd(x, iters, 1.0, cooling, METRIC_MAXPRO, True, 99, True, n_chains=1)
+    assert np.array_equal(got2, ref) and math.isclose(best2, ref_best, rel_tol=REL)
+
+
 def test_anneal_large_design_runs():
     x = oracle.generate_lhd(1000, 20, 42)  # C4 shape: 160 KB of shared memory per chain
     got, best, _ = engine.anneal_lhd(x, 50, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, n_chains=4)
