@@ -116,3 +116,27 @@ def test_c_abi_argument_errors_before_device():
     assert L.maxpro_generate_lhd(3, 0, 1, _lib.dptr(out)) == _lib.ERR_INVALID  # lhd.rs:106
     assert L.maxpro_order_design(None, 0, 3, 0, 1, None, None) == _lib.OK      # order.rs:38-46
     assert L.maxpro_anneal_lhd(None, 0, 3, 5, 1.0, 0.9, 0, 1, 1, 1, 1, None, None, None) == _lib.OK  # anneal.rs:69-71
+
+
+def test_rust_crate_declares_only_exported_symbols_with_header_arity():
+    """rust/ is source only (no cargo in the image): at least its extern "C" block must name
+    symbols the library exports, with as many parameters as the header declares."""
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    block = ffi[ffi.index('unsafe extern "C" {'):]
+    block = block[:block.index("\n}")]
+    decls = re.findall(r"pub fn (maxpro_[a-z0-9_]+)\s*\(([^)]*)\)", block, flags=re.S)
+    assert len(decls) >= 8
+    hdr = open(os.path.join(ROOT, "include", "maxpro_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name, params in decls:
+        assert name in _lib.EXPORTS, name
+        m = re.search(r"\b%s\s*\(([^)]*)\)" % name, hdr, flags=re.S)
+        assert m, name
+        c_params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        rust_params = [p for p in params.split(",") if p.strip()]
+        assert len(c_params) == len(rust_params), (name, c_params, rust_params)
+    # build.rs compiles exactly the sources the Makefile does
+    mk = open(os.path.join(ROOT, "maxpro_b200", "csrc", "Makefile")).read()
+    srcs = re.search(r"^SRCS\s*:=\s*(.*)$", mk, flags=re.M).group(1).split()
+    build_rs = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    assert sorted(re.findall(r'"([a-z_]+\.cu)"', build_rs)) == sorted(srcs)
