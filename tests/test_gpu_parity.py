@@ -311,6 +311,52 @@ def test_anneal_swap_pipeline_matches_oracle(n, d, iters, cooling, monkeypatch):
     assert np.array_equal(got2, ref) and math.isclose(best2, ref_best, rel_tol=REL)
 
 
+@pytest.mark.parametrize("n,d", [(4, 1), (5, 2), (7, 3), (33, 1), (51, 7), (97, 2)])
+def test_anneal_swap_pipeline_edge_shapes(n, d):
+    """Tiny and odd shapes: almost every pair of consecutive moves shares a row at n = 4..7 (the
+    pipeline runs drained), odd n exercises the padded row, d = 1 has no untouched dimension."""
+    x = oracle.generate_lhd(n, d, 5)
+    ref, ref_best = oracle.anneal_lhd(x, 700, 1.0, 0.98, METRIC_MAXPRO, True, 17, True)
+    got, best, _ = engine.anneal_lhd(x, 700, 1.0, 0.98, METRIC_MAXPRO, True, 17, True, n_chains=1)
+    assert math.isclose(best, ref_best, rel_tol=REL)
+    if d == 1:
+        # one dimension: a swap permutes the same point set, the criterion cannot change, and the
+        # reference's accept/reject is decided by the rounding of two differently ordered sums --
+        # only the invariants are comparable
+        assert np.array_equal(np.sort(got[:, 0]), np.sort(x[:, 0]))
+        assert math.isclose(oracle.maxpro_criterion(got), oracle.maxpro_criterion(x), rel_tol=REL)
+    else:
+        assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("swap", [True, False])
+def test_anneal_design_outside_unit_cube(swap):
+    """Designs a caller supplies may leave [0,1]^d: the reciprocal chains and shared denominators
+    are not range-safe there, the kernels must fall back to IEEE divides (and jitter clamps)."""
+    x = oracle.generate_lhd(40, 3, 11) * 7.0 - 2.0
+    ref, ref_best = oracle.anneal_lhd(x, 400, 1.0, 0.99, METRIC_MAXPRO, True, 21, swap)
+    got, best, _ = engine.anneal_lhd(x, 400, 1.0, 0.99, METRIC_MAXPRO, True, 21, swap, n_chains=1)
+    assert np.array_equal(got, ref) and math.isclose(best, ref_best, rel_tol=REL)
+
+
+def test_anneal_many_chains_large_design_properties():
+    """C4 shape at a bounded size: every chain starts from the same design, so the best of 296
+    chains is never worse than the start, is an LHD (swaps permute columns), re-scores to the
+    reported metric, and the call is deterministic."""
+    x = oracle.generate_lhd(1000, 20, 42)
+    start = oracle.maxpro_criterion(x)
+    got, best, chain = engine.anneal_lhd(x, 300, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, n_chains=296)
+    assert best <= start and lhd_bins_ok(got)
+    assert math.isclose(oracle.maxpro_criterion(got), best, rel_tol=REL)
+    for k in range(20):  # column k of the result is a permutation of column k of the start
+        assert np.array_equal(np.sort(got[:, k]), np.sort(x[:, k]))
+    got2, best2, chain2 = engine.anneal_lhd(x, 300, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, n_chains=296)
+    assert chain2 == chain and best2 == best and np.array_equal(got2, got)
+    # the winning chain alone reproduces the result (chain c draws from stream seed + c)
+    got3, best3, _ = engine.anneal_lhd(x, 300, 1.0, 0.99, METRIC_MAXPRO, True, 43 + chain, True, n_chains=1)
+    assert best3 == best and np.array_equal(got3, got)
+
+
 def test_anneal_large_design_runs():
     x = oracle.generate_lhd(1000, 20, 42)  # C4 shape: 160 KB of shared memory per chain
     got, best, _ = engine.anneal_lhd(x, 50, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, n_chains=4)
