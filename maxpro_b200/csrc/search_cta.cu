@@ -3,7 +3,7 @@
 // Replaces the same reference code as the other search kernels: generate_lhd
 // (src/lhd.rs:97-132) -> criterion (src/maxpro_utils.rs:28-83 / src/maximin_utils.rs:54-67)
 // -> fold (src/lib.rs:76-98), for designs too big for the thread-group kernels.  The
-// candidate lives in shared memory, dimension-major X[k][i] with an odd row stride; nothing but
+// candidate lives in shared memory, dimension-major X[k][i] (row stride: cta_row_stride); nothing but
 // one 16-byte record per CTA reaches HBM.
 //
 // Generation (LHD-Philox v1, bit-identical to generate.cu / the oracle):
@@ -29,13 +29,29 @@ constexpr int kTileRows = 64;  // 2 rows per lane
 constexpr int kJB = 8;         // columns per block
 
 struct CtaParams {
-    int n, d, ns;  // ns = odd row stride of the [k][i] layout
+    int n, d, ns;  // ns = row stride of the [k][i] layout (cta_row_stride)
     unsigned long long seed, lo, hi;
     double c1, c0, n_pairs, inv_d;
     BestRec* block_best;
     unsigned int* done_counter;
     BestRec* result;
 };
+
+// Eight consecutive partner coordinates as four 16-byte warp-wide broadcasts.  The row stride is
+// even and a block starts at a multiple of 8, so the address is 16-byte aligned; a block that
+// runs past row n-1 reads the stride padding (or the next dimension) and is masked by the caller.
+__device__ __forceinline__ void load_block(double (&bv)[kJB], const double* src) {
+#pragma unroll
+    for (int c = 0; c < kJB; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(src + c);
+        bv[c] = v.x; bv[c + 1] = v.y;
+    }
+}
+
+// Row stride of the [k][i] layout: n rounded up to a multiple of 8 (whole partner blocks), plus 2.
+// Even, so partner blocks are 16-byte aligned; 2 or 10 modulo 16, so the lanes that walk one
+// column each in generation phase 2 (stride ns doubles) fall into 8 different bank groups.
+__host__ __device__ __forceinline__ unsigned long long cta_row_stride(unsigned long long n) { return (n + 7) / 8 * 8 + 2; }
 
 template <bool MAXPRO>
 __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p) {
@@ -102,9 +118,11 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
                 // dimension 0, then the rest
                 {
                     const double a0 = xs[i0c], a1 = xs[i1c];
+                    double bv[kJB];
+                    load_block(bv, xs + j0);
 #pragma unroll
                     for (int c = 0; c < kJB; ++c) {
-                        const double b = xs[min(j0 + c, n - 1)];
+                        const double b = bv[c];
                         if (MAXPRO) { prod[0][c] = a0 - b; prod[1][c] = a1 - b; }
                         else {
                             double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
@@ -115,9 +133,11 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
                 for (int k = 1; k < d; ++k) {
                     const double* xk = xs + k * ns;
                     const double a0 = xk[i0c], a1 = xk[i1c];
+                    double bv[kJB];
+                    load_block(bv, xk + j0);
 #pragma unroll
                     for (int c = 0; c < kJB; ++c) {
-                        const double b = xk[min(j0 + c, n - 1)];
+                        const double b = bv[c];
                         if (MAXPRO) { prod[0][c] *= (a0 - b); prod[1][c] *= (a1 - b); }
                         else {
                             double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
 }
 
 static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) {
-    unsigned long long ns = n | 1ull;
+    unsigned long long ns = cta_row_stride(n);
     return (size_t)(((d * ns * 10 + 15) / 16) * 16 + 4 * sizeof(double));
 }
 
@@ -198,7 +218,7 @@ int search_cta_grid(unsigned long long n, unsigned long long d, int sms) {
 
 cudaError_t launch_search_cta(const SearchLaunch& L) {
     CtaParams p;
-    p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)(L.n | 1ull);
+    p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)cta_row_stride(L.n);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.c1 = ldexp(1.0 / (double)L.n, -32);
     p.c0 = 0.5 * p.c1;
