@@ -339,7 +339,12 @@ def main():
                          "each step scores fresh candidate indices, nothing is cached between steps",
                    "last_winner": {"score": last_score, "index": last_index}},
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": None,
+                     "frac": achieved_tflops / peak_tflops if peak_tflops else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full`
+                     # (profiles/r1f_search_cyclic_metrics.csv: 46,848 B read, 0 B written for 16.8M candidates;
+                     # it is instruction/constant fetch and does not grow with the candidate count).
+                     # Algorithmic HBM bytes per candidate: 0.
+                     "traffic": 46848,
                      "peak_source": ("DFMA probe measured in this run" if peak_tflops == probed_tflops else
                                      "nominal (the in-run DFMA probe came out lower and was discarded)")
                                     + "; MEASURED_PEAKS.json has no FP64 figure; "

@@ -140,3 +140,10 @@ def test_rust_crate_declares_only_exported_symbols_with_header_arity():
     srcs = re.search(r"^SRCS\s*:=\s*(.*)$", mk, flags=re.M).group(1).split()
     build_rs = open(os.path.join(ROOT, "rust", "build.rs")).read()
     assert sorted(re.findall(r'"([a-z_]+\.cu)"', build_rs)) == sorted(srcs)
+
+
+def test_import_maxpro_is_the_reference_module_name():
+    """`import maxpro` (pyo3 module name, src/lib.rs:166-176) resolves to the engine's mirror."""
+    import maxpro as ref_named
+    for fn in ("generate_lhd", "build_lhd", "maxpro_criterion", "maximin_criterion", "anneal_lhd", "order_design"):
+        assert getattr(ref_named, fn) is getattr(maxpro, fn)

@@ -6,6 +6,7 @@ maximin (min/sqrt of exactly-rounded terms) bit-exact.
 Nothing here reads /root/reference: fixtures live in tests/golden/.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -434,3 +435,27 @@ def test_python_module_pipeline():
     assert maxpro.maximin_criterion(lhd) == oracle.maximin_criterion(lhd)
     g = maxpro.generate_lhd(10, 3, 1)
     assert lhd_bins_ok(np.array(g)) and maxpro.generate_lhd(10, 3) != g
+
+
+def test_reference_scripts_flow_through_import_maxpro():
+    """The steps of the reference's python/comparison_r.py:124-167 and comparisons.py:95-104,
+    through `import maxpro` (the module name the scripts use) instead of maxpro_b200.maxpro."""
+    import json
+
+    import maxpro as ref_named
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "r_design_100x2.json")))
+    value = ref_named.maxpro_criterion(gold["design"])
+    assert math.isclose(value, gold["r_measure"], rel_tol=1e-7)          # comparison_r.py:131
+    assert math.isclose(value, gold["rust_value_readme"], rel_tol=1e-12)  # README.md:90
+    n_iterations = 63401 // 3                                             # comparison_r.py:117,139
+    lhd = ref_named.build_lhd(100, 2, n_iterations, "maxpro", 42)
+    a = ref_named.anneal_lhd(lhd, n_iterations, 1.0, 0.5, "maxpro", True, True, 42)
+    b = ref_named.anneal_lhd(a, n_iterations, 1.0, 0.5, "maxpro", True, False, 42)
+    m0, m1, m2 = (ref_named.maxpro_criterion(x) for x in (lhd, a, b))
+    assert m2 <= m1 <= m0 and lhd_bins_ok(np.array(a))
+    # R's MaxProLHD reaches 95.98506 with 63,401 iterations in 5.5 s (comparison_r.py:115-117)
+    assert m2 < 2 * gold["r_measure"]
+    ordered = ref_named.order_design(b, "maxpro")                         # comparisons.py:99-104
+    assert sorted(map(tuple, ordered)) == sorted(map(tuple, b))
+    assert ref_named.build_lhd(10, 3, 100, "maximin", seed=12345) == ref_named.build_lhd(10, 3, 100, "maximin", seed=12345)
