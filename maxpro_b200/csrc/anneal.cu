@@ -60,19 +60,16 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
         }
         // reciprocal chains and shared denominators are range-safe only in the unit cube
         const bool in_cube = __syncthreads_and(ok) != 0;
-        publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
-        __syncthreads();
         // chain state, kept by warp 0 (every lane holds the same values)
         double raw_cur = 0.0, cur_metric = 0.0, global_best = 0.0;
         double temp = p.t0;                                                             // anneal.rs:81
         bool materialized = false, overflow = false;  // HBM best exists / the move log lost entries
         int log_n = 0;                                // moves accepted since the HBM best equalled cur
         if (warp == 0) {
-            raw_cur = warp_total<MAXPRO>(part, (blockDim.x + 31) >> 5);
+            raw_cur = *p.raw0;  // the start design's raw criterion, computed once for all chains
             cur_metric = metric_from_raw<MAXPRO>(raw_cur, n, p.n_pairs, p.inv_d);       // :90
             global_best = cur_metric;                                                   // :94
         }
-        __syncthreads();  // part[] is free again
         double* best_out = p.best_design + chain * (unsigned long long)nd;
         unsigned long long until_resync = p.resync;  // iterations until the next full re-sum of S
 
@@ -214,6 +211,51 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     }
 }
 
+// The raw criterion of the start design (anneal.rs:90), once per call: one CTA, same layout and
+// summation as the in-chain re-sum.
+template <bool MAXPRO>
+__global__ void __launch_bounds__(512) anneal_raw0_kernel(const double* design, int n, int d, double* raw0) {
+    extern __shared__ __align__(16) double smem_d[];
+    const int ns = (n + 1) & ~1;
+    double* cur = smem_d;
+    double* part = smem_d + d * ns;
+    if (ns != n)
+        for (int k = threadIdx.x; k < d; k += blockDim.x) cur[k * ns + n] = 0.0;
+    int ok = 1;
+    for (int e = threadIdx.x; e < n * d; e += blockDim.x) {
+        const int i = e / d, k = e - i * d;
+        const double v = design[e];
+        ok &= (v >= 0.0 && v <= 1.0) ? 1 : 0;
+        cur[k * ns + i] = v;
+    }
+    const bool in_cube = __syncthreads_and(ok) != 0;
+    publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const double raw = warp_total<MAXPRO>(part, (blockDim.x + 31) >> 5);
+        if (threadIdx.x == 0) *raw0 = raw;
+    }
+}
+
+cudaError_t launch_anneal_raw0(const AnnealLaunch& L) {
+    const unsigned long long ns = (L.n + 1) & ~1ull;
+    const size_t smem = (size_t)(ns * L.d + 32) * sizeof(double);
+    int threads = (int)((L.n + 31) / 32 * 32);
+    if (threads > 512) threads = 512;
+    cudaError_t e;
+    if (L.metric == 0) {
+        e = cudaFuncSetAttribute(anneal_raw0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        anneal_raw0_kernel<true><<<1, threads, smem, L.stream>>>(L.design, (int)L.n, (int)L.d, L.raw0);
+    } else {
+        e = cudaFuncSetAttribute(anneal_raw0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        anneal_raw0_kernel<false><<<1, threads, smem, L.stream>>>(L.design, (int)L.n, (int)L.d, L.raw0);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 size_t anneal_smem_bytes(unsigned long long n, unsigned long long d, int swap) {
     const unsigned long long ns = (n + 1) & ~1ull;
     return (size_t)(ns * d * (swap ? 1 : 2) + 34 + 2 * d) * sizeof(double) + (size_t)kDrawBatch * sizeof(uint4) + (size_t)kLogCap * sizeof(ushort4);
@@ -226,6 +268,7 @@ bool anneal_supported(unsigned long long n, unsigned long long d, int swap) {
 static int round_up_32(unsigned long long v) { return (int)((v + 31) / 32 * 32); }
 
 cudaError_t launch_anneal(const AnnealLaunch& L) {
+    if (cudaError_t e0 = launch_anneal_raw0(L); e0 != cudaSuccess) return e0;
     if (anneal_pipe_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_pipe(L);
     AnnealParams p;
     p.design = L.design; p.n = L.n; p.d = L.d; p.iters = L.iters; p.seed = L.seed; p.n_chains = L.n_chains;
@@ -235,7 +278,7 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     p.resync = rs < 1024 ? 1024 : rs;
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
-    p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved;
+    p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
     size_t smem = anneal_smem_bytes(L.n, L.d, L.swap);
     int threads;
     if (L.swap && L.metric == 0) {

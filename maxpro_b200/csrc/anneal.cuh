@@ -20,6 +20,8 @@ struct AnnealParams {
     double* best_design;        // [n_chains][n*d] row-major, valid where improved[c] != 0
     double* best_metric;        // [n_chains]
     unsigned int* improved;     // [n_chains]
+    const double* raw0;         // S (or min squared distance) of the start design: every chain starts there,
+                                // so it is computed once by anneal_raw0_kernel instead of once per chain
 };
 
 // Deterministic block reduction in two halves.  Every thread: lane tree, lane 0 publishes the

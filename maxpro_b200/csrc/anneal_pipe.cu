@@ -257,19 +257,16 @@ __global__ void __launch_bounds__(PPT == 2 ? 320 : 480) anneal_swap_pipe_kernel(
         }
         fill_moves(ring, 0ull, kRing, blockDim.x, n, d, key0, key1);
         const bool in_cube = __syncthreads_and(ok) != 0;
-        publish_partial<true>(full_score_partial<true, 4>(cur, n, d, ns, in_cube), part);
-        __syncthreads();
         // chain state, kept by the decider warp (every lane holds the same values)
         double raw_cur = 0.0, cur_metric = 0.0, global_best = 0.0;
         double temp = p.t0;                                                             // anneal.rs:81
         bool materialized = false, overflow = false;
         int log_n = 0, prev_applied = 0;
         if (decider) {
-            raw_cur = warp_total<true>(part, nwarps);
+            raw_cur = *p.raw0;  // S of the start design, computed once for all chains (anneal_raw0_kernel)
             cur_metric = metric_from_raw<true>(raw_cur, n, p.n_pairs, p.inv_d);         // :90
             global_best = cur_metric;                                                   // :94
         }
-        __syncthreads();
         double* best_out = p.best_design + chain * (unsigned long long)nd;
         unsigned long long until_resync = p.resync;
         bool have_bulk = false, use_fix = false;
@@ -423,7 +420,7 @@ cudaError_t launch_anneal_pipe(const AnnealLaunch& L) {
     p.resync = rs < 1024 ? 1024 : rs;
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
-    p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved;
+    p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
     const size_t smem = pipe_smem_bytes(L.n, L.d);
     // worker warps: one thread per PPT pairs of partner rows; plus the decider and the specialist warp
     const int ppt = L.n >= 768 ? 2 : 1;

@@ -579,8 +579,9 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     if (!mp::anneal_supported(n, d, swap))
         return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the shared-memory annealer (n*d*8 bytes, doubled for jitter, must fit 227 KB)");
     const size_t nd = n * d;
-    DevBuf dx, db, dm, di;
+    DevBuf dx, db, dm, di, dr;
     CUDA_TRY(dx.alloc(nd * sizeof(double)));
+    CUDA_TRY(dr.alloc(sizeof(double)));
     CUDA_TRY(db.alloc(n_chains * nd * sizeof(double)));
     CUDA_TRY(dm.alloc(n_chains * sizeof(double)));
     CUDA_TRY(di.alloc(n_chains * sizeof(unsigned int)));
@@ -589,7 +590,7 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     mp::AnnealLaunch L{};
     L.design = dx.as<double>(); L.n = n; L.d = d; L.iters = n_iterations; L.seed = seed; L.n_chains = n_chains;
     L.t0 = initial_temp; L.cooling = cooling_rate; L.metric = metric; L.minimize = minimize ? 1 : 0; L.swap = swap ? 1 : 0;
-    L.best_design = db.as<double>(); L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.stream = st;
+    L.best_design = db.as<double>(); L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.raw0 = dr.as<double>(); L.stream = st;
     CUDA_TRY(mp::launch_anneal(L));
     std::vector<double> metrics(n_chains);
     std::vector<unsigned int> improved(n_chains);

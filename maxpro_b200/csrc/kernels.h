@@ -76,6 +76,7 @@ struct AnnealLaunch {
     double* best_design;     // [n_chains][n*d]
     double* best_metric;     // [n_chains]
     unsigned int* improved;  // [n_chains]
+    double* raw0;            // device scratch, 1 double: S (or min squared distance) of the start design
     cudaStream_t stream;
 };
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap);
