@@ -156,8 +156,11 @@ unsigned long long generic_chunk(unsigned long long n, unsigned long long d) {
 }
 
 // which fused kernel a shape takes (MAXPRO_NO_CTA=1 forces the chunked path; used by the tests)
+bool use_warp_kernel(unsigned long long n, unsigned long long d) {
+    return !mp::search_small_supported(n, d) && mp::search_warp_supported(n, d) && !getenv("MAXPRO_NO_CTA");
+}
 bool use_cta_kernel(unsigned long long n, unsigned long long d) {
-    return !mp::search_small_supported(n, d) && mp::search_cta_supported(n, d) && !getenv("MAXPRO_NO_CTA");
+    return !mp::search_small_supported(n, d) && !use_warp_kernel(n, d) && mp::search_cta_supported(n, d) && !getenv("MAXPRO_NO_CTA");
 }
 
 struct SearchWs {
@@ -180,7 +183,7 @@ SearchWs carve_search_ws(void* base, unsigned long long n, unsigned long long d)
     w.block_best = reinterpret_cast<BestRec*>(take(kMaxBlockRecs * sizeof(BestRec)));
     w.chunk_result = reinterpret_cast<BestRec*>(take(256));
     w.survivors = reinterpret_cast<unsigned long long*>(take(kMaxBlockRecs * 16 * sizeof(unsigned long long)));
-    if (!mp::search_small_supported(n, d) && !use_cta_kernel(n, d)) {
+    if (!mp::search_small_supported(n, d) && !use_cta_kernel(n, d) && !use_warp_kernel(n, d)) {
         unsigned long long bc = generic_chunk(n, d);
         w.designs = reinterpret_cast<double*>(take(bc * n * d * sizeof(double)));
         w.partial = reinterpret_cast<double*>(take(bc * mp::score_items(n) * sizeof(double)));
@@ -270,6 +273,19 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
         L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
         L.stream = stream;
         CUDA_TRY(mp::launch_search_small(L));
+        mp::count_launch();
+        return MAXPRO_OK;
+    }
+    if (use_warp_kernel(n, d)) {
+        mp::SearchLaunch L{};
+        L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
+        L.block_best = w.block_best; L.done_counter = w.counter; L.result = result;
+        unsigned long long total = hi - lo;
+        unsigned long long want = (total + 7) / 8;  // 8 candidates (warps) per CTA
+        unsigned long long g = (unsigned long long)mp::search_warp_grid(sms);
+        L.grid = (int)(want < g ? want : g);
+        L.threads = 256; L.group = 0; L.stream = stream;
+        CUDA_TRY(mp::launch_search_warp(L));
         mp::count_launch();
         return MAXPRO_OK;
     }

@@ -189,8 +189,9 @@ def test_search_matches_oracle(n, d, metric):
 
 @pytest.mark.parametrize("n,d,iters", [(40, 9, 3000), (130, 10, 3000), (300, 4, 3000), (301, 7, 1500), (500, 10, 1500),
                                        (1000, 20, 300), (1999, 2, 400), (63, 12, 2000), (2, 9, 50), (9, 33, 500)])
-def test_search_cta_path(n, d, iters):
-    """CTA-per-candidate kernel (designs too large for the thread-group kernels)."""
+def test_search_warp_and_cta_paths(n, d, iters):
+    """Designs too large for the thread-group kernels: warp-per-candidate kernel while 16 candidates
+    fit one SM's shared memory (n*d*10 B <= ~14 KB), CTA-per-candidate kernel above that."""
     seed = 7
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
@@ -198,6 +199,32 @@ def test_search_cta_path(n, d, iters):
         assert i == i_ref
         assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
         assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
+
+
+@pytest.mark.parametrize("n,d", [(40, 9), (130, 10), (300, 4), (33, 12), (100, 5)])
+def test_search_cta_path_on_medium_shapes(n, d, monkeypatch):
+    """The CTA kernel must still serve the shapes the warp kernel normally takes."""
+    monkeypatch.setenv("MAXPRO_NO_WARP", "1")
+    iters, seed = 3000, 7
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
+        design, s, i = engine.build_lhd(n, d, iters, metric, seed)
+        assert i == i_ref
+        assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+        assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
+
+
+@pytest.mark.parametrize("n,d", [(100, 5), (128, 8), (150, 3), (200, 4), (31, 9), (64, 9), (101, 10)])
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+def test_search_warp_path_winner(n, d, metric):
+    """Warp-per-candidate kernel on the shapes it was written for: winner index and score against
+    the oracle's brute force over 20,000 candidates (maximin bit-exact)."""
+    iters, seed = 20_000, 11
+    s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
+    design, s, i = engine.build_lhd(n, d, iters, metric, seed)
+    assert i == i_ref
+    assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+    assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
 
 
 @pytest.mark.parametrize("n,d", [(40, 9), (130, 10), (300, 4)])
