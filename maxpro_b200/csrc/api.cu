@@ -281,10 +281,10 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
         L.block_best = w.block_best; L.done_counter = w.counter; L.result = result;
         unsigned long long total = hi - lo;
-        unsigned long long want = (total + 7) / 8;  // 8 candidates (warps) per CTA
-        unsigned long long g = (unsigned long long)mp::search_warp_grid(sms);
+        unsigned long long want = (total + 3) / 4;  // 4 candidates (warps) per CTA
+        unsigned long long g = (unsigned long long)mp::search_warp_grid(n, d, sms);
         L.grid = (int)(want < g ? want : g);
-        L.threads = 256; L.group = 0; L.stream = stream;
+        L.threads = 128; L.group = 0; L.stream = stream;
         CUDA_TRY(mp::launch_search_warp(L));
         mp::count_launch();
         return MAXPRO_OK;

@@ -42,7 +42,7 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* surv
 
 // warp-per-candidate kernel for medium designs (search_warp.cu): 16 candidates per SM in shared memory
 bool search_warp_supported(unsigned long long n, unsigned long long d);
-int search_warp_grid(int sms);
+int search_warp_grid(unsigned long long n, unsigned long long d, int sms);
 cudaError_t launch_search_warp(const SearchLaunch& L);
 
 // CTA-per-candidate kernel for designs that do not fit the thread-group kernels (search_cta.cu)

@@ -17,7 +17,9 @@
 // are dealt to the lanes in row-major order (consecutive lanes <-> consecutive rows: conflict-
 // free), so every lane gets the same number of items whatever n is.  The 8 running products
 // stay in registers across the dimensions; MaxPro terms go through the reciprocal chains of
-// common.cuh (candidates are in the unit cube by construction).
+// common.cuh (candidates are in the unit cube by construction).  Each column is followed by a
+// copy of its first 8*ceil(smax/8) rows, so row (i+s) mod n is simply row i+s: the 8 partner
+// loads of an item are one address plus immediates, with no wrap arithmetic and no index array.
 #include "common.cuh"
 #include "philox.cuh"
 #include "reduce.cuh"
@@ -27,11 +29,11 @@
 
 namespace mp {
 
-constexpr int kWarpCtaThreads = 256;  // 8 candidates per CTA
+constexpr int kWarpCtaThreads = 128;  // 4 candidates per CTA, up to 4 CTAs per SM
 constexpr int kWarpSB = 8;            // shifts per work item
 
 struct WarpParams {
-    int n, d, ns;  // ns = odd row stride of the [k][i] layout (the column walkers hit different banks)
+    int n, d, ns;  // ns = odd row stride of the [k][i] layout (the column walkers hit different banks): n + copied rows
     unsigned int cand_bytes;  // shared memory of one candidate slot
     unsigned long long seed, lo, hi;
     double c1, c0, n_pairs, inv_d;
@@ -41,13 +43,13 @@ struct WarpParams {
 };
 
 template <bool MAXPRO>
-__global__ void __launch_bounds__(kWarpCtaThreads, 2) search_warp_kernel(WarpParams p) {
+__global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BestRec warp_best[kWarpCtaThreads / 32];
     const int n = p.n, d = p.d, ns = p.ns;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* xs = reinterpret_cast<double*>(smem_raw + (size_t)warp * p.cand_bytes);  // [d][ns]
-    unsigned short* jst = reinterpret_cast<unsigned short*>(xs + (size_t)d * ns);    // [d][ns]
+    unsigned short* jst = reinterpret_cast<unsigned short*>(xs + (size_t)d * ns);    // [d][n]
     const int nb = (n + 1) / 2;
     const int half = (n - 1) / 2;
     const bool even = (n & 1) == 0;
@@ -68,17 +70,17 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) search_warp_kernel(WarpPar
             Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
             const int i = 2 * b;
             xs[k * ns + i] = stratum_value((uint32_t)i, w.x, p.c1, p.c0);
-            jst[k * ns + i] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
+            jst[k * n + i] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
             if (i + 1 < n) {
                 xs[k * ns + i + 1] = stratum_value((uint32_t)(i + 1), w.z, p.c1, p.c0);
-                jst[k * ns + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
+                jst[k * n + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
             }
         }
         __syncwarp();
         // ---- generation, phase 2: one lane per column
         for (int k = lane; k < d; k += 32) {
             double* a = xs + k * ns;
-            const unsigned short* js = jst + k * ns;
+            const unsigned short* js = jst + k * n;
             for (int i = 0; i < n; ++i) {
                 const int j = js[i];
                 const double v = a[i];
@@ -86,6 +88,12 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) search_warp_kernel(WarpPar
                 a[i] = t;
                 a[j] = v;
             }
+        }
+        __syncwarp();
+        // rows n .. n + 8*nblk - 1 repeat rows 0 .. (wrapping again if the design is tiny)
+        for (int e = lane; e < d * kWarpSB * nblk; e += 32) {
+            const int k = e / (kWarpSB * nblk), r = e - k * (kWarpSB * nblk);
+            xs[k * ns + n + r] = xs[k * ns + r % n];
         }
         __syncwarp();
 
@@ -99,45 +107,51 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) search_warp_kernel(WarpPar
         for (int q = lane; q < items; q += 32) {
             const int s0 = 1 + b * kWarpSB;
             const int my_smax = half + ((even && i < n / 2) ? 1 : 0);
-            int jj[kWarpSB];
-#pragma unroll
-            for (int c = 0; c < kWarpSB; ++c) {
-                int j = i + s0 + c;
-                if (j >= n) j -= n;
-                jj[c] = (s0 + c <= my_smax) ? j : i;  // masked slots pair the row with itself
-            }
+            const double* pi = xs + i;        // row i
+            const double* pj = pi + s0;       // rows i+s0 .. i+s0+7 (copies past row n-1)
             double pr[kWarpSB];
             {
-                const double xi = xs[i];
+                const double xi = pi[0];
 #pragma unroll
                 for (int c = 0; c < kWarpSB; ++c) {
-                    if (MAXPRO) pr[c] = xi - xs[jj[c]];
-                    else { const double df = __dsub_rn(xi, xs[jj[c]]); pr[c] = __dmul_rn(df, df); }
+                    if (MAXPRO) pr[c] = xi - pj[c];
+                    else { const double df = __dsub_rn(xi, pj[c]); pr[c] = __dmul_rn(df, df); }
                 }
             }
             for (int k = 1; k < d; ++k) {
-                const double* xk = xs + k * ns;
-                const double xi = xk[i];
+                pi += ns; pj += ns;
+                const double xi = pi[0];
 #pragma unroll
                 for (int c = 0; c < kWarpSB; ++c) {
-                    if (MAXPRO) pr[c] *= xi - xk[jj[c]];
-                    else { const double df = __dsub_rn(xi, xk[jj[c]]); pr[c] = __dadd_rn(pr[c], __dmul_rn(df, df)); }
+                    if (MAXPRO) pr[c] *= xi - pj[c];
+                    else { const double df = __dsub_rn(xi, pj[c]); pr[c] = __dadd_rn(pr[c], __dmul_rn(df, df)); }
                 }
             }
+            const bool whole = s0 + kWarpSB - 1 <= my_smax;  // false only in a row's last shift block
             if (MAXPRO) {
                 if (pushed == kMaxChainTerms) {
 #pragma unroll
                     for (int c = 0; c < kWarpSB; ++c) acc += ch[c].flush();
                     pushed = 0;
                 }
+                if (whole) {
 #pragma unroll
-                for (int c = 0; c < kWarpSB; ++c)
-                    if (s0 + c <= my_smax) ch[c].push(fma(pr[c], pr[c], kEps));
+                    for (int c = 0; c < kWarpSB; ++c) ch[c].push(fma(pr[c], pr[c], kEps));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kWarpSB; ++c)
+                        if (s0 + c <= my_smax) ch[c].push(fma(pr[c], pr[c], kEps));
+                }
                 ++pushed;
             } else {
+                if (whole) {
 #pragma unroll
-                for (int c = 0; c < kWarpSB; ++c)
-                    if (s0 + c <= my_smax) mn = fmin(mn, pr[c]);
+                    for (int c = 0; c < kWarpSB; ++c) mn = fmin(mn, pr[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kWarpSB; ++c)
+                        if (s0 + c <= my_smax) mn = fmin(mn, pr[c]);
+                }
             }
             // next item of this lane: 32 rows further, wrapping into the next shift block
             i += 32;
@@ -156,23 +170,36 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) search_warp_kernel(WarpPar
     block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
+static unsigned long long warp_row_stride(unsigned long long n) {
+    const unsigned long long smax = (n - 1) / 2 + ((n & 1) == 0 ? 1 : 0);
+    const unsigned long long nblk = (smax + kWarpSB - 1) / kWarpSB;
+    return (n + kWarpSB * nblk) | 1ull;  // n rows + the copied ones, odd
+}
 static unsigned int warp_cand_bytes(unsigned long long n, unsigned long long d) {
-    const unsigned long long ns = n | 1ull;
-    return (unsigned int)(((d * ns * 10 + 15) / 16) * 16);
+    return (unsigned int)(((d * warp_row_stride(n) * 8 + d * n * 2 + 15) / 16) * 16);
 }
 
-// Medium designs: too big for the thread-group kernels, small enough that 16 candidates fit the
-// shared memory of one SM (two CTAs of 8 warps).
+static int warp_ctas_per_sm(unsigned long long n, unsigned long long d) {
+    const size_t per_cta = (size_t)warp_cand_bytes(n, d) * (kWarpCtaThreads / 32) + 1024;  // + static and reserved shared memory
+    size_t c = kSmemBudget / per_cta;
+    return (int)(c > 4 ? 4 : c);
+}
+
+// Medium designs: too big for the thread-group kernels, small enough that at least 12 candidates
+// (3 CTAs of 4 warps) fit the shared memory of one SM -- below that the Fisher-Yates walks are no
+// longer hidden and the CTA-per-candidate kernel does better.
 bool search_warp_supported(unsigned long long n, unsigned long long d) {
     if (const char* e = getenv("MAXPRO_NO_WARP")) if (atoi(e) != 0) return false;
-    return n >= 2 && n <= 65535 && d >= 1 && (size_t)warp_cand_bytes(n, d) * 16 + 2048 <= kSmemBudget;
+    int need = 3;
+    if (const char* e = getenv("MAXPRO_WARP_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4) need = v; }
+    return n >= 2 && n <= 65535 && d >= 1 && d <= 65535 && warp_ctas_per_sm(n, d) >= need;
 }
 
-int search_warp_grid(int sms) { return 2 * sms; }
+int search_warp_grid(unsigned long long n, unsigned long long d, int sms) { return warp_ctas_per_sm(n, d) * sms; }
 
 cudaError_t launch_search_warp(const SearchLaunch& L) {
     WarpParams p;
-    p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)(L.n | 1ull);
+    p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)warp_row_stride(L.n);
     p.cand_bytes = warp_cand_bytes(L.n, L.d);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.c1 = ldexp(1.0 / (double)L.n, -32);
