@@ -8,6 +8,9 @@ namespace mp {
 
 constexpr double kEps = 1e-12;  // src/maxpro_utils.rs:35
 constexpr int kMaxChainTerms = 16;  // terms a RecipChain may hold before a flush (den >= 1e-192)
+// A chain whose denominator starts at 2^1000 instead of 1 (num/den is scale-free) has the whole
+// exponent range below it: 2^1000 * (1e-12)^k >= 1e-300 holds for k <= 50, and num <= k * 2^1000.
+constexpr int kMaxBigChainTerms = 48;
 
 // Winner record that leaves the chip: 16 bytes.
 struct __align__(16) BestRec {
@@ -72,6 +75,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 struct RecipChain {
     double num, den;
     __device__ __forceinline__ void reset() { num = 0.0; den = 1.0; }
+    __device__ __forceinline__ void reset_big() { num = 0.0; den = 0x1p1000; }
     __device__ __forceinline__ void push(double p) { num = fma(num, p, den); den *= p; }
     __device__ __forceinline__ double flush() { double v = num * fast_rcp(den); reset(); return v; }
     // acc + num/den with the quotient good to ~2^-40 (one Newton step on the 20-bit MUFU seed,
@@ -84,6 +88,17 @@ struct RecipChain {
         const double nr = num * r;
         const double v = fma(nr, e, nr);  // num * r * (1 + e)
         reset();
+        return acc + v;
+    }
+    // the same for a chain started by reset_big(): den in [1e-300, 2^1000], so the seed and the
+    // Newton residual stay normal numbers
+    __device__ __forceinline__ double flush_big_into(double acc) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+        const double e = fma(-den, r, 1.0);
+        const double nr = num * r;
+        const double v = fma(nr, e, nr);
+        reset_big();
         return acc + v;
     }
 };

@@ -11,11 +11,11 @@
 // cyclic schedule has ONE block shape and nothing else:
 //     pair {i, (i+s) mod n},  s = 1 .. (n-1)/2,  every row i          (+ the n/2 diameters)
 // The two lanes of a candidate split the s range in halves (s = 1..12 and 13..24 at n = 50),
-// walk the rows in register tiles of R = 5, and for S = 4 consecutive shifts load the
-// R+S-1 = 8 partner rows once: 20 pairs per block, 24 LDS.64, fully unrolled, no triangle,
-// no remainder, identical trip counts in both lanes (no divergence).  Row wrap-around costs
-// one add and one unsigned min per loaded row.  With N and C constant every shared-memory
-// address is base + immediate.
+// walk the rows in register tiles of R = 5 and read the 5 + 12 - 1 = 16 partner rows of a tile
+// once: 60 pairs per tile, 63 LDS.64, fully unrolled, no triangle, no remainder, identical trip
+// counts in both lanes (no divergence).  With N and C constant every shared-memory address of
+// the lower tiles is base + immediate; the upper tiles pay one add and one unsigned min per
+// partner row for the wrap-around.
 #include "common.cuh"
 #include "philox.cuh"
 #include "reduce.cuh"
@@ -122,68 +122,107 @@ __device__ __forceinline__ void cyc_generate_three(unsigned char* cand, uint32_t
     cyc_generate_blocks<N, D, C>(cand + (g ? 2u : 0u) * DB, g ? 2u : 0u, g ? H : NB - H, H, s_lo, s_hi, c1, c0);
 }
 
+// One tile of the cyclic schedule: R rows against the lane's KP shifts.  The R + KP - 1 partner rows
+// are read once for all shifts (16 row loads per 60 pairs at R = 5, KP = 12).  Tiles whose partner
+// rows stay below N for both lanes (WRAP = false) address them as base + immediate; only the
+// upper tiles pay one add and one unsigned min per row for the wrap-around.
+template <int N, int D, int C, bool MAXPRO, bool SAFE, bool WRAP, int R, int KP>
+__device__ __forceinline__ void cyc_tile_window(const unsigned char* cand, unsigned i0_off, unsigned first_off,
+                                                const double (&xi)[R][D], RecipChain (&ch)[R], double (&mins)[R], double& acc) {
+    constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
+    constexpr unsigned NB = N * RB;
+    constexpr int W = R + KP - 1;
+    double xj[W][D];
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        unsigned off = i0_off + first_off + u * RB;
+        if (WRAP) off = min(off, off - NB);
+        load_row_at<N, D, C>(xj[u], cand, off);
+    }
+#pragma unroll
+    for (int c = 0; c < KP; ++c)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xj[r + c]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c])); }
+            else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xj[r + c]));
+        }
+}
+
 // SAFE: designs a caller supplied may lie outside the unit cube, where the reciprocal chains
 // are not range-safe; then every term takes an IEEE divide (src/maxpro_utils.rs:54 literally).
+//
+// FP64 instructions per pair: 3 DADD + 2 DMUL + 1 DFMA for the term, 1 DFMA + 1 DMUL for the
+// chain push = 8, plus 4 per chain flush.  The chains start at den = 2^1000 (common.cuh), so one
+// flush serves three tiles (36-39 terms) instead of one: 20 flushes per lane and candidate
+// instead of 50.  The n/2 diameters are split between the two lanes by ADDRESS (lane 0 rows
+// 0..12, lane 1 rows 13..24), not by predicate: 13 pair slots per lane instead of 25.
 template <int N, int D, int C, bool MAXPRO, bool SAFE = false>
 __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
-    constexpr int R = 5, S = 4, G = 2;
-    constexpr int kHalf = (N - 1) / 2;       // shifts 1..kHalf pair every row once
-    constexpr int kPerLane = kHalf / G;      // shifts per lane
-    constexpr int kBlocks = kPerLane / S;    // blocks of S shifts per tile
-    static_assert(N % R == 0, "row tiles must divide n");
-    static_assert(kHalf % (G * S) == 0, "shift range must split into whole blocks");
-    static_assert(kPerLane <= 16, "one flush per tile keeps every chain within 16 terms");
+    constexpr int R = 5, G = 2;
+    constexpr int kHalf = (N - 1) / 2;
+    constexpr int kPerLane = kHalf / G;
+    constexpr int kTiles = N / R;
+    constexpr int kNoWrap = (N - kHalf - R) / R + 1;  // tiles with t*R + kHalf + R-1 <= N-1
+    constexpr int kFlushEvery = 3;                    // tiles between flushes
+    constexpr int kDiam = (N % 2 == 0) ? (N / 2 + 1) / 2 : 0;  // diameter pairs per lane
+    static_assert(N % R == 0 && kHalf % G == 0, "whole tiles, equal shift ranges");
+    static_assert(kFlushEvery * kPerLane + (kDiam + R - 1) / R <= kMaxBigChainTerms, "chains stay in range between flushes");
     constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
-    constexpr unsigned NB = N * RB;          // wrap modulus in bytes
 
     RecipChain ch[R];
     double mins[R];
     double acc = 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { ch[r].reset(); mins[r] = CUDART_INF; }
+    for (int r = 0; r < R; ++r) { ch[r].reset_big(); mins[r] = CUDART_INF; }
+    const unsigned first_off = (1u + (unsigned)g * kPerLane) * RB;  // this lane's first shift
+    auto flush_all = [&]() {
+        if (MAXPRO && !SAFE) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc = ch[r].flush_big_into(acc);
+        }
+    };
 
-    const unsigned s_first = 1u + (unsigned)g * kPerLane;  // this lane's first shift
 #pragma unroll 1
-    for (int t = 0; t < N / R; ++t) {
+    for (int t = 0; t < kNoWrap; ++t) {
         const unsigned i0_off = (unsigned)t * R * RB;
         double xi[R][D];
 #pragma unroll
         for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xi[r], cand, i0_off + r * RB);
+        cyc_tile_window<N, D, C, MAXPRO, SAFE, false, R, kPerLane>(cand, i0_off, first_off, xi, ch, mins, acc);
+        if (t % kFlushEvery == kFlushEvery - 1) flush_all();
+    }
+    // diameters {i, i + N/2} (even N), i < N/2: lane 0 takes i = 0 .. kDiam-1, lane 1 the rest.  The
+    // rows are addressed per lane, so both lanes run the same instructions (no divergence); when
+    // N/2 is odd lane 1's last slot is a repeat of row 0 that is not pushed.
+    if (N % 2 == 0) {
+        constexpr int H = N / 2;
 #pragma unroll
-        for (int b = 0; b < kBlocks; ++b) {
-            // partner rows (i0 + s0 + u) mod N, u = 0 .. R+S-2
-            const unsigned base = i0_off + (s_first + (unsigned)b * S) * RB;
-            double xj[R + S - 1][D];
-#pragma unroll
-            for (int u = 0; u < R + S - 1; ++u) {
-                unsigned off = base + u * RB;
-                off = min(off, off - NB);  // off >= NB ? off - NB : off   (unsigned wrap)
-                load_row_at<N, D, C>(xj[u], cand, off);
+        for (int j = 0; j < kDiam; ++j) {
+            const bool live = (H % 2 == 0) || j < kDiam - 1 || g == 0;
+            const unsigned off = live ? ((unsigned)g * kDiam + j) * RB : 0u;
+            double xa[D], xb[D];
+            load_row_at<N, D, C>(xa, cand, off);
+            load_row_at<N, D, C>(xb, cand, off + H * RB);
+            if (MAXPRO) {
+                const double pterm = cyc_maxpro_term<D>(xa, xb);
+                if (live) { if (SAFE) acc += 1.0 / pterm; else ch[j % R].push(pterm); }
+            } else {
+                const double dterm = cyc_sqdist_term<D>(xa, xb);
+                if (live) mins[j % R] = fmin(mins[j % R], dterm);
             }
-#pragma unroll
-            for (int c = 0; c < S; ++c)
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xj[r + c]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c])); }
-                    else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xj[r + c]));
-                }
-        }
-        // diameters {i, i + N/2} (even N): rows of the lower half only, tiles dealt to the lanes
-        if (N % 2 == 0 && t < N / (2 * R) && (t & 1) == g) {
-            double xd[R][D];
-#pragma unroll
-            for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xd[r], cand, i0_off + (N / 2 + r) * RB);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xd[r]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xd[r])); }
-                else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xd[r]));
-            }
-        }
-        if (MAXPRO && !SAFE) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc = ch[r].flush_into(acc);  // <= kPerLane + 1 terms per chain
         }
     }
+    flush_all();
+#pragma unroll 1
+    for (int t = kNoWrap; t < kTiles; ++t) {
+        const unsigned i0_off = (unsigned)t * R * RB;
+        double xi[R][D];
+#pragma unroll
+        for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xi[r], cand, i0_off + r * RB);
+        cyc_tile_window<N, D, C, MAXPRO, SAFE, true, R, kPerLane>(cand, i0_off, first_off, xi, ch, mins, acc);
+        if ((t - kNoWrap) % kFlushEvery == kFlushEvery - 1) flush_all();
+    }
+    if ((kTiles - kNoWrap) % kFlushEvery != 0) flush_all();
     if (MAXPRO) return acc;
     double m = mins[0];
 #pragma unroll
