@@ -22,6 +22,8 @@
 #include "reduce.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace mp {
 
 constexpr int kCtaThreads = 128;
@@ -53,6 +55,124 @@ __device__ __forceinline__ void load_block(double (&bv)[kJB], const double* src)
 // column each in generation phase 2 (stride ns doubles) fall into 8 different bank groups.
 __host__ __device__ __forceinline__ unsigned long long cta_row_stride(unsigned long long n) { return (n + 7) / 8 * 8 + 2; }
 
+// Per-lane scoring state of one candidate: eight reciprocal chains (one per block column), the
+// number of terms each holds, the running sum (MaxPro) or the running minimum (maximin).
+struct CtaScore {
+    RecipChain ch[kJB];
+    int pushed;
+    double acc, mn;
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int c = 0; c < kJB; ++c) ch[c].reset_big();
+        pushed = 0; acc = 0.0; mn = CUDART_INF;
+    }
+    __device__ __forceinline__ void flush() {
+#pragma unroll
+        for (int c = 0; c < kJB; ++c) acc = ch[c].flush_big_into(acc);
+        pushed = 0;
+    }
+};
+
+// One work item: the 64 rows of tile row0 (lane <-> rows row0+lane, row0+lane+32) against the 8
+// columns j0 .. j0+7.
+template <bool MAXPRO>
+__device__ __forceinline__ void cta_score_item(const double* xs, int n, int d, int ns, int row0, int j0, int lane, CtaScore& st) {
+    const int i0 = row0 + lane, i1 = i0 + 32;
+    const int i0c = min(i0, n - 1), i1c = min(i1, n - 1);
+    double prod[2][kJB];
+    // dimension 0, then the rest
+    {
+        const double a0 = xs[i0c], a1 = xs[i1c];
+        double bv[kJB];
+        load_block(bv, xs + j0);
+#pragma unroll
+        for (int c = 0; c < kJB; ++c) {
+            const double b = bv[c];
+            if (MAXPRO) { prod[0][c] = a0 - b; prod[1][c] = a1 - b; }
+            else {
+                double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
+                prod[0][c] = __dmul_rn(d0, d0); prod[1][c] = __dmul_rn(d1, d1);
+            }
+        }
+    }
+    for (int k = 1; k < d; ++k) {
+        const double* xk = xs + k * ns;
+        const double a0 = xk[i0c], a1 = xk[i1c];
+        double bv[kJB];
+        load_block(bv, xk + j0);
+#pragma unroll
+        for (int c = 0; c < kJB; ++c) {
+            const double b = bv[c];
+            if (MAXPRO) { prod[0][c] *= (a0 - b); prod[1][c] *= (a1 - b); }
+            else {
+                double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
+                prod[0][c] = __dadd_rn(prod[0][c], __dmul_rn(d0, d0));
+                prod[1][c] = __dadd_rn(prod[1][c], __dmul_rn(d1, d1));
+            }
+        }
+    }
+    // full blocks: every row of the tile precedes every column and all are < n
+    const bool full = (j0 >= row0 + kTileRows) && (j0 + kJB <= n) && (row0 + kTileRows <= n);
+    if (MAXPRO) {
+        if (st.pushed + 2 > kMaxBigChainTerms) st.flush();
+        if (full) {
+#pragma unroll
+            for (int c = 0; c < kJB; ++c) {
+                st.ch[c].push(fma(prod[0][c], prod[0][c], kEps));
+                st.ch[c].push(fma(prod[1][c], prod[1][c], kEps));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < kJB; ++c) {
+                const int j = j0 + c;
+                if (j < n && i0 < j) st.ch[c].push(fma(prod[0][c], prod[0][c], kEps));
+                if (j < n && i1 < j) st.ch[c].push(fma(prod[1][c], prod[1][c], kEps));
+            }
+        }
+        st.pushed += 2;
+    } else {
+#pragma unroll
+        for (int c = 0; c < kJB; ++c) {
+            const int j = j0 + c;
+            if (full || (j < n && i0 < j)) st.mn = fmin(st.mn, prod[0][c]);
+            if (full || (j < n && i1 < j)) st.mn = fmin(st.mn, prod[1][c]);
+        }
+    }
+}
+
+// Generation phase 1 for one candidate: every thread runs Philox for its share of the (column,
+// element-pair) blocks and stages v_i at a[i] and the Fisher-Yates index j_i in the side array.
+__device__ __forceinline__ void cta_stage_candidate(double* xs, unsigned short* jst, int n, int d, int ns, uint32_t s_lo, uint32_t s_hi,
+                                                    double c1, double c0, int tid, int nthreads) {
+    const int nb = (n + 1) / 2;
+    for (int q = tid; q < d * nb; q += nthreads) {
+        const int k = q / nb, b = q - k * nb;
+        Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+        const int i = 2 * b;
+        xs[k * ns + i] = stratum_value((uint32_t)i, w.x, c1, c0);
+        jst[k * ns + i] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
+        if (i + 1 < n) {
+            xs[k * ns + i + 1] = stratum_value((uint32_t)i + 1u, w.z, c1, c0);
+            jst[k * ns + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
+        }
+    }
+}
+
+// Generation phase 2: lane k of the calling group walks the n dependent steps of column k.
+__device__ __forceinline__ void cta_walk_columns(double* xs, const unsigned short* jst, int n, int d, int ns, int first, int step) {
+    for (int k = first; k < d; k += step) {
+        double* a = xs + k * ns;
+        const unsigned short* js = jst + k * ns;
+        for (int i = 0; i < n; ++i) {
+            const int j = js[i];
+            const double v = a[i];
+            const double t = a[j];
+            a[i] = t;
+            a[j] = v;
+        }
+    }
+}
+
 template <bool MAXPRO>
 __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -62,7 +182,6 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
     double* red = reinterpret_cast<double*>(smem_raw + (((size_t)d * ns * 10 + 15) / 16) * 16);  // [4] warp partials
     __shared__ BestRec warp_best[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nb = (n + 1) / 2;
     const int tiles = (n + kTileRows - 1) / kTileRows;
 
     double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by thread 0
@@ -72,117 +191,24 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         __syncthreads();  // previous candidate fully consumed
-        // ---- generation, phase 1
-        for (int q = tid; q < d * nb; q += kCtaThreads) {
-            const int k = q / nb, b = q - k * nb;
-            Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
-            const int i = 2 * b;
-            xs[k * ns + i] = fma((double)(((unsigned long long)(uint32_t)i << 32) | w.x), p.c1, p.c0);
-            jst[k * ns + i] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
-            if (i + 1 < n) {
-                xs[k * ns + i + 1] = fma((double)(((unsigned long long)(uint32_t)(i + 1) << 32) | w.z), p.c1, p.c0);
-                jst[k * ns + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
-            }
-        }
+        cta_stage_candidate(xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, kCtaThreads);
         __syncthreads();
-        // ---- generation, phase 2: one lane per column
-        for (int k = tid; k < d; k += kCtaThreads) {
-            double* a = xs + k * ns;
-            const unsigned short* js = jst + k * ns;
-            for (int i = 0; i < n; ++i) {
-                const int j = js[i];
-                const double v = a[i];
-                const double t = a[j];
-                a[i] = t;
-                a[j] = v;
-            }
-        }
+        cta_walk_columns(xs, jst, n, d, ns, tid, kCtaThreads);
         __syncthreads();
 
-        // ---- scoring
-        double acc = 0.0, mn = CUDART_INF;
-        RecipChain ch[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) ch[c].reset();
-        int pushed = 0;
-        int item = 0;
-        for (int t = 0; t < tiles; ++t) {
-            const int row0 = t * kTileRows;
-            const int i0 = row0 + lane, i1 = i0 + 32;
-            const int i0c = min(i0, n - 1), i1c = min(i1, n - 1);
-            const int nblk = (n - row0 + kJB - 1) / kJB;  // column blocks from the tile's first row
-            for (int jb = 0; jb < nblk; ++jb, ++item) {
-                if ((item & 3) != warp) continue;
-                const int j0 = row0 + jb * kJB;
-                double prod[2][kJB];
-                // dimension 0, then the rest
-                {
-                    const double a0 = xs[i0c], a1 = xs[i1c];
-                    double bv[kJB];
-                    load_block(bv, xs + j0);
-#pragma unroll
-                    for (int c = 0; c < kJB; ++c) {
-                        const double b = bv[c];
-                        if (MAXPRO) { prod[0][c] = a0 - b; prod[1][c] = a1 - b; }
-                        else {
-                            double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
-                            prod[0][c] = __dmul_rn(d0, d0); prod[1][c] = __dmul_rn(d1, d1);
-                        }
-                    }
-                }
-                for (int k = 1; k < d; ++k) {
-                    const double* xk = xs + k * ns;
-                    const double a0 = xk[i0c], a1 = xk[i1c];
-                    double bv[kJB];
-                    load_block(bv, xk + j0);
-#pragma unroll
-                    for (int c = 0; c < kJB; ++c) {
-                        const double b = bv[c];
-                        if (MAXPRO) { prod[0][c] *= (a0 - b); prod[1][c] *= (a1 - b); }
-                        else {
-                            double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
-                            prod[0][c] = __dadd_rn(prod[0][c], __dmul_rn(d0, d0));
-                            prod[1][c] = __dadd_rn(prod[1][c], __dmul_rn(d1, d1));
-                        }
-                    }
-                }
-                // full blocks: every row of the tile precedes every column and all are < n
-                const bool full = (j0 >= row0 + kTileRows) && (j0 + kJB <= n) && (row0 + kTileRows <= n);
-                if (MAXPRO) {
-                    if (pushed + 2 > kMaxChainTerms) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) acc += ch[c].flush();
-                        pushed = 0;
-                    }
-                    if (full) {
-#pragma unroll
-                        for (int c = 0; c < kJB; ++c) {
-                            ch[c].push(fma(prod[0][c], prod[0][c], kEps));
-                            ch[c].push(fma(prod[1][c], prod[1][c], kEps));
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < kJB; ++c) {
-                            const int j = j0 + c;
-                            if (j < n && i0 < j) ch[c].push(fma(prod[0][c], prod[0][c], kEps));
-                            if (j < n && i1 < j) ch[c].push(fma(prod[1][c], prod[1][c], kEps));
-                        }
-                    }
-                    pushed += 2;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < kJB; ++c) {
-                        const int j = j0 + c;
-                        if (full || (j < n && i0 < j)) mn = fmin(mn, prod[0][c]);
-                        if (full || (j < n && i1 < j)) mn = fmin(mn, prod[1][c]);
-                    }
-                }
-            }
+        // ---- scoring: items (row tile, column block) dealt round-robin to the warps
+        CtaScore st;
+        st.reset();
+        int t = 0, jb = warp;
+        int nblk = (n + kJB - 1) / kJB;  // column blocks from the tile's first row
+        while (true) {
+            while (t < tiles && jb >= nblk) { jb -= nblk; ++t; nblk = (n - t * kTileRows + kJB - 1) / kJB; }
+            if (t >= tiles) break;
+            cta_score_item<MAXPRO>(xs, n, d, ns, t * kTileRows, t * kTileRows + jb * kJB, lane, st);
+            jb += kCtaThreads / 32;
         }
-        if (MAXPRO) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc += ch[c].flush();
-        }
+        if (MAXPRO) st.flush();
+        const double acc = st.acc, mn = st.mn;
         double part = MAXPRO ? warp_reduce_sum(acc) : warp_reduce_min(mn);
         if (lane == 0) red[warp] = part;
         __syncthreads();
@@ -199,9 +225,101 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
     block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
+// ---- pipelined variant ---------------------------------------------------------------------------
+// Two design buffers per CTA.  While the CTA scores candidate c out of one buffer, candidate c+1 is
+// built in the other: every thread runs its share of the Philox blocks at the top of the
+// iteration (a few hundred instructions), then ONE warp walks the sequential Fisher-Yates steps
+// (n dependent shared-memory round trips, ~20k cycles at n = 500) while the other warps are
+// already scoring; it joins them when the walk is done.  Items are handed out by a shared counter,
+// so the late warp simply takes fewer.  In the single-buffer kernel above the walk holds three of
+// the four warps at a barrier (16% of all warp samples at n = 500, d = 10).
+constexpr int kPipeThreads = 256;
+
+template <bool MAXPRO>
+__global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, d = p.d, ns = p.ns;
+    const size_t xbytes = (size_t)d * ns * sizeof(double);
+    double* const xbase = reinterpret_cast<double*>(smem_raw);
+    const size_t xstride = (size_t)d * ns;  // doubles per buffer
+    unsigned short* jst = reinterpret_cast<unsigned short*>(smem_raw + 2 * xbytes);  // [d][ns]
+    constexpr int kWarps = kPipeThreads / 32;
+    __shared__ double red[kWarps];
+    __shared__ int next_item;
+    __shared__ BestRec warp_best[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles = (n + kTileRows - 1) / kTileRows;
+
+    double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by thread 0
+    unsigned long long best_idx = kNoIndex;
+
+    unsigned long long idx = p.lo + blockIdx.x;
+    if (idx < p.hi) {  // prologue: the first candidate, nothing to overlap it with
+        const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
+        cta_stage_candidate(xbase, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
+        __syncthreads();
+        cta_walk_columns(xbase, jst, n, d, ns, tid, kPipeThreads);
+    }
+    __syncthreads();  // the side array is rewritten at the top of the loop
+    int cur = 0;
+    for (; idx < p.hi; idx += gridDim.x, cur ^= 1) {
+        const unsigned long long nidx = idx + gridDim.x;
+        const bool has_next = nidx < p.hi;
+        // the side array is free (the previous walk ended before the last barrier) and so is the other buffer
+        if (has_next) {
+            const unsigned long long stream = p.seed + nidx;
+            cta_stage_candidate(xbase + (cur ^ 1) * xstride, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
+        }
+        if (tid == 0) next_item = 0;
+        __syncthreads();  // staged values visible to the walker; buffer `cur` complete; counter armed
+        if (has_next && warp == kWarps - 1) cta_walk_columns(xbase + (cur ^ 1) * xstride, jst, n, d, ns, lane, 32);
+
+        // ---- scoring: items (row tile, column block) in tile-major order from the shared counter
+        const double* xs = xbase + cur * xstride;
+        CtaScore st;
+        st.reset();
+        int t = 0, base = 0;
+        int nblk = (n + kJB - 1) / kJB;  // column blocks from the tile's first row
+        while (true) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&next_item, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            while (t < tiles && item - base >= nblk) { base += nblk; ++t; nblk = (n - t * kTileRows + kJB - 1) / kJB; }
+            if (t >= tiles) break;
+            cta_score_item<MAXPRO>(xs, n, d, ns, t * kTileRows, t * kTileRows + (item - base) * kJB, lane, st);
+        }
+        if (MAXPRO) st.flush();
+        const double part = MAXPRO ? warp_reduce_sum(st.acc) : warp_reduce_min(st.mn);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();  // all partial sums in; the walk of the next candidate is done
+        if (tid == 0) {
+            double s = red[0];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s = MAXPRO ? s + red[w] : fmin(s, red[w]);
+            if (!MAXPRO) s = sqrt(s);
+            if (MAXPRO ? (s <= best) : (s >= best)) { best = s; best_idx = idx; }  // later index on ties
+        }
+    }
+    if (tid == 0 && MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
+    if (tid != 0) { best = MAXPRO ? CUDART_INF : -CUDART_INF; best_idx = kNoIndex; }
+    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+}
+
 static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) {
     unsigned long long ns = cta_row_stride(n);
     return (size_t)(((d * ns * 10 + 15) / 16) * 16 + 4 * sizeof(double));
+}
+
+static size_t cta_pipe_smem_bytes(unsigned long long n, unsigned long long d) {
+    unsigned long long ns = cta_row_stride(n);
+    return (size_t)(((d * ns * 18 + 15) / 16) * 16);
+}
+
+// The pipelined kernel pays for its second buffer with occupancy; it is used while two CTAs of
+// eight warps still fit one SM (the single-buffer kernel then runs four CTAs of four warps).
+static bool cta_use_pipe(unsigned long long n, unsigned long long d) {
+    if (const char* e = getenv("MAXPRO_CTA_PIPE")) return atoi(e) != 0 && cta_pipe_smem_bytes(n, d) + 1024 <= kSmemBudget;
+    return 2 * (cta_pipe_smem_bytes(n, d) + 2048) <= kSmemBudget;
 }
 
 bool search_cta_supported(unsigned long long n, unsigned long long d) {
@@ -209,6 +327,12 @@ bool search_cta_supported(unsigned long long n, unsigned long long d) {
 }
 
 int search_cta_grid(unsigned long long n, unsigned long long d, int sms) {
+    if (cta_use_pipe(n, d)) {
+        int per_sm = (int)(kSmemBudget / (cta_pipe_smem_bytes(n, d) + 2048));
+        if (per_sm > 2) per_sm = 2;
+        if (per_sm < 1) per_sm = 1;
+        return sms * per_sm;
+    }
     size_t smem = cta_smem_bytes(n, d) + 1024;
     int per_sm = (int)(kSmemBudget / smem);
     if (per_sm > 4) per_sm = 4;
@@ -225,8 +349,21 @@ cudaError_t launch_search_cta(const SearchLaunch& L) {
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;
-    size_t smem = cta_smem_bytes(L.n, L.d);
     cudaError_t e;
+    if (cta_use_pipe(L.n, L.d)) {
+        const size_t psmem = cta_pipe_smem_bytes(L.n, L.d);
+        if (L.metric == 0) {
+            e = cudaFuncSetAttribute(search_cta_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            if (e != cudaSuccess) return e;
+            search_cta_pipe_kernel<true><<<L.grid, kPipeThreads, psmem, L.stream>>>(p);
+        } else {
+            e = cudaFuncSetAttribute(search_cta_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            if (e != cudaSuccess) return e;
+            search_cta_pipe_kernel<false><<<L.grid, kPipeThreads, psmem, L.stream>>>(p);
+        }
+        return cudaGetLastError();
+    }
+    size_t smem = cta_smem_bytes(L.n, L.d);
     if (L.metric == 0) {
         e = cudaFuncSetAttribute(search_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

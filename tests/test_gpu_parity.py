@@ -214,6 +214,22 @@ def test_search_cta_path_on_medium_shapes(n, d, monkeypatch):
         assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
 
 
+@pytest.mark.parametrize("pipe", ["0", "1"])
+@pytest.mark.parametrize("n,d,iters", [(500, 10, 2500), (130, 10, 3000), (65, 40, 2000), (700, 3, 1200), (64, 1, 900), (9, 33, 700)])
+def test_search_cta_single_and_double_buffered(n, d, iters, pipe, monkeypatch):
+    """Both CTA kernels (one design buffer with a barrier around the Fisher-Yates walk; two buffers
+    with the walk of the next candidate overlapped with the scoring of this one) find the oracle's
+    winner; more candidates than CTAs, so every CTA runs its pipeline for several rounds."""
+    monkeypatch.setenv("MAXPRO_NO_WARP", "1")
+    monkeypatch.setenv("MAXPRO_CTA_PIPE", pipe)
+    seed = 11
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        s_ref, i_ref = oracle.search_range(n, d, metric, seed, 5, 5 + iters)
+        s, i = engine.search_range(n, d, metric, seed, 5, 5 + iters)
+        assert i == i_ref
+        assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+
+
 @pytest.mark.parametrize("n,d", [(100, 5), (128, 8), (150, 3), (200, 4), (31, 9), (64, 9), (101, 10)])
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 def test_search_warp_path_winner(n, d, metric):
