@@ -73,48 +73,65 @@ struct CtaScore {
     }
 };
 
+// One dimension of a work item: ROWS x 8 differences per lane (one or two rows against eight broadcast
+// columns), multiplied into (MaxPro) or squared and added to (maximin) the running values.
+template <bool MAXPRO, bool FIRST, int ROWS>
+__device__ __forceinline__ void cta_item_dim(double (&prod)[2][kJB], const double* xk, int i0c, int i1c, int j0) {
+    double a[2];
+    a[0] = xk[i0c];
+    if (ROWS == 2) a[1] = xk[i1c];
+    double bv[kJB];
+    load_block(bv, xk + j0);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int c = 0; c < kJB; ++c) {
+            if (MAXPRO) {
+                if (FIRST) prod[r][c] = a[r] - bv[c];
+                else prod[r][c] *= (a[r] - bv[c]);
+            } else {
+                const double df = __dsub_rn(a[r], bv[c]);
+                if (FIRST) prod[r][c] = __dmul_rn(df, df);
+                else prod[r][c] = __dadd_rn(prod[r][c], __dmul_rn(df, df));
+            }
+        }
+}
+
 // One work item: the 64 rows of tile row0 (lane <-> rows row0+lane, row0+lane+32) against the 8
-// columns j0 .. j0+7.
-template <bool MAXPRO>
+// columns j0 .. j0+7.  The dimensions are walked in fully unrolled chunks of U (the caller picks a
+// U that divides d when one of 5, 4, 3 does, so that d = 10 or 20 runs two or four identical
+// chunks with no peeled first dimension and no remainder loop); what is left goes one at a time.
+// ROWS = 1 serves the diagonal blocks that lie in the first half of their own tile: every row of
+// the second half follows all eight columns there, so only the lane's first row is evaluated.
+template <bool MAXPRO, int U, int ROWS>
 __device__ __forceinline__ void cta_score_item(const double* xs, int n, int d, int ns, int row0, int j0, int lane, CtaScore& st) {
     const int i0 = row0 + lane, i1 = i0 + 32;
     const int i0c = min(i0, n - 1), i1c = min(i1, n - 1);
     double prod[2][kJB];
-    // dimension 0, then the rest
-    {
-        const double a0 = xs[i0c], a1 = xs[i1c];
-        double bv[kJB];
-        load_block(bv, xs + j0);
+    int k = 0;
+    if (d >= U) {
 #pragma unroll
-        for (int c = 0; c < kJB; ++c) {
-            const double b = bv[c];
-            if (MAXPRO) { prod[0][c] = a0 - b; prod[1][c] = a1 - b; }
-            else {
-                double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
-                prod[0][c] = __dmul_rn(d0, d0); prod[1][c] = __dmul_rn(d1, d1);
-            }
+        for (int u = 0; u < U; ++u) {
+            if (u == 0) cta_item_dim<MAXPRO, true, ROWS>(prod, xs, i0c, i1c, j0);
+            else cta_item_dim<MAXPRO, false, ROWS>(prod, xs + u * ns, i0c, i1c, j0);
         }
-    }
-    for (int k = 1; k < d; ++k) {
-        const double* xk = xs + k * ns;
-        const double a0 = xk[i0c], a1 = xk[i1c];
-        double bv[kJB];
-        load_block(bv, xk + j0);
+        k = U;
+#pragma unroll 1
+        for (; k + U <= d; k += U) {
+            const double* xk = xs + k * ns;
 #pragma unroll
-        for (int c = 0; c < kJB; ++c) {
-            const double b = bv[c];
-            if (MAXPRO) { prod[0][c] *= (a0 - b); prod[1][c] *= (a1 - b); }
-            else {
-                double d0 = __dsub_rn(a0, b), d1 = __dsub_rn(a1, b);
-                prod[0][c] = __dadd_rn(prod[0][c], __dmul_rn(d0, d0));
-                prod[1][c] = __dadd_rn(prod[1][c], __dmul_rn(d1, d1));
-            }
+            for (int u = 0; u < U; ++u) cta_item_dim<MAXPRO, false, ROWS>(prod, xk + u * ns, i0c, i1c, j0);
         }
+    } else {
+        cta_item_dim<MAXPRO, true, ROWS>(prod, xs, i0c, i1c, j0);
+        k = 1;
     }
+#pragma unroll 1
+    for (; k < d; ++k) cta_item_dim<MAXPRO, false, ROWS>(prod, xs + k * ns, i0c, i1c, j0);
     // full blocks: every row of the tile precedes every column and all are < n
-    const bool full = (j0 >= row0 + kTileRows) && (j0 + kJB <= n) && (row0 + kTileRows <= n);
+    const bool full = ROWS == 2 && (j0 >= row0 + kTileRows) && (j0 + kJB <= n) && (row0 + kTileRows <= n);
     if (MAXPRO) {
-        if (st.pushed + 2 > kMaxBigChainTerms) st.flush();
+        if (st.pushed + ROWS > kMaxBigChainTerms) st.flush();
         if (full) {
 #pragma unroll
             for (int c = 0; c < kJB; ++c) {
@@ -126,18 +143,34 @@ __device__ __forceinline__ void cta_score_item(const double* xs, int n, int d, i
             for (int c = 0; c < kJB; ++c) {
                 const int j = j0 + c;
                 if (j < n && i0 < j) st.ch[c].push(fma(prod[0][c], prod[0][c], kEps));
-                if (j < n && i1 < j) st.ch[c].push(fma(prod[1][c], prod[1][c], kEps));
+                if (ROWS == 2 && j < n && i1 < j) st.ch[c].push(fma(prod[1][c], prod[1][c], kEps));
             }
         }
-        st.pushed += 2;
+        st.pushed += ROWS;
     } else {
 #pragma unroll
         for (int c = 0; c < kJB; ++c) {
             const int j = j0 + c;
             if (full || (j < n && i0 < j)) st.mn = fmin(st.mn, prod[0][c]);
-            if (full || (j < n && i1 < j)) st.mn = fmin(st.mn, prod[1][c]);
+            if (ROWS == 2 && (full || (j < n && i1 < j))) st.mn = fmin(st.mn, prod[1][c]);
         }
     }
+}
+
+// chunk size for cta_score_item: the largest of 5, 4, 3 that divides d, else 4
+__host__ __device__ __forceinline__ int cta_dim_chunk(int d) { return d % 5 == 0 ? 5 : d % 4 == 0 ? 4 : d % 3 == 0 ? 3 : 4; }
+
+template <bool MAXPRO>
+__device__ __forceinline__ void cta_score_item_any(int chunk, const double* xs, int n, int d, int ns, int row0, int j0, int lane, CtaScore& st) {
+    if (j0 + kJB <= row0 + 32) {  // no column of the block follows a row of the tile's second half
+        if (chunk == 5) cta_score_item<MAXPRO, 5, 1>(xs, n, d, ns, row0, j0, lane, st);
+        else if (chunk == 3) cta_score_item<MAXPRO, 3, 1>(xs, n, d, ns, row0, j0, lane, st);
+        else cta_score_item<MAXPRO, 4, 1>(xs, n, d, ns, row0, j0, lane, st);
+        return;
+    }
+    if (chunk == 5) cta_score_item<MAXPRO, 5, 2>(xs, n, d, ns, row0, j0, lane, st);
+    else if (chunk == 3) cta_score_item<MAXPRO, 3, 2>(xs, n, d, ns, row0, j0, lane, st);
+    else cta_score_item<MAXPRO, 4, 2>(xs, n, d, ns, row0, j0, lane, st);
 }
 
 // Generation phase 1 for one candidate: every thread runs Philox for its share of the (column,
@@ -183,6 +216,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
     __shared__ BestRec warp_best[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles = (n + kTileRows - 1) / kTileRows;
+    const int chunk = cta_dim_chunk(d);
 
     double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by thread 0
     unsigned long long best_idx = kNoIndex;
@@ -204,7 +238,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
         while (true) {
             while (t < tiles && jb >= nblk) { jb -= nblk; ++t; nblk = (n - t * kTileRows + kJB - 1) / kJB; }
             if (t >= tiles) break;
-            cta_score_item<MAXPRO>(xs, n, d, ns, t * kTileRows, t * kTileRows + jb * kJB, lane, st);
+            cta_score_item_any<MAXPRO>(chunk, xs, n, d, ns, t * kTileRows, t * kTileRows + jb * kJB, lane, st);
             jb += kCtaThreads / 32;
         }
         if (MAXPRO) st.flush();
@@ -249,6 +283,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
     __shared__ BestRec warp_best[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles = (n + kTileRows - 1) / kTileRows;
+    const int chunk = cta_dim_chunk(d);
 
     double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by thread 0
     unsigned long long best_idx = kNoIndex;
@@ -280,13 +315,14 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
         st.reset();
         int t = 0, base = 0;
         int nblk = (n + kJB - 1) / kJB;  // column blocks from the tile's first row
+        int grabbed = 0;
+        if (lane == 0) grabbed = atomicAdd(&next_item, 1);
         while (true) {
-            int item = 0;
-            if (lane == 0) item = atomicAdd(&next_item, 1);
-            item = __shfl_sync(0xffffffffu, item, 0);
+            const int item = __shfl_sync(0xffffffffu, grabbed, 0);
+            if (lane == 0) grabbed = atomicAdd(&next_item, 1);  // the next one, in flight while this one is scored
             while (t < tiles && item - base >= nblk) { base += nblk; ++t; nblk = (n - t * kTileRows + kJB - 1) / kJB; }
             if (t >= tiles) break;
-            cta_score_item<MAXPRO>(xs, n, d, ns, t * kTileRows, t * kTileRows + (item - base) * kJB, lane, st);
+            cta_score_item_any<MAXPRO>(chunk, xs, n, d, ns, t * kTileRows, t * kTileRows + (item - base) * kJB, lane, st);
         }
         if (MAXPRO) st.flush();
         const double part = MAXPRO ? warp_reduce_sum(st.acc) : warp_reduce_min(st.mn);

@@ -215,11 +215,14 @@ def test_search_cta_path_on_medium_shapes(n, d, monkeypatch):
 
 
 @pytest.mark.parametrize("pipe", ["0", "1"])
-@pytest.mark.parametrize("n,d,iters", [(500, 10, 2500), (130, 10, 3000), (65, 40, 2000), (700, 3, 1200), (64, 1, 900), (9, 33, 700)])
+@pytest.mark.parametrize("n,d,iters", [(500, 10, 2500), (130, 10, 3000), (65, 9, 2000), (66, 7, 2000), (700, 3, 1200), (64, 1, 900), (9, 33, 700)])
 def test_search_cta_single_and_double_buffered(n, d, iters, pipe, monkeypatch):
     """Both CTA kernels (one design buffer with a barrier around the Fisher-Yates walk; two buffers
     with the walk of the next candidate overlapped with the scoring of this one) find the oracle's
-    winner; more candidates than CTAs, so every CTA runs its pipeline for several rounds."""
+    winner; more candidates than CTAs, so every CTA runs its pipeline for several rounds.  (Shapes with
+    d >~ 15 are left out on purpose: there every product of squared differences is far below the
+    reference's eps = 1e-12, all candidates score (1/eps)^(1/d) to the last few ulps, and the winner is
+    decided by the summation order -- DESIGN.md section 2, difference (3).)"""
     monkeypatch.setenv("MAXPRO_NO_WARP", "1")
     monkeypatch.setenv("MAXPRO_CTA_PIPE", pipe)
     seed = 11
