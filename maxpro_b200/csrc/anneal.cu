@@ -270,6 +270,7 @@ static int round_up_32(unsigned long long v) { return (int)((v + 31) / 32 * 32);
 cudaError_t launch_anneal(const AnnealLaunch& L) {
     if (cudaError_t e0 = launch_anneal_raw0(L); e0 != cudaSuccess) return e0;
     if (anneal_pipe_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_pipe(L);
+    if (anneal_maximin_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_maximin(L);
     AnnealParams p;
     p.design = L.design; p.n = L.n; p.d = L.d; p.iters = L.iters; p.seed = L.seed; p.n_chains = L.n_chains;
     p.t0 = L.t0; p.cooling = L.cooling; p.step = 0.01 / (double)L.n;  // anneal.rs:86-87

@@ -22,6 +22,8 @@ struct AnnealParams {
     unsigned int* improved;     // [n_chains]
     const double* raw0;         // S (or min squared distance) of the start design: every chain starts there,
                                 // so it is computed once by anneal_raw0_kernel instead of once per chain
+    const double* rowmin0;      // anneal_maximin.cu: nearest-neighbour squared distance of every row of the start design
+    const unsigned short* rowarg0;  //               and the neighbour that attains it
 };
 
 // Deterministic block reduction in two halves.  Every thread: lane tree, lane 0 publishes the

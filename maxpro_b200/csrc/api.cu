@@ -597,7 +597,7 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     const size_t nd = n * d;
     DevBuf dx, db, dm, di, dr;
     CUDA_TRY(dx.alloc(nd * sizeof(double)));
-    CUDA_TRY(dr.alloc(sizeof(double)));
+    CUDA_TRY(dr.alloc((2 * n + 2) * sizeof(double)));  // raw0, then the nearest-neighbour table: n doubles, n 16-bit indices
     CUDA_TRY(db.alloc(n_chains * nd * sizeof(double)));
     CUDA_TRY(dm.alloc(n_chains * sizeof(double)));
     CUDA_TRY(di.alloc(n_chains * sizeof(unsigned int)));
@@ -607,6 +607,7 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     L.design = dx.as<double>(); L.n = n; L.d = d; L.iters = n_iterations; L.seed = seed; L.n_chains = n_chains;
     L.t0 = initial_temp; L.cooling = cooling_rate; L.metric = metric; L.minimize = minimize ? 1 : 0; L.swap = swap ? 1 : 0;
     L.best_design = db.as<double>(); L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.raw0 = dr.as<double>(); L.stream = st;
+    L.rowmin0 = dr.as<double>() + 1; L.rowarg0 = reinterpret_cast<unsigned short*>(dr.as<double>() + 1 + n);
     CUDA_TRY(mp::launch_anneal(L));
     std::vector<double> metrics(n_chains);
     std::vector<unsigned int> improved(n_chains);

@@ -82,6 +82,8 @@ struct AnnealLaunch {
     double* best_metric;     // [n_chains]
     unsigned int* improved;  // [n_chains]
     double* raw0;            // device scratch, 1 double: S (or min squared distance) of the start design
+    double* rowmin0;         // device scratch, n doubles and n 16-bit indices: nearest-neighbour table of the
+    unsigned short* rowarg0; // start design (incremental maximin chains, anneal_maximin.cu)
     cudaStream_t stream;
 };
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap);
@@ -89,6 +91,9 @@ cudaError_t launch_anneal(const AnnealLaunch& L);
 // swap moves on MaxPro as a two-stage pipeline (anneal_pipe.cu); launch_anneal dispatches to it
 bool anneal_pipe_supported(unsigned long long n, unsigned long long d, int metric, int swap);
 cudaError_t launch_anneal_pipe(const AnnealLaunch& L);
+// swap moves on maximin with an exact nearest-neighbour table (anneal_maximin.cu); launch_anneal dispatches to it
+bool anneal_maximin_supported(unsigned long long n, unsigned long long d, int metric, int swap);
+cudaError_t launch_anneal_maximin(const AnnealLaunch& L);
 
 // ---- K4: greedy ordering ------------------------------------------------------------
 struct OrderLaunch {

@@ -358,6 +358,35 @@ def test_anneal_swap_pipeline_matches_oracle(n, d, iters, cooling, monkeypatch):
     assert np.array_equal(got2, ref) and math.isclose(best2, ref_best, rel_tol=REL)
 
 
+@pytest.mark.parametrize("n,d,iters,minimize", [(200, 4, 1500, False), (121, 6, 1200, False), (64, 3, 3000, False), (2, 3, 50, False),
+                                                 (3, 1, 200, False), (33, 1, 800, False), (40, 35, 600, False), (90, 2, 1500, True),
+                                                 (700, 5, 250, False)])
+def test_anneal_maximin_swap_incremental_matches_oracle(n, d, iters, minimize, monkeypatch):
+    """Swap moves on maximin keep an exact nearest-neighbour table (anneal_maximin.cu) instead of
+    re-scoring all pairs: the criterion of every step is the reference's bit for bit, so the chain
+    must end in the oracle's design; the full re-score kernel (MAXPRO_NO_ANNEAL_MAXIMIN_INC=1)
+    must agree as well.  minimize=True walks the other way (towards clustered points, many dirty rows)."""
+    x = oracle.generate_lhd(n, d, 31)
+    ref, ref_best = oracle.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True)
+    got, best, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
+    assert np.array_equal(got, ref) and best == ref_best
+    assert best == oracle.maximin_criterion(got)  # the returned design is the global best of the chain
+    monkeypatch.setenv("MAXPRO_NO_ANNEAL_MAXIMIN_INC", "1")
+    got2, best2, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
+    assert np.array_equal(got2, ref) and best2 == ref_best
+
+
+def test_anneal_maximin_swap_incremental_grid_design_and_chains(r_golden):
+    """Exact ties everywhere (the R design lies on a grid) and many chains at once."""
+    x = np.asarray(r_golden["design"], dtype=np.float64)
+    refs = [oracle.anneal_lhd(x, 800, 0.02, 0.99, METRIC_MAXIMIN, False, 5 + c, True) for c in range(8)]
+    got, best, chain = engine.anneal_lhd(x, 800, 0.02, 0.99, METRIC_MAXIMIN, False, 5, True, n_chains=8)
+    ref_best = max(r[1] for r in refs)
+    ref_chain = [r[1] for r in refs].index(ref_best)
+    assert chain == ref_chain and best == ref_best
+    assert np.array_equal(got, refs[ref_chain][0])
+
+
 @pytest.mark.parametrize("n,d", [(4, 1), (5, 2), (7, 3), (33, 1), (51, 7), (97, 2)])
 def test_anneal_swap_pipeline_edge_shapes(n, d):
     """Tiny and odd shapes: almost every pair of consecutive moves shares a row at n = 4..7 (the
