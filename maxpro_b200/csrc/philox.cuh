@@ -69,6 +69,34 @@ __device__ __forceinline__ double stratum_value(uint32_t i, uint32_t jit, double
     return fma(__ull2double_rn(m), c1, c0);
 }
 
+// The sequential half of the inside-out Fisher-Yates shuffle for one column whose draws were staged
+// beforehand: a[i] holds the stratum value v_i and js[i] the index drawn for step i, and step i does
+//   t = a[j_i];  a[i] = t;  a[j_i] = v_i.
+// Steps before i touch positions below i only, so a[i] and js[i] of the next eight steps are read
+// ahead of the dependent part: one shared-memory round trip per step instead of two.
+__device__ __forceinline__ void fy_walk_column(double* a, const unsigned short* js, int n) {
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        int j[8];
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { j[u] = js[i + u]; v[u] = a[i + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double t = a[j[u]];
+            a[i + u] = t;
+            a[j[u]] = v[u];
+        }
+    }
+    for (; i < n; ++i) {
+        const int j = js[i];
+        const double v = a[i];
+        const double t = a[j];
+        a[i] = t;
+        a[j] = v;
+    }
+}
+
 // (w * bound) >> 32 : multiply-shift map of a 32-bit word onto [0, bound).
 __host__ __device__ __forceinline__ uint32_t mulhi_bound(uint32_t w, uint32_t bound) {
     return (uint32_t)(((uint64_t)w * (uint64_t)bound) >> 32);

@@ -193,17 +193,7 @@ __device__ __forceinline__ void cta_stage_candidate(double* xs, unsigned short* 
 
 // Generation phase 2: lane k of the calling group walks the n dependent steps of column k.
 __device__ __forceinline__ void cta_walk_columns(double* xs, const unsigned short* jst, int n, int d, int ns, int first, int step) {
-    for (int k = first; k < d; k += step) {
-        double* a = xs + k * ns;
-        const unsigned short* js = jst + k * ns;
-        for (int i = 0; i < n; ++i) {
-            const int j = js[i];
-            const double v = a[i];
-            const double t = a[j];
-            a[i] = t;
-            a[j] = v;
-        }
-    }
+    for (int k = first; k < d; k += step) fy_walk_column(xs + k * ns, jst + k * ns, n);
 }
 
 template <bool MAXPRO>

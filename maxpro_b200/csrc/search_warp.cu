@@ -78,17 +78,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
         }
         __syncwarp();
         // ---- generation, phase 2: one lane per column
-        for (int k = lane; k < d; k += 32) {
-            double* a = xs + k * ns;
-            const unsigned short* js = jst + k * n;
-            for (int i = 0; i < n; ++i) {
-                const int j = js[i];
-                const double v = a[i];
-                const double t = a[j];
-                a[i] = t;
-                a[j] = v;
-            }
-        }
+        for (int k = lane; k < d; k += 32) fy_walk_column(xs + k * ns, jst + k * n, n);
         __syncwarp();
         // rows n .. n + 8*nblk - 1 repeat rows 0 .. (wrapping again if the design is tiny)
         for (int e = lane; e < d * kWarpSB * nblk; e += 32) {
