@@ -341,10 +341,10 @@ def main():
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / peak_tflops if peak_tflops else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full`
-                     # (profiles/r1f_search_cyclic_metrics.csv: 46,848 B read, 0 B written for 16.8M candidates;
+                     # (profiles/r1g_search_cyclic_metrics.csv: 236,544 B read, 0 B written for 16.8M candidates;
                      # it is instruction/constant fetch and does not grow with the candidate count).
                      # Algorithmic HBM bytes per candidate: 0.
-                     "traffic": 46848,
+                     "traffic": 236544,
                      "peak_source": ("DFMA probe measured in this run" if peak_tflops == probed_tflops else
                                      "nominal (the in-run DFMA probe came out lower and was discarded)")
                                     + "; MEASURED_PEAKS.json has no FP64 figure; "
@@ -352,7 +352,7 @@ def main():
                      "peak_probed": probed_tflops,
                      "flops_per_candidate": FLOPS_PER_CANDIDATE, "kernel": "search_cyclic_kernel<50,3,192,true>",
                      "kernel_ms_per_launch": kernel_ms, "candidates_per_launch": per_gpu,
-                     "note": "algorithmic flops; the kernel issues ~8.4 FP64-pipe instructions per pair for 12 "
+                     "note": "algorithmic flops; the kernel issues ~8.3 FP64-pipe instructions per pair for 12 "
                              "algorithmic flops, see profiles/ for pipe utilisation"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 16 + N_POINTS * N_DIMS * 8,

@@ -265,14 +265,17 @@ __device__ __forceinline__ void cyc_token_wait(int id) { asm volatile("bar.sync 
 __device__ __forceinline__ void cyc_token_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 // Turn-taking on the FP64 pipe.  Each warp alternates an integer-only, latency-bound phase
-// (Philox + Fisher-Yates, ~17k cycles) and an FP64-bound phase (the pair loop, ~10k pipe
+// (Philox + Fisher-Yates, ~15k cycles) and an FP64-bound phase (the pair loop, ~10k pipe
 // cycles).  The warps of a sub-partition (warp id mod 4) share the pipe fairly, so left alone
 // they tend to finish scoring together and then generate together.  With p.ring = 2 the first
 // two warps of every sub-partition pass a token (strict alternation) and the third runs free;
 // p.ring = 3 serialises all three.  MEASURED (profiles/README.md): neither helps -- 1.07 / 1.01
-// vs 1.08 Gcand/s without -- because an FP64 instruction holds the sub-partition's issue port
-// for 2 cycles, so time ~ 2*N_fp64 + N_other whatever the interleaving.  Kept as an
-// experiment switch (MAXPRO_CYCLIC_RING), off by default.
+// vs 1.08 Gcand/s without.  The micro-probes of tools/micro (philox_lat.cu, issue2.cu) say why:
+// Philox's IMAD.WIDE + LOP3 stream and a DFMA stream do not overlap on a sub-partition, whether
+// they come from two warps or are interleaved in one (a Philox warp slows a DFMA warp beside it
+// from 2.07 to 3.56 cycles per instruction), so the two phases cost their sum however they are
+// arranged, and a lone scoring warp reaches only ~62% of the pipe.  Kept as an experiment switch
+// (MAXPRO_CYCLIC_RING), off by default.
 template <int N, int D, int C, bool MAXPRO, bool SUPPLIED = false>
 __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -375,7 +378,7 @@ bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* ca
 
 cudaError_t launch_search_cyclic(const SearchLaunch& L) {
     CyclicParams p;
-    p.ring = 0;  // measured: turn-taking does not pay (the FP64 issue port, not phase overlap, is the limit)
+    p.ring = 0;  // measured: turn-taking does not pay (generation and scoring cost their sum either way)
     if (const char* e = getenv("MAXPRO_CYCLIC_RING")) { int v = atoi(e); if (v == 0 || v == 2 || v == 3) p.ring = v; }
     if (p.ring > (L.threads / 32) / 4) p.ring = 0;
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;

@@ -12,8 +12,8 @@
 // It replaces the same reference code as the fp64 kernels (src/lib.rs:65-98, src/lhd.rs:97-132,
 // src/maxpro_utils.rs:28-83) and draws the same LHD-Philox v1 stream (values rounded to fp32).
 //
-// Why it is faster: fp32 instructions issue at 1 per cycle per sub-partition (an FP64
-// instruction holds the issue port for 2), a design is 600 B instead of 1200 B so ONE lane per
+// Why it is faster: an fp32 instruction occupies its pipe for one cycle per warp where an FP64
+// instruction occupies the FP64 pipe for two, a design is 600 B instead of 1200 B so ONE lane per
 // candidate still gives 12 warps per SM (no duplicated tile loads, no idle generator lane).
 //
 // fp32 range: terms p = q^2 + eps span [1e-12, 1] = [2^-40, 1]; a reciprocal chain of 6 terms

@@ -72,6 +72,18 @@ if "c4" in which:
          cpu_chain_steps_per_s_1core_full_rescore=20 / t_cpu, start_metric=oracle.maxpro_criterion(x), best_metric=best)
     (out, best, ch), t_gpu = timed(engine.anneal_lhd, x, steps, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, chains)
     emit(config="C4-second-call", gpu_s=t_gpu, gpu_chain_steps_per_s=chains * steps / t_gpu)
+    # swap moves on maximin: exact nearest-neighbour table (anneal_maximin.cu) vs the full re-score kernel
+    import os
+    engine.anneal_lhd(x, 10, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
+    (out, bestm, ch), t_m = timed(engine.anneal_lhd, x, 1000, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
+    os.environ["MAXPRO_NO_ANNEAL_MAXIMIN_INC"] = "1"
+    engine.anneal_lhd(x, 2, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
+    (_, bestf, _), t_f = timed(engine.anneal_lhd, x, 20, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
+    del os.environ["MAXPRO_NO_ANNEAL_MAXIMIN_INC"]
+    (_, b20, _), _t = timed(engine.anneal_lhd, x, 20, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
+    emit(config="C4-maximin-swap", n=n, d=d, chains=chains, steps=1000, gpu_s=t_m, gpu_chain_steps_per_s=chains * 1000 / t_m,
+         full_rescore_chain_steps_per_s=chains * 20 / t_f, same_best_after_20_steps=(b20 == bestf),
+         start_metric=oracle.maximin_criterion(x), best_metric=bestm)
     # jitter moves need the proposal beside the current design in shared memory: n*d*16 B <= 227 KB
     xj = engine.generate_lhd(500, 10, 42)
     (out, best, ch), t_j = timed(engine.anneal_lhd, xj, 100, 1.0, 0.99, METRIC_MAXPRO, True, 43, False, 1184)

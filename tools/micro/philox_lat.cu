@@ -1,6 +1,7 @@
 // Philox4x32-10 latency/throughput probe and cross-warp interference with an FP64 stream.
 // roles per warp (warp w runs on sub-partition w % 4): 'P' = dependent Philox chains (ILP chains per
-// thread), 'D' = 8 independent DFMA chains, '-' = exit at once.  Prints cycles per Philox call
+// thread), 'Q' = the same with the products split into mul.hi + mul.lo, 'D' = 8 independent DFMA chains,
+// 'M'/'N' = one Philox call + 40/80 DFMAs interleaved in one warp, '-' = exit at once.  Prints cycles per Philox call
 // (per chain) and cycles per DFMA for every configuration.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../maxpro_b200/csrc -o philox_lat philox_lat.cu
 #include <cstdio>
@@ -10,9 +11,7 @@
 using namespace mp;
 
 // Philox round with the 32x32->64 product taken as mul.hi + mul.lo instead of one mul.wide
-__device__ uint32_t g_m[2] = {0xD2511F53u, 0xCD9E8D57u};
-__device__ __forceinline__ Philox4 philox_hilo(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-    const uint32_t m0 = ((volatile uint32_t*)g_m)[0], m1 = ((volatile uint32_t*)g_m)[1];
+__device__ __forceinline__ Philox4 philox_hilo(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t m0, uint32_t m1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
@@ -27,14 +26,14 @@ __device__ __forceinline__ Philox4 philox_hilo(uint32_t c0, uint32_t c1, uint32_
     return Philox4{c0, c1, c2, c3};
 }
 template <int ILP>
-__device__ __forceinline__ unsigned philox2_role(int iters) {
+__device__ __forceinline__ unsigned philox2_role(int iters, uint32_t m0, uint32_t m1) {
     uint32_t c[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; ++i) c[i] = threadIdx.x * 7 + i;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < ILP; ++i) {
-            Philox4 w = philox_hilo(c[i], 1u, 2u, 3u, kKeyLhd0, kKeyLhd1);
+            Philox4 w = philox_hilo(c[i], 1u, 2u, 3u, kKeyLhd0, kKeyLhd1, m0, m1);
             c[i] = w.x ^ w.y ^ w.z ^ w.w;
         }
     }
@@ -107,14 +106,14 @@ __device__ __forceinline__ double mixed_role(int iters, double y, double z) {
 
 // roles: string of up to 16 chars, one per warp
 template <int ILP>
-__global__ void probe(const char* roles, int nw, int p_iters, int d_iters, double y, double z, long long* cyc, double* sink) {
+__global__ void probe(const char* roles, int nw, int p_iters, int d_iters, double y, double z, long long* cyc, double* sink, uint32_t m0, uint32_t m1) {
     const int w = threadIdx.x >> 5;
     const char role = roles[w];
     __syncthreads();
     long long t0 = clock64();
     double s = 0;
     if (role == 'P') s = philox_role<ILP>(p_iters);
-    else if (role == 'Q') s = philox2_role<ILP>(p_iters);
+    else if (role == 'Q') s = philox2_role<ILP>(p_iters, m0, m1);
     else if (role == 'D') s = dfma_role(d_iters, y, z);
     else if (role == 'M') s = mixed_role<ILP, 40>(p_iters, y, z);
     else if (role == 'N') s = mixed_role<ILP, 80>(p_iters, y, z);
@@ -131,7 +130,7 @@ static void run(const char* roles) {
     double* sink; cudaMalloc(&sink, 8);
     const int p_iters = 4096 / ILP, d_iters = 4096;
     for (int r = 0; r < 2; ++r) {
-        probe<ILP><<<148, 32 * nw>>>(d_roles, nw, p_iters, d_iters, 0.9999999, 1e-9, cyc, sink);
+        probe<ILP><<<148, 32 * nw>>>(d_roles, nw, p_iters, d_iters, 0.9999999, 1e-9, cyc, sink, kPhiloxM0, kPhiloxM1);
         cudaDeviceSynchronize();
     }
     printf("roles %-16s ILP %d:", roles, ILP);
@@ -146,8 +145,16 @@ static void run(const char* roles) {
 
 int main() {
     printf("warp w runs on sub-partition w %% 4; 'P' Philox4x32-10 chains, 'D' DFMA stream\n");
-    run<2>("P"); run<2>("P---P---P"); run<2>("P---D"); run<2>("P---D---D");
-    run<2>("Q"); run<4>("Q"); run<2>("Q---Q---Q"); run<2>("Q---D"); run<2>("Q---D---D"); run<2>("Q---Q---D"); run<4>("Q---D---D");
+    printf("-- Philox alone: latency (ILP 1) and throughput\n");
+    run<1>("P"); run<2>("P"); run<4>("P"); run<8>("P"); run<2>("P---P"); run<2>("P---P---P");
+    printf("-- DFMA alone\n");
+    run<1>("D"); run<1>("D---D"); run<1>("D---D---D");
+    printf("-- a Philox warp beside DFMA warps on the same sub-partition\n");
+    run<2>("P---D"); run<2>("P---D---D"); run<2>("P---P---D"); run<4>("P---D---D");
+    printf("-- one call + 40 (M) or 80 (N) DFMAs interleaved in the same warp\n");
+    run<2>("M"); run<2>("M---M---M"); run<4>("M---M---M"); run<2>("N"); run<2>("N---N---N");
+    printf("-- 32x32->64 products as mul.hi + mul.lo with a register multiplier (no IMAD.WIDE)\n");
+    run<2>("Q"); run<2>("Q---Q---Q"); run<2>("Q---D"); run<2>("Q---D---D");
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
