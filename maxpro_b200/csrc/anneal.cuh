@@ -54,7 +54,7 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
     double acc = 0.0, mn = CUDART_INF;
     RecipChain ch[SB];
 #pragma unroll
-    for (int c = 0; c < SB; ++c) ch[c].reset_big();
+    for (int c = 0; c < SB; ++c) ch[c].reset();
     int pushed = 0;
     const int half = (n - 1) / 2;
     const bool even = (n & 1) == 0;
@@ -89,9 +89,9 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
             }
             if (MAXPRO) {
                 if (in_cube) {
-                    if (pushed == kMaxBigChainTerms) {
+                    if (pushed == kMaxChainTerms) {
 #pragma unroll
-                        for (int c = 0; c < SB; ++c) acc = ch[c].flush_big_into(acc);
+                        for (int c = 0; c < SB; ++c) acc = ch[c].flush_into(acc);
                         pushed = 0;
                     }
 #pragma unroll
@@ -112,7 +112,7 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
     }
     if (MAXPRO) {
 #pragma unroll
-        for (int c = 0; c < SB; ++c) acc = ch[c].flush_big_into(acc);
+        for (int c = 0; c < SB; ++c) acc = ch[c].flush_into(acc);
     }
     return MAXPRO ? acc : mn;  // this thread's share; the caller reduces
 }

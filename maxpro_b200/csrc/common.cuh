@@ -7,10 +7,10 @@
 namespace mp {
 
 constexpr double kEps = 1e-12;  // src/maxpro_utils.rs:35
-constexpr int kMaxChainTerms = 16;  // terms a RecipChain may hold before a flush (den >= 1e-192)
-// A chain whose denominator starts at 2^1000 instead of 1 (num/den is scale-free) has the whole
-// exponent range below it: 2^1000 * (1e-12)^k >= 1e-300 holds for k <= 50, and num <= k * 2^1000.
-constexpr int kMaxBigChainTerms = 48;
+// Terms a RecipChain may hold before a flush.  The chain's denominator starts at 2^1000 instead of 1
+// (num/den is scale-free), so it has the whole exponent range below it: 2^1000 * (1e-12)^k >= 1e-300
+// holds for k <= 50, and num <= k * 2^1000.
+constexpr int kMaxChainTerms = 48;
 
 // Winner record that leaves the chip: 16 bytes.
 struct __align__(16) BestRec {
@@ -69,18 +69,17 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 // Running sum of reciprocals without a divide per term:
 //   num/den + 1/p = (num*p + den) / (den*p)
-// Two FP64 ops per pushed term; one reciprocal per flush.  Safe while the
-// product of pushed terms stays in range: every p is in [1e-12, ~1] for
-// designs in the unit cube, so <= 16 terms keep den >= 1e-192.
+// Two FP64 ops per pushed term; one reciprocal per flush.  Safe while the product of pushed terms
+// stays in range: every p is in [1e-12, ~1] for designs in the unit cube, so kMaxChainTerms terms
+// keep den inside [1e-300, 2^1000] (see above).
 struct RecipChain {
     double num, den;
-    __device__ __forceinline__ void reset() { num = 0.0; den = 1.0; }
-    __device__ __forceinline__ void reset_big() { num = 0.0; den = 0x1p1000; }
+    __device__ __forceinline__ void reset() { num = 0.0; den = 0x1p1000; }
     __device__ __forceinline__ void push(double p) { num = fma(num, p, den); den *= p; }
-    __device__ __forceinline__ double flush() { double v = num * fast_rcp(den); reset(); return v; }
     // acc + num/den with the quotient good to ~2^-40 (one Newton step on the 20-bit MUFU seed,
     // the residual folded into the final FMA): every partial sum is then within 1e-12 relative,
-    // three orders inside the 1e-9 parity bar, for 3 FP64 instructions instead of 5.
+    // three orders inside the 1e-9 parity bar, for 4 FP64 instructions.  den is a normal number
+    // throughout, so are the seed and the residual.
     __device__ __forceinline__ double flush_into(double acc) {
         double r;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
@@ -88,17 +87,6 @@ struct RecipChain {
         const double nr = num * r;
         const double v = fma(nr, e, nr);  // num * r * (1 + e)
         reset();
-        return acc + v;
-    }
-    // the same for a chain started by reset_big(): den in [1e-300, 2^1000], so the seed and the
-    // Newton residual stay normal numbers
-    __device__ __forceinline__ double flush_big_into(double acc) {
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-        const double e = fma(-den, r, 1.0);
-        const double nr = num * r;
-        const double v = fma(nr, e, nr);
-        reset_big();
         return acc + v;
     }
 };

@@ -63,12 +63,12 @@ struct CtaScore {
     double acc, mn;
     __device__ __forceinline__ void reset() {
 #pragma unroll
-        for (int c = 0; c < kJB; ++c) ch[c].reset_big();
+        for (int c = 0; c < kJB; ++c) ch[c].reset();
         pushed = 0; acc = 0.0; mn = CUDART_INF;
     }
     __device__ __forceinline__ void flush() {
 #pragma unroll
-        for (int c = 0; c < kJB; ++c) acc = ch[c].flush_big_into(acc);
+        for (int c = 0; c < kJB; ++c) acc = ch[c].flush_into(acc);
         pushed = 0;
     }
 };
@@ -131,7 +131,7 @@ __device__ __forceinline__ void cta_score_item(const double* xs, int n, int d, i
     // full blocks: every row of the tile precedes every column and all are < n
     const bool full = ROWS == 2 && (j0 >= row0 + kTileRows) && (j0 + kJB <= n) && (row0 + kTileRows <= n);
     if (MAXPRO) {
-        if (st.pushed + ROWS > kMaxBigChainTerms) st.flush();
+        if (st.pushed + ROWS > kMaxChainTerms) st.flush();
         if (full) {
 #pragma unroll
             for (int c = 0; c < kJB; ++c) {

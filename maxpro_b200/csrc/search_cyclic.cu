@@ -166,19 +166,19 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
     constexpr int kFlushEvery = 3;                    // tiles between flushes
     constexpr int kDiam = (N % 2 == 0) ? (N / 2 + 1) / 2 : 0;  // diameter pairs per lane
     static_assert(N % R == 0 && kHalf % G == 0, "whole tiles, equal shift ranges");
-    static_assert(kFlushEvery * kPerLane + (kDiam + R - 1) / R <= kMaxBigChainTerms, "chains stay in range between flushes");
+    static_assert(kFlushEvery * kPerLane + (kDiam + R - 1) / R <= kMaxChainTerms, "chains stay in range between flushes");
     constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
 
     RecipChain ch[R];
     double mins[R];
     double acc = 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { ch[r].reset_big(); mins[r] = CUDART_INF; }
+    for (int r = 0; r < R; ++r) { ch[r].reset(); mins[r] = CUDART_INF; }
     const unsigned first_off = (1u + (unsigned)g * kPerLane) * RB;  // this lane's first shift
     auto flush_all = [&]() {
         if (MAXPRO && !SAFE) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc = ch[r].flush_big_into(acc);
+            for (int r = 0; r < R; ++r) acc = ch[r].flush_into(acc);
         }
     };
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ void generate_column(double* col, int stride, int n, 
     }
 }
 
-constexpr int kMaxChain = kMaxBigChainTerms;  // terms per RecipChain (started at 2^1000, common.cuh) before a flush
+constexpr int kMaxChain = kMaxChainTerms;  // terms per RecipChain (started at 2^1000, common.cuh) before a flush
 
 // Score one design held in shared memory by a group of G lanes (G = 1 or 2).
 // MAXPRO: returns this lane's share of S = sum_{i<j} 1/(prod diff^2 + eps)
@@ -106,12 +106,12 @@ __device__ __forceinline__ double score_group_design(const double* xs, int strid
     double mins[R];
     double acc = 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { ch[r].reset_big(); mins[r] = CUDART_INF; }
+    for (int r = 0; r < R; ++r) { ch[r].reset(); mins[r] = CUDART_INF; }
     int pushed = 0;  // uniform upper bound on terms held by any chain
 
     auto flush_all = [&]() {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc = ch[r].flush_big_into(acc);
+        for (int r = 0; r < R; ++r) acc = ch[r].flush_into(acc);
         pushed = 0;
     };
     auto load_row = [&](double (&dst)[D], int row) {

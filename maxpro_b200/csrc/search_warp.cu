@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
         double acc = 0.0, mn = CUDART_INF;
         RecipChain ch[kWarpSB];
 #pragma unroll
-        for (int c = 0; c < kWarpSB; ++c) ch[c].reset_big();
+        for (int c = 0; c < kWarpSB; ++c) ch[c].reset();
         int pushed = 0;
         int i = lane % n, b = lane / n;  // n may be below 32
         for (int q = lane; q < items; q += 32) {
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
             }
             const bool whole = s0 + kWarpSB - 1 <= my_smax;  // false only in a row's last shift block
             if (MAXPRO) {
-                if (pushed == kMaxBigChainTerms) {
+                if (pushed == kMaxChainTerms) {
 #pragma unroll
-                    for (int c = 0; c < kWarpSB; ++c) acc = ch[c].flush_big_into(acc);
+                    for (int c = 0; c < kWarpSB; ++c) acc = ch[c].flush_into(acc);
                     pushed = 0;
                 }
                 if (whole) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
         }
         if (MAXPRO) {
 #pragma unroll
-            for (int c = 0; c < kWarpSB; ++c) acc = ch[c].flush_big_into(acc);
+            for (int c = 0; c < kWarpSB; ++c) acc = ch[c].flush_into(acc);
         }
         double s = MAXPRO ? warp_reduce_sum(acc) : warp_reduce_min(mn);
         if (!MAXPRO) s = sqrt(s);
