@@ -311,8 +311,14 @@ static cudaError_t launch_d(const SearchLaunch& L, const SearchParams& p) {
     }
 }
 
+// Shapes this kernel takes: at least 48 candidates must fit one SM's shared memory (n*d*8 B <= ~4.8 KB).
+// Measured against the warp-per-candidate kernel (tools/shape_sweep.py): with 48 instead of 64,
+// (100,5) 8.3 -> 9.3, (128,4) 9.4 -> 11.1, (300,2) 11.1 -> 12.7 algorithmic TFLOP/s; with 32, (200,4),
+// (250,3) and (100,8) lose 25-30 %.
 bool search_small_supported(unsigned long long n, unsigned long long d) {
-    return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * 64 + 32 * sizeof(BestRec) <= kSmemBudget;
+    unsigned long long min_cands = 48;
+    if (const char* e = getenv("MAXPRO_SMALL_MIN_CANDS")) { int v = atoi(e); if (v >= 16 && v <= 512 && v % 16 == 0) min_cands = (unsigned long long)v; }
+    return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * min_cands + 32 * sizeof(BestRec) <= kSmemBudget;
 }
 
 // Lanes per candidate and CTA size.  Two lanes per candidate whenever there are at least two

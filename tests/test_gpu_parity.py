@@ -172,7 +172,7 @@ def test_generate_lhd_reference_test():
 
 # ---------------------------------------------------------------- fused search (K1+K2)
 
-SMALL_SHAPES = [(50, 3), (50, 2), (7, 2), (13, 5), (50, 8), (2, 1), (3, 3), (9, 4), (25, 6), (11, 7), (100, 1)]
+SMALL_SHAPES = [(50, 3), (50, 2), (7, 2), (13, 5), (50, 8), (2, 1), (3, 3), (9, 4), (25, 6), (11, 7), (100, 1), (100, 5), (120, 5), (300, 2), (75, 8)]
 
 
 @pytest.mark.parametrize("n,d", SMALL_SHAPES)
