@@ -36,9 +36,15 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     const int n = (int)p.n, d = (int)p.d, nd = n * d;
     const int ns = (n + 1) & ~1;                      // even row stride: 16-byte partner loads
     const int dns = d * ns;
-    double* cur = smem_d;                             // [k][i]
-    double* cand = p.swap ? cur : smem_d + dns;       // jitter needs the proposal beside the current
-    double* part = smem_d + (p.swap ? dns : 2 * dns);   // 32 doubles: warp partials of a reduction
+    // Jitter needs the proposal beside the current design.  When both fit, both live in shared memory;
+    // when only one does (n*d*8 B > ~113 KB, e.g. n=1000, d=20), the proposal takes the shared memory
+    // and the current design lives in a per-CTA scratch buffer in HBM (p.cur_global): it is read once
+    // per iteration to build the proposal and written once per ACCEPTED move -- 2 x 160 KB per step
+    // next to a full O(n^2 d) re-score, i.e. a few percent of the step.
+    const bool cur_in_hbm = !p.swap && p.cur_global != nullptr;
+    double* cur = cur_in_hbm ? p.cur_global + (size_t)blockIdx.x * dns : smem_d;   // [k][i]
+    double* cand = p.swap ? cur : (cur_in_hbm ? smem_d : smem_d + dns);
+    double* part = smem_d + ((p.swap || cur_in_hbm) ? dns : 2 * dns);   // 32 doubles: warp partials of a reduction
     Decision* dec = reinterpret_cast<Decision*>(part + 32);
     uint4* draws = reinterpret_cast<uint4*>(part + 34);   // kDrawBatch swap draws
     double2* rows = reinterpret_cast<double2*>(draws + kDrawBatch);  // [d] {x[r1][k], x[r2][k]} of the move
@@ -256,9 +262,28 @@ cudaError_t launch_anneal_raw0(const AnnealLaunch& L) {
     return cudaGetLastError();
 }
 
-size_t anneal_smem_bytes(unsigned long long n, unsigned long long d, int swap) {
+static size_t anneal_smem_bytes_buffers(unsigned long long n, unsigned long long d, int buffers) {
     const unsigned long long ns = (n + 1) & ~1ull;
-    return (size_t)(ns * d * (swap ? 1 : 2) + 34 + 2 * d) * sizeof(double) + (size_t)kDrawBatch * sizeof(uint4) + (size_t)kLogCap * sizeof(ushort4);
+    return (size_t)(ns * d * buffers + 34 + 2 * d) * sizeof(double) + (size_t)kDrawBatch * sizeof(uint4) + (size_t)kLogCap * sizeof(ushort4);
+}
+
+// Jitter chains keep the proposal beside the current design; when the two do not fit shared memory
+// together the current design moves to HBM scratch (one buffer per CTA) and one buffer is enough.
+static bool anneal_jitter_in_hbm(unsigned long long n, unsigned long long d, int swap) {
+    return !swap && anneal_smem_bytes_buffers(n, d, 2) > kSmemBudget;
+}
+
+size_t anneal_smem_bytes(unsigned long long n, unsigned long long d, int swap) {
+    return anneal_smem_bytes_buffers(n, d, (swap || anneal_jitter_in_hbm(n, d, swap)) ? 1 : 2);
+}
+
+constexpr unsigned long long kJitterHbmGrid = 1024;  // CTAs (= scratch buffers) of a jitter launch with the design in HBM
+
+size_t anneal_jitter_scratch_bytes(unsigned long long n, unsigned long long d, int swap, unsigned long long n_chains) {
+    if (!anneal_jitter_in_hbm(n, d, swap)) return 0;
+    const unsigned long long ns = (n + 1) & ~1ull;
+    const unsigned long long grid = n_chains < kJitterHbmGrid ? n_chains : kJitterHbmGrid;
+    return (size_t)(grid * ns * d) * sizeof(double);
 }
 
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap) {
@@ -280,6 +305,10 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
+    p.rowmin0 = nullptr; p.rowarg0 = nullptr;
+    const bool in_hbm = anneal_jitter_in_hbm(L.n, L.d, L.swap);
+    if (in_hbm && !L.cur_scratch) return cudaErrorInvalidValue;
+    p.cur_global = in_hbm ? L.cur_scratch : nullptr;
     size_t smem = anneal_smem_bytes(L.n, L.d, L.swap);
     int threads;
     if (L.swap && L.metric == 0) {
@@ -293,6 +322,7 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     if (threads > 512) threads = 512;
     if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
+    if (in_hbm && grid > kJitterHbmGrid) grid = kJitterHbmGrid;  // one scratch buffer per CTA; the chains are grid-strided
     cudaError_t e;
     if (L.metric == 0) {
         e = cudaFuncSetAttribute(anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -22,6 +22,7 @@ struct AnnealParams {
     unsigned int* improved;     // [n_chains]
     const double* raw0;         // S (or min squared distance) of the start design: every chain starts there,
                                 // so it is computed once by anneal_raw0_kernel instead of once per chain
+    double* cur_global;         // anneal.cu, jitter moves on designs that fit shared memory only once: [grid][d][ns] scratch
     const double* rowmin0;      // anneal_maximin.cu: nearest-neighbour squared distance of every row of the start design
     const unsigned short* rowarg0;  //               and the neighbour that attains it
 };

@@ -593,9 +593,10 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     if (!design || !out_design) return fail(MAXPRO_ERR_INVALID, "null pointer");
     if (int rc = ensure_device()) return rc;
     if (!mp::anneal_supported(n, d, swap))
-        return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the shared-memory annealer (n*d*8 bytes, doubled for jitter, must fit 227 KB)");
+        return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the shared-memory annealer (n*d*8 bytes must fit 227 KB)");
     const size_t nd = n * d;
-    DevBuf dx, db, dm, di, dr;
+    DevBuf dx, db, dm, di, dr, dcur;
+    if (const size_t sb = mp::anneal_jitter_scratch_bytes(n, d, swap ? 1 : 0, n_chains)) CUDA_TRY(dcur.alloc(sb));
     CUDA_TRY(dx.alloc(nd * sizeof(double)));
     CUDA_TRY(dr.alloc((2 * n + 2) * sizeof(double)));  // raw0, then the nearest-neighbour table: n doubles, n 16-bit indices
     CUDA_TRY(db.alloc(n_chains * nd * sizeof(double)));
@@ -608,6 +609,7 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     L.t0 = initial_temp; L.cooling = cooling_rate; L.metric = metric; L.minimize = minimize ? 1 : 0; L.swap = swap ? 1 : 0;
     L.best_design = db.as<double>(); L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.raw0 = dr.as<double>(); L.stream = st;
     L.rowmin0 = dr.as<double>() + 1; L.rowarg0 = reinterpret_cast<unsigned short*>(dr.as<double>() + 1 + n);
+    L.cur_scratch = dcur.as<double>();
     CUDA_TRY(mp::launch_anneal(L));
     std::vector<double> metrics(n_chains);
     std::vector<unsigned int> improved(n_chains);

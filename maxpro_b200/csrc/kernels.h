@@ -82,11 +82,14 @@ struct AnnealLaunch {
     double* best_metric;     // [n_chains]
     unsigned int* improved;  // [n_chains]
     double* raw0;            // device scratch, 1 double: S (or min squared distance) of the start design
+    double* cur_scratch;     // device scratch for jitter chains whose design fits shared memory only once:
+                             // anneal_jitter_scratch_bytes(n, d, n_chains) bytes, else null
     double* rowmin0;         // device scratch, n doubles and n 16-bit indices: nearest-neighbour table of the
     unsigned short* rowarg0; // start design (incremental maximin chains, anneal_maximin.cu)
     cudaStream_t stream;
 };
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap);
+size_t anneal_jitter_scratch_bytes(unsigned long long n, unsigned long long d, int swap, unsigned long long n_chains);  // 0: not needed
 cudaError_t launch_anneal(const AnnealLaunch& L);
 // swap moves on MaxPro as a two-stage pipeline (anneal_pipe.cu); launch_anneal dispatches to it
 bool anneal_pipe_supported(unsigned long long n, unsigned long long d, int metric, int swap);

@@ -433,6 +433,32 @@ def test_anneal_many_chains_large_design_properties():
     assert best3 == best and np.array_equal(got3, got)
 
 
+@pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)])
+def test_anneal_jitter_design_that_fits_shared_memory_once(metric, minimize):
+    """Jitter moves keep the proposal beside the current design.  Above n*d*8 B ~ 113 KB only one of the
+    two fits shared memory; the current design then lives in HBM scratch.  Same draws, same decisions:
+    the trajectory is the oracle's."""
+    n, d = 1200, 12  # 115 KB
+    x = oracle.generate_lhd(n, d, 8)
+    ref, ref_best = oracle.anneal_lhd(x, 6, 1.0, 0.9, metric, minimize, 21, False)
+    got, best, chain = engine.anneal_lhd(x, 6, 1.0, 0.9, metric, minimize, 21, False, n_chains=3)
+    refs = [oracle.anneal_lhd(x, 6, 1.0, 0.9, metric, minimize, 21 + c, False) for c in range(3)]
+    bests = [r[1] for r in refs]
+    rb = min(bests) if minimize else max(bests)
+    assert chain == bests.index(rb)
+    assert np.array_equal(got, refs[chain][0])
+    assert math.isclose(best, rb, rel_tol=REL) if metric == METRIC_MAXPRO else best == rb
+
+
+def test_anneal_jitter_c4_shape_runs():
+    """BASELINE config C4 in perturb mode: n=1000, d=20 (160 KB) -- more chains than scratch buffers."""
+    x = oracle.generate_lhd(1000, 20, 42)
+    got, best, chain = engine.anneal_lhd(x, 2, 1.0, 0.99, METRIC_MAXIMIN, False, 43, False, n_chains=1100)
+    assert got.shape == x.shape and best >= oracle.maximin_criterion(x)
+    assert best == oracle.maximin_criterion(got)
+    assert np.all((got >= 0.0) & (got <= 1.0))
+
+
 def test_anneal_large_design_runs():
     x = oracle.generate_lhd(1000, 20, 42)  # C4 shape: 160 KB of shared memory per chain
     got, best, _ = engine.anneal_lhd(x, 50, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, n_chains=4)
