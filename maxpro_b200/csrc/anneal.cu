@@ -30,7 +30,7 @@
 
 namespace mp {
 
-template <bool MAXPRO>
+template <bool MAXPRO, bool CUR_IN_HBM>
 __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     extern __shared__ __align__(16) double smem_d[];
     const int n = (int)p.n, d = (int)p.d, nd = n * d;
@@ -41,10 +41,11 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     // and the current design lives in a per-CTA scratch buffer in HBM (p.cur_global): it is read once
     // per iteration to build the proposal and written once per ACCEPTED move -- 2 x 160 KB per step
     // next to a full O(n^2 d) re-score, i.e. a few percent of the step.
-    const bool cur_in_hbm = !p.swap && p.cur_global != nullptr;
-    double* cur = cur_in_hbm ? p.cur_global + (size_t)blockIdx.x * dns : smem_d;   // [k][i]
-    double* cand = p.swap ? cur : (cur_in_hbm ? smem_d : smem_d + dns);
-    double* part = smem_d + ((p.swap || cur_in_hbm) ? dns : 2 * dns);   // 32 doubles: warp partials of a reduction
+    // CUR_IN_HBM is a template parameter so that every pointer keeps a single address space (a
+    // run-time choice between the two turns the scoring loads into generic ones: 15 % slower).
+    double* cur = CUR_IN_HBM ? p.cur_global + (size_t)blockIdx.x * dns : smem_d;   // [k][i]
+    double* cand = CUR_IN_HBM ? smem_d : (p.swap ? cur : smem_d + dns);
+    double* part = smem_d + ((CUR_IN_HBM || p.swap) ? dns : 2 * dns);   // 32 doubles: warp partials of a reduction
     Decision* dec = reinterpret_cast<Decision*>(part + 32);
     uint4* draws = reinterpret_cast<uint4*>(part + 34);   // kDrawBatch swap draws
     double2* rows = reinterpret_cast<double2*>(draws + kDrawBatch);  // [d] {x[r1][k], x[r2][k]} of the move
@@ -323,16 +324,14 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
     if (in_hbm && grid > kJitterHbmGrid) grid = kJitterHbmGrid;  // one scratch buffer per CTA; the chains are grid-strided
-    cudaError_t e;
-    if (L.metric == 0) {
-        e = cudaFuncSetAttribute(anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        anneal_kernel<true><<<(unsigned int)grid, threads, smem, L.stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(anneal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        anneal_kernel<false><<<(unsigned int)grid, threads, smem, L.stream>>>(p);
-    }
+    cudaError_t e = cudaSuccess;
+    auto go = [&](auto kernel) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) kernel<<<(unsigned int)grid, threads, smem, L.stream>>>(p);
+    };
+    if (L.metric == 0) { if (in_hbm) go(anneal_kernel<true, true>); else go(anneal_kernel<true, false>); }
+    else { if (in_hbm) go(anneal_kernel<false, true>); else go(anneal_kernel<false, false>); }
+    if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }
