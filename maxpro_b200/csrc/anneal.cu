@@ -30,22 +30,27 @@
 
 namespace mp {
 
-template <bool MAXPRO, bool CUR_IN_HBM>
+template <bool MAXPRO, int PLACE>
 __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     extern __shared__ __align__(16) double smem_d[];
     const int n = (int)p.n, d = (int)p.d, nd = n * d;
     const int ns = (n + 1) & ~1;                      // even row stride: 16-byte partner loads
     const int dns = d * ns;
-    // Jitter needs the proposal beside the current design.  When both fit, both live in shared memory;
-    // when only one does (n*d*8 B > ~113 KB, e.g. n=1000, d=20), the proposal takes the shared memory
-    // and the current design lives in a per-CTA scratch buffer in HBM (p.cur_global): it is read once
-    // per iteration to build the proposal and written once per ACCEPTED move -- 2 x 160 KB per step
-    // next to a full O(n^2 d) re-score, i.e. a few percent of the step.
-    // CUR_IN_HBM is a template parameter so that every pointer keeps a single address space (a
-    // run-time choice between the two turns the scoring loads into generic ones: 15 % slower).
-    double* cur = CUR_IN_HBM ? p.cur_global + (size_t)blockIdx.x * dns : smem_d;   // [k][i]
-    double* cand = CUR_IN_HBM ? smem_d : (p.swap ? cur : smem_d + dns);
-    double* part = smem_d + ((CUR_IN_HBM || p.swap) ? dns : 2 * dns);   // 32 doubles: warp partials of a reduction
+    // Where the chain's design lives (PLACE, chosen by the host from the shared-memory budget):
+    //   0  in shared memory: the current design, and for jitter moves the proposal beside it;
+    //   1  jitter moves on a design that fits shared memory only once (n*d*8 B > ~113 KB, e.g. n=1000,
+    //      d=20): the proposal takes the shared memory, the current design lives in a per-CTA scratch
+    //      buffer in HBM, read once per iteration to build the proposal and written once per
+    //      ACCEPTED move -- 2 x 160 KB per step beside a full O(n^2 d) re-score;
+    //   2  a design that does not fit shared memory at all (n*d*8 B > 227 KB): current design and
+    //      proposal both in the scratch buffer, every load served by L2/L1.  Slow, but any size the
+    //      reference accepts can be annealed.
+    // PLACE is a template parameter so that every pointer keeps a single address space (a run-time
+    // choice between shared and global turns the scoring loads into generic ones: 15 % slower).
+    double* const scratch = PLACE != 0 ? p.cur_global + (size_t)blockIdx.x * (PLACE == 2 ? 2 : 1) * dns : nullptr;
+    double* cur = PLACE != 0 ? scratch : smem_d;   // [k][i]
+    double* cand = PLACE == 2 ? (p.swap ? cur : scratch + dns) : (PLACE == 1 ? smem_d : (p.swap ? cur : smem_d + dns));
+    double* part = smem_d + (PLACE == 2 ? 0 : ((PLACE == 1 || p.swap) ? dns : 2 * dns));   // 32 doubles: warp partials of a reduction
     Decision* dec = reinterpret_cast<Decision*>(part + 32);
     uint4* draws = reinterpret_cast<uint4*>(part + 34);   // kDrawBatch swap draws
     double2* rows = reinterpret_cast<double2*>(draws + kDrawBatch);  // [d] {x[r1][k], x[r2][k]} of the move
@@ -220,12 +225,12 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
 
 // The raw criterion of the start design (anneal.rs:90), once per call: one CTA, same layout and
 // summation as the in-chain re-sum.
-template <bool MAXPRO>
-__global__ void __launch_bounds__(512) anneal_raw0_kernel(const double* design, int n, int d, double* raw0) {
+template <bool MAXPRO, bool IN_HBM>
+__global__ void __launch_bounds__(512) anneal_raw0_kernel(const double* design, int n, int d, double* raw0, double* scratch) {
     extern __shared__ __align__(16) double smem_d[];
     const int ns = (n + 1) & ~1;
-    double* cur = smem_d;
-    double* part = smem_d + d * ns;
+    double* cur = IN_HBM ? scratch : smem_d;
+    double* part = IN_HBM ? smem_d : smem_d + d * ns;
     if (ns != n)
         for (int k = threadIdx.x; k < d; k += blockDim.x) cur[k * ns + n] = 0.0;
     int ok = 1;
@@ -244,21 +249,23 @@ __global__ void __launch_bounds__(512) anneal_raw0_kernel(const double* design, 
     }
 }
 
+static bool anneal_all_in_hbm(unsigned long long n, unsigned long long d);
+
 cudaError_t launch_anneal_raw0(const AnnealLaunch& L) {
     const unsigned long long ns = (L.n + 1) & ~1ull;
-    const size_t smem = (size_t)(ns * L.d + 32) * sizeof(double);
+    const bool hbm = anneal_all_in_hbm(L.n, L.d);
+    if (hbm && !L.cur_scratch) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)((hbm ? 0 : ns * L.d) + 32) * sizeof(double);
     int threads = (int)((L.n + 31) / 32 * 32);
     if (threads > 512) threads = 512;
-    cudaError_t e;
-    if (L.metric == 0) {
-        e = cudaFuncSetAttribute(anneal_raw0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        anneal_raw0_kernel<true><<<1, threads, smem, L.stream>>>(L.design, (int)L.n, (int)L.d, L.raw0);
-    } else {
-        e = cudaFuncSetAttribute(anneal_raw0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        anneal_raw0_kernel<false><<<1, threads, smem, L.stream>>>(L.design, (int)L.n, (int)L.d, L.raw0);
-    }
+    cudaError_t e = cudaSuccess;
+    auto go = [&](auto kernel) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) kernel<<<1, threads, smem, L.stream>>>(L.design, (int)L.n, (int)L.d, L.raw0, L.cur_scratch);
+    };
+    if (L.metric == 0) { if (hbm) go(anneal_raw0_kernel<true, true>); else go(anneal_raw0_kernel<true, false>); }
+    else { if (hbm) go(anneal_raw0_kernel<false, true>); else go(anneal_raw0_kernel<false, false>); }
+    if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }
@@ -268,27 +275,36 @@ static size_t anneal_smem_bytes_buffers(unsigned long long n, unsigned long long
     return (size_t)(ns * d * buffers + 34 + 2 * d) * sizeof(double) + (size_t)kDrawBatch * sizeof(uint4) + (size_t)kLogCap * sizeof(ushort4);
 }
 
-// Jitter chains keep the proposal beside the current design; when the two do not fit shared memory
-// together the current design moves to HBM scratch (one buffer per CTA) and one buffer is enough.
-static bool anneal_jitter_in_hbm(unsigned long long n, unsigned long long d, int swap) {
-    return !swap && anneal_smem_bytes_buffers(n, d, 2) > kSmemBudget;
+// Placement of a chain's design (see anneal_kernel): 0 shared memory, 1 jitter with the current design in
+// HBM scratch, 2 everything in HBM scratch.
+static bool anneal_all_in_hbm(unsigned long long n, unsigned long long d) {
+    return anneal_smem_bytes_buffers(n, d, 1) > kSmemBudget;
+}
+static int anneal_place(unsigned long long n, unsigned long long d, int swap) {
+    if (anneal_all_in_hbm(n, d)) return 2;
+    if (!swap && anneal_smem_bytes_buffers(n, d, 2) > kSmemBudget) return 1;
+    return 0;
 }
 
 size_t anneal_smem_bytes(unsigned long long n, unsigned long long d, int swap) {
-    return anneal_smem_bytes_buffers(n, d, (swap || anneal_jitter_in_hbm(n, d, swap)) ? 1 : 2);
+    const int place = anneal_place(n, d, swap);
+    return anneal_smem_bytes_buffers(n, d, place == 2 ? 0 : ((swap || place == 1) ? 1 : 2));
 }
 
-constexpr unsigned long long kJitterHbmGrid = 1024;  // CTAs (= scratch buffers) of a jitter launch with the design in HBM
+constexpr unsigned long long kHbmGrid = 1024;  // CTAs (= scratch buffers) of a launch that keeps designs in HBM
 
 size_t anneal_jitter_scratch_bytes(unsigned long long n, unsigned long long d, int swap, unsigned long long n_chains) {
-    if (!anneal_jitter_in_hbm(n, d, swap)) return 0;
+    const int place = anneal_place(n, d, swap);
+    if (place == 0) return 0;
     const unsigned long long ns = (n + 1) & ~1ull;
-    const unsigned long long grid = n_chains < kJitterHbmGrid ? n_chains : kJitterHbmGrid;
-    return (size_t)(grid * ns * d) * sizeof(double);
+    const unsigned long long grid = n_chains < kHbmGrid ? n_chains : kHbmGrid;
+    return (size_t)(grid * ns * d * (place == 2 ? 2 : 1)) * sizeof(double);
 }
 
+// Every design the 16-bit row indices can address is supported: what does not fit shared memory is annealed out of HBM.
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap) {
-    return n >= 1 && d >= 1 && n < (1ull << 30) / (d ? d : 1) && n <= 65535 && d <= 65535 && anneal_smem_bytes(n, d, swap) <= kSmemBudget;
+    return n >= 1 && d >= 1 && n < (1ull << 30) / (d ? d : 1) && n <= 65535 && d <= 65535 &&
+           anneal_smem_bytes(n, d, swap) <= kSmemBudget;  // the staged rows of a move (2 d doubles) stay in shared memory
 }
 
 static int round_up_32(unsigned long long v) { return (int)((v + 31) / 32 * 32); }
@@ -307,9 +323,9 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     p.inv_d = 1.0 / (double)L.d;
     p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
     p.rowmin0 = nullptr; p.rowarg0 = nullptr;
-    const bool in_hbm = anneal_jitter_in_hbm(L.n, L.d, L.swap);
-    if (in_hbm && !L.cur_scratch) return cudaErrorInvalidValue;
-    p.cur_global = in_hbm ? L.cur_scratch : nullptr;
+    const int place = anneal_place(L.n, L.d, L.swap);
+    if (place != 0 && !L.cur_scratch) return cudaErrorInvalidValue;
+    p.cur_global = place != 0 ? L.cur_scratch : nullptr;
     size_t smem = anneal_smem_bytes(L.n, L.d, L.swap);
     int threads;
     if (L.swap && L.metric == 0) {
@@ -323,14 +339,14 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     if (threads > 512) threads = 512;
     if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
-    if (in_hbm && grid > kJitterHbmGrid) grid = kJitterHbmGrid;  // one scratch buffer per CTA; the chains are grid-strided
+    if (place != 0 && grid > kHbmGrid) grid = kHbmGrid;  // one scratch buffer per CTA; the chains are grid-strided
     cudaError_t e = cudaSuccess;
     auto go = [&](auto kernel) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) kernel<<<(unsigned int)grid, threads, smem, L.stream>>>(p);
     };
-    if (L.metric == 0) { if (in_hbm) go(anneal_kernel<true, true>); else go(anneal_kernel<true, false>); }
-    else { if (in_hbm) go(anneal_kernel<false, true>); else go(anneal_kernel<false, false>); }
+    if (L.metric == 0) { if (place == 2) go(anneal_kernel<true, 2>); else if (place == 1) go(anneal_kernel<true, 1>); else go(anneal_kernel<true, 0>); }
+    else { if (place == 2) go(anneal_kernel<false, 2>); else if (place == 1) go(anneal_kernel<false, 1>); else go(anneal_kernel<false, 0>); }
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();

@@ -593,7 +593,7 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     if (!design || !out_design) return fail(MAXPRO_ERR_INVALID, "null pointer");
     if (int rc = ensure_device()) return rc;
     if (!mp::anneal_supported(n, d, swap))
-        return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the shared-memory annealer (n*d*8 bytes must fit 227 KB)");
+        return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the annealer (at most 65535 points and ~14000 dimensions)");
     const size_t nd = n * d;
     DevBuf dx, db, dm, di, dr, dcur;
     if (const size_t sb = mp::anneal_jitter_scratch_bytes(n, d, swap ? 1 : 0, n_chains)) CUDA_TRY(dcur.alloc(sb));

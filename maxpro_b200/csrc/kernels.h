@@ -82,8 +82,8 @@ struct AnnealLaunch {
     double* best_metric;     // [n_chains]
     unsigned int* improved;  // [n_chains]
     double* raw0;            // device scratch, 1 double: S (or min squared distance) of the start design
-    double* cur_scratch;     // device scratch for jitter chains whose design fits shared memory only once:
-                             // anneal_jitter_scratch_bytes(n, d, n_chains) bytes, else null
+    double* cur_scratch;     // device scratch for chains whose design (or its proposal) does not fit shared
+                             // memory: anneal_jitter_scratch_bytes(n, d, swap, n_chains) bytes, null when that is 0
     double* rowmin0;         // device scratch, n doubles and n 16-bit indices: nearest-neighbour table of the
     unsigned short* rowarg0; // start design (incremental maximin chains, anneal_maximin.cu)
     cudaStream_t stream;

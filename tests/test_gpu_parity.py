@@ -450,6 +450,24 @@ def test_anneal_jitter_design_that_fits_shared_memory_once(metric, minimize):
     assert math.isclose(best, rb, rel_tol=REL) if metric == METRIC_MAXPRO else best == rb
 
 
+@pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)])
+@pytest.mark.parametrize("swap", [True, False])
+def test_anneal_design_larger_than_shared_memory(metric, minimize, swap):
+    """n*d*8 B = 240 KB: the chain's design and its proposal both live in HBM scratch (the reference
+    accepts any size, src/anneal.rs:56-143).  Same trajectory as the oracle."""
+    n, d = 3000, 10
+    x = oracle.generate_lhd(n, d, 5)
+    iters = 40 if swap else 3
+    ref, ref_best = oracle.anneal_lhd(x, iters, 1.0, 0.9, metric, minimize, 77, swap)
+    got, best, chain = engine.anneal_lhd(x, iters, 1.0, 0.9, metric, minimize, 77, swap, n_chains=2)
+    ref1, ref_best1 = oracle.anneal_lhd(x, iters, 1.0, 0.9, metric, minimize, 78, swap)
+    better1 = ref_best1 < ref_best if minimize else ref_best1 > ref_best
+    exp, exp_best = (ref1, ref_best1) if better1 else (ref, ref_best)
+    assert chain == (1 if better1 else 0)
+    assert np.array_equal(got, exp)
+    assert math.isclose(best, exp_best, rel_tol=REL) if metric == METRIC_MAXPRO else best == exp_best
+
+
 def test_anneal_jitter_c4_shape_runs():
     """BASELINE config C4 in perturb mode: n=1000, d=20 (160 KB) -- more chains than scratch buffers."""
     x = oracle.generate_lhd(1000, 20, 42)
