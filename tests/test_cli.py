@@ -67,3 +67,19 @@ def test_cli_pipeline_end_to_end():
     assert abs(oracle.maxpro_criterion(design) - vals["Annealed metric"]) <= 1e-9 * vals["Annealed metric"]
     r2 = run("-i", "1000", "-s", "12", "-n", "3", "-m", "maxi-min", "--seed", "7", "--anneal-iterations", "200")
     assert r2.returncode == 0 and "Annealed metric:" in r2.stdout
+
+
+@pytest.mark.gpu
+def test_cli_pipeline_on_a_design_larger_than_shared_memory():
+    """--samples 5000 --ndims 8 is the design size of BASELINE config C5 (320 KB): the search takes the chunked
+    path, both annealing stages keep the design in HBM.  The reference CLI runs at any size; so does this one."""
+    r = run("--iterations", "8", "--samples", "5000", "--ndims", "8", "--metric", "maxi-min", "--seed", "3",
+            "--anneal-iterations", "10")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    design = np.array(eval(lines[1]))
+    assert design.shape == (5000, 8)
+    vals = {ln.split(":")[0]: float(ln.split(":")[1]) for ln in lines[2:5]}
+    assert vals["Annealed metric"] >= vals["Swapped metric"] >= vals["Original metric"]
+    import oracle
+    assert oracle.maximin_criterion(design) == vals["Annealed metric"]
