@@ -13,13 +13,15 @@
 // every lane runs Philox for its share of the blocks and stages v_i and the Fisher-Yates
 // target j_i; then one lane per column walks the n dependent swaps.
 // Scoring: pairs enumerated cyclically, {i, (i+s) mod n} for s = 1..(n-1)/2 (+ the n/2 diameters
-// of the lower half for even n), as work items of (row i, 8 consecutive shifts).  The items
-// are dealt to the lanes in row-major order (consecutive lanes <-> consecutive rows: conflict-
-// free), so every lane gets the same number of items whatever n is.  The 8 running products
-// stay in registers across the dimensions; MaxPro terms go through the reciprocal chains of
-// common.cuh (candidates are in the unit cube by construction).  Each column is followed by a
-// copy of its first 8*ceil(smax/8) rows, so row (i+s) mod n is simply row i+s: the 8 partner
-// loads of an item are one address plus immediates, with no wrap arithmetic and no index array.
+// of the lower half for even n), as work items of (two neighbouring rows, 8 consecutive shifts):
+// 16 pairs from six 16-byte loads per dimension -- the two rows in one, their ten partner rows in
+// five (0.4 loads per pair; one row per item needed 1.1).  The items are dealt to the lanes in
+// row-major order (consecutive lanes <-> consecutive row pairs: contiguous, conflict-free), so
+// every lane gets the same number of items whatever n is.  The 16 running products stay in
+// registers across the dimensions; MaxPro terms go through the reciprocal chains of common.cuh
+// (candidates are in the unit cube by construction).  Each column is followed by a copy of its
+// first 8*ceil(smax/8)+2 rows, so row (i+s) mod n is simply row i+s: the partner loads of an item
+// are one address plus immediates, with no wrap arithmetic and no index array.
 #include "common.cuh"
 #include "philox.cuh"
 #include "reduce.cuh"
@@ -33,7 +35,7 @@ constexpr int kWarpCtaThreads = 128;  // 4 candidates per CTA, up to 4 CTAs per 
 constexpr int kWarpSB = 8;            // shifts per work item
 
 struct WarpParams {
-    int n, d, ns;  // ns = odd row stride of the [k][i] layout (the column walkers hit different banks): n + copied rows
+    int n, d, ns;  // ns = row stride of the [k][i] layout: n + copied rows, even (16-byte loads), 2 or 10 mod 16 (the column walkers hit different banks)
     unsigned int cand_bytes;  // shared memory of one candidate slot
     unsigned long long seed, lo, hi;
     double c1, c0, n_pairs, inv_d;
@@ -54,7 +56,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
     const int half = (n - 1) / 2;
     const bool even = (n & 1) == 0;
     const int nblk = (half + (even ? 1 : 0) + kWarpSB - 1) / kWarpSB;  // shift blocks per row
-    const int items = n * nblk;
+    const int npairs = (n + 1) / 2;            // row pairs (the last one has a single row when n is odd)
+    const int items = npairs * nblk;
+    const int wrap = kWarpSB * nblk + 2;       // copied rows behind each column
+    const int ns2 = ns / 2;                    // row stride in 16-byte units
 
     double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by lane 0 of each warp
     unsigned long long best_idx = kNoIndex;
@@ -64,88 +69,125 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         __syncwarp();  // previous candidate fully consumed
-        // ---- generation, phase 1
-        for (int q = lane; q < d * nb; q += 32) {
-            const int k = q / nb, b = q - k * nb;
-            Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
-            const int i = 2 * b;
-            xs[k * ns + i] = stratum_value((uint32_t)i, w.x, p.c1, p.c0);
-            jst[k * n + i] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
-            if (i + 1 < n) {
-                xs[k * ns + i + 1] = stratum_value((uint32_t)(i + 1), w.z, p.c1, p.c0);
-                jst[k * n + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
+        // ---- generation, phase 1: block q <-> (column k, element pair b), walked without a division
+        {
+            int k = 0, b = lane;
+            while (b >= nb) { b -= nb; ++k; }
+            while (k < d) {
+                Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+                const int i = 2 * b;
+                double* col = xs + k * ns + i;
+                unsigned short* jc = jst + k * n + i;
+                col[0] = stratum_value((uint32_t)i, w.x, p.c1, p.c0);
+                jc[0] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
+                if (i + 1 < n) {
+                    col[1] = stratum_value((uint32_t)(i + 1), w.z, p.c1, p.c0);
+                    jc[1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
+                }
+                b += 32;
+                while (b >= nb) { b -= nb; ++k; }
             }
         }
         __syncwarp();
         // ---- generation, phase 2: one lane per column
         for (int k = lane; k < d; k += 32) fy_walk_column(xs + k * ns, jst + k * n, n);
         __syncwarp();
-        // rows n .. n + 8*nblk - 1 repeat rows 0 .. (wrapping again if the design is tiny)
-        for (int e = lane; e < d * kWarpSB * nblk; e += 32) {
-            const int k = e / (kWarpSB * nblk), r = e - k * (kWarpSB * nblk);
-            xs[k * ns + n + r] = xs[k * ns + r % n];
+        // rows n .. n + wrap - 1 repeat rows 0 .. (wrapping again if the design is tiny)
+        for (int k = 0; k < d; ++k) {
+            double* col = xs + k * ns;
+            for (int r = lane; r < wrap; r += 32) {
+                int src = r;
+                while (src >= n) src -= n;
+                col[n + r] = col[src];
+            }
         }
         __syncwarp();
 
-        // ---- scoring: item q <-> (row q mod n, shift block q / n)
+        // ---- scoring: item q <-> (row pair q mod npairs, shift block q / npairs)
         double acc = 0.0, mn = CUDART_INF;
         RecipChain ch[kWarpSB];
 #pragma unroll
         for (int c = 0; c < kWarpSB; ++c) ch[c].reset();
         int pushed = 0;
-        int i = lane % n, b = lane / n;  // n may be below 32
+        int m = lane, b = 0;
+        while (m >= npairs) { m -= npairs; ++b; }  // n may be below 64
         for (int q = lane; q < items; q += 32) {
+            const int i0 = 2 * m, i1 = i0 + 1;
             const int s0 = 1 + b * kWarpSB;
-            const int my_smax = half + ((even && i < n / 2) ? 1 : 0);
-            const double* pi = xs + i;        // row i
-            const double* pj = pi + s0;       // rows i+s0 .. i+s0+7 (copies past row n-1)
-            double pr[kWarpSB];
+            // rows i0, i0+1 (one 16-byte load) against rows i0 + s0 - 1 .. i0 + s0 + 8 (five 16-byte loads):
+            // row i0 meets partners [1, 9), row i0+1 partners [2, 10) -- the same eight shifts s0 .. s0+7
+            const double2* pa = reinterpret_cast<const double2*>(xs + i0);
+            const double2* pp = reinterpret_cast<const double2*>(xs + i0 + s0 - 1);
+            double pr[2][kWarpSB];
             {
-                const double xi = pi[0];
+                const double2 a = pa[0];
+                double pt[kWarpSB + 2];
+#pragma unroll
+                for (int c = 0; c < kWarpSB / 2 + 1; ++c) { const double2 v = pp[c]; pt[2 * c] = v.x; pt[2 * c + 1] = v.y; }
 #pragma unroll
                 for (int c = 0; c < kWarpSB; ++c) {
-                    if (MAXPRO) pr[c] = xi - pj[c];
-                    else { const double df = __dsub_rn(xi, pj[c]); pr[c] = __dmul_rn(df, df); }
+                    if (MAXPRO) { pr[0][c] = a.x - pt[c + 1]; pr[1][c] = a.y - pt[c + 2]; }
+                    else {
+                        const double d0 = __dsub_rn(a.x, pt[c + 1]), d1 = __dsub_rn(a.y, pt[c + 2]);
+                        pr[0][c] = __dmul_rn(d0, d0); pr[1][c] = __dmul_rn(d1, d1);
+                    }
                 }
             }
             for (int k = 1; k < d; ++k) {
-                pi += ns; pj += ns;
-                const double xi = pi[0];
+                pa += ns2; pp += ns2;
+                const double2 a = pa[0];
+                double pt[kWarpSB + 2];
+#pragma unroll
+                for (int c = 0; c < kWarpSB / 2 + 1; ++c) { const double2 v = pp[c]; pt[2 * c] = v.x; pt[2 * c + 1] = v.y; }
 #pragma unroll
                 for (int c = 0; c < kWarpSB; ++c) {
-                    if (MAXPRO) pr[c] *= xi - pj[c];
-                    else { const double df = __dsub_rn(xi, pj[c]); pr[c] = __dadd_rn(pr[c], __dmul_rn(df, df)); }
+                    if (MAXPRO) { pr[0][c] *= a.x - pt[c + 1]; pr[1][c] *= a.y - pt[c + 2]; }
+                    else {
+                        const double d0 = __dsub_rn(a.x, pt[c + 1]), d1 = __dsub_rn(a.y, pt[c + 2]);
+                        pr[0][c] = __dadd_rn(pr[0][c], __dmul_rn(d0, d0));
+                        pr[1][c] = __dadd_rn(pr[1][c], __dmul_rn(d1, d1));
+                    }
                 }
             }
-            const bool whole = s0 + kWarpSB - 1 <= my_smax;  // false only in a row's last shift block
+            // shift s0 + c of row i is a pair iff s0 + c <= half, or it is the diameter of a lower-half row
+            const int smax0 = half + ((even && i0 < n / 2) ? 1 : 0);
+            const int smax1 = i1 < n ? half + ((even && i1 < n / 2) ? 1 : 0) : 0;  // odd n: the last item has one row
+            const bool whole = s0 + kWarpSB - 1 <= half && i1 < n;
             if (MAXPRO) {
-                if (pushed == kMaxChainTerms) {
+                if (pushed + 2 > kMaxChainTerms) {
 #pragma unroll
                     for (int c = 0; c < kWarpSB; ++c) acc = ch[c].flush_into(acc);
                     pushed = 0;
                 }
                 if (whole) {
 #pragma unroll
-                    for (int c = 0; c < kWarpSB; ++c) ch[c].push(fma(pr[c], pr[c], kEps));
+                    for (int c = 0; c < kWarpSB; ++c) {
+                        ch[c].push(fma(pr[0][c], pr[0][c], kEps));
+                        ch[c].push(fma(pr[1][c], pr[1][c], kEps));
+                    }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < kWarpSB; ++c)
-                        if (s0 + c <= my_smax) ch[c].push(fma(pr[c], pr[c], kEps));
+                    for (int c = 0; c < kWarpSB; ++c) {
+                        if (s0 + c <= smax0) ch[c].push(fma(pr[0][c], pr[0][c], kEps));
+                        if (s0 + c <= smax1) ch[c].push(fma(pr[1][c], pr[1][c], kEps));
+                    }
                 }
-                ++pushed;
+                pushed += 2;
             } else {
                 if (whole) {
 #pragma unroll
-                    for (int c = 0; c < kWarpSB; ++c) mn = fmin(mn, pr[c]);
+                    for (int c = 0; c < kWarpSB; ++c) mn = fmin(mn, fmin(pr[0][c], pr[1][c]));
                 } else {
 #pragma unroll
-                    for (int c = 0; c < kWarpSB; ++c)
-                        if (s0 + c <= my_smax) mn = fmin(mn, pr[c]);
+                    for (int c = 0; c < kWarpSB; ++c) {
+                        if (s0 + c <= smax0) mn = fmin(mn, pr[0][c]);
+                        if (s0 + c <= smax1) mn = fmin(mn, pr[1][c]);
+                    }
                 }
             }
-            // next item of this lane: 32 rows further, wrapping into the next shift block
-            i += 32;
-            while (i >= n) { i -= n; ++b; }
+            // next item of this lane: 32 row pairs further, wrapping into the next shift block
+            m += 32;
+            while (m >= npairs) { m -= npairs; ++b; }
         }
         if (MAXPRO) {
 #pragma unroll
@@ -163,7 +205,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
 static unsigned long long warp_row_stride(unsigned long long n) {
     const unsigned long long smax = (n - 1) / 2 + ((n & 1) == 0 ? 1 : 0);
     const unsigned long long nblk = (smax + kWarpSB - 1) / kWarpSB;
-    return (n + kWarpSB * nblk) | 1ull;  // n rows + the copied ones, odd
+    unsigned long long ns = n + kWarpSB * nblk + 2;  // n rows + the copied ones
+    ns += ns & 1;                                     // even: every column starts on a 16-byte boundary
+    while (ns % 16 != 2 && ns % 16 != 10) ns += 2;    // the lanes that walk one column each fall into different bank groups
+    return ns;
 }
 static unsigned int warp_cand_bytes(unsigned long long n, unsigned long long d) {
     return (unsigned int)(((d * warp_row_stride(n) * 8 + d * n * 2 + 15) / 16) * 16);
