@@ -311,12 +311,13 @@ static cudaError_t launch_d(const SearchLaunch& L, const SearchParams& p) {
     }
 }
 
-// Shapes this kernel takes: at least 48 candidates must fit one SM's shared memory (n*d*8 B <= ~4.8 KB).
-// Measured against the warp-per-candidate kernel (tools/shape_sweep.py): with 48 instead of 64,
-// (100,5) 8.3 -> 9.3, (128,4) 9.4 -> 11.1, (300,2) 11.1 -> 12.7 algorithmic TFLOP/s; with 32, (200,4),
-// (250,3) and (100,8) lose 25-30 %.
+// Shapes this kernel takes: at least 64 candidates must fit one SM's shared memory (n*d*8 B <= ~3.5 KB).
+// Measured against the warp-per-candidate kernel (tools/shape_sweep.py, after that kernel moved to
+// row-pair items): at 3.0-3.2 KB this kernel leads ((100,4) 13.3 vs 10.1, (80,5) 11.5 vs 9.9, (50,8)
+// 8.7 vs 6.2 algorithmic TFLOP/s), from 3.8 KB up the warp kernel does ((100,5) 9.3 vs 10.7, (300,2)
+// 12.7 vs 14.0, (75,8) 7.9 vs 9.6).
 bool search_small_supported(unsigned long long n, unsigned long long d) {
-    unsigned long long min_cands = 48;
+    unsigned long long min_cands = 64;
     if (const char* e = getenv("MAXPRO_SMALL_MIN_CANDS")) { int v = atoi(e); if (v >= 16 && v <= 512 && v % 16 == 0) min_cands = (unsigned long long)v; }
     return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * min_cands + 32 * sizeof(BestRec) <= kSmemBudget;
 }

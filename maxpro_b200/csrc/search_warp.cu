@@ -3,7 +3,7 @@
 // Replaces the same reference code as the other search kernels: generate_lhd
 // (src/lhd.rs:97-132) -> criterion (src/maxpro_utils.rs:28-83 / src/maximin_utils.rs:54-67)
 // -> fold (src/lib.rs:76-98).  It fills the gap between the thread-group kernels
-// (search_small.cu: designs up to 4.8 KB) and the CTA-per-candidate kernel (search_cta.cu):
+// (search_small.cu: designs up to 3.5 KB) and the CTA-per-candidate kernel (search_cta.cu):
 // at n ~ 100-200 a CTA spends most of a candidate in the sequential Fisher-Yates walk (one
 // lane per column, n dependent steps) and in half-empty diagonal tiles, and its 128 registers
 // x 128 threads allow only 4 candidates in flight per SM.  Here 16 warps per SM each carry
