@@ -202,7 +202,9 @@ __device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0
 
 // G lanes per candidate: lane g generates columns g, g+G, ... and scores its share of
 // the pairs.  G = 2 doubles the resident warps for the same shared memory (12 warps per
-// SM at n=50, d=3).
+// SM at n=50, d=3); G = 4 serves the designs of 2-3.5 KB with four or more columns, which
+// otherwise run on four to six warps per SM -- one per sub-partition, nothing to overlap its
+// generation phase with.
 //
 // LOCK: the warps of one SM sub-partition (warp id mod 4) take turns on the FP64 pipe.
 // Every warp alternates an integer-only, latency-bound phase (Philox + Fisher-Yates) and an
@@ -217,13 +219,20 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
     const int C = blockDim.x / G;  // candidates resident in this CTA
     const int n = p.n;
     // Lane layout inside a warp: lanes [0, 32/G) are lane-role 0 of 32/G consecutive
-    // candidates, lanes [32/G, 2*32/G) lane-role 1 of the same candidates.  Each half-warp
-    // (the unit a 64-bit shared-memory access is split into) then touches 16 different
-    // candidates = 16 different bank pairs: no conflicts for any per-lane element index.
+    // candidates, lanes [32/G, 2*32/G) lane-role 1 of the same candidates, and so on.  With
+    // G <= 2 each half-warp (the unit a 64-bit shared-memory access is split into) touches 16
+    // different candidates = 16 different bank pairs: no conflicts for any per-lane element
+    // index.  With G = 4 a half-warp holds two roles of 8 candidates; the host then picks C = 8
+    // (mod 16), which puts rows of different parity into different halves of the banks: the
+    // partner rows of phase A (roles differ by one row) stay conflict-free, the same row read by
+    // both roles is a broadcast, and only the data-dependent Fisher-Yates accesses collide (half
+    // of the time, two-way).
     constexpr int kPerWarp = 32 / G;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = wid * kPerWarp + (lane % kPerWarp), g = lane / kPerWarp;
-    const unsigned int group_mask = (G == 1) ? (1u << lane) : ((1u << (lane % kPerWarp)) | (1u << (lane % kPerWarp + kPerWarp)));
+    unsigned int group_mask = 0u;  // the G lanes of this candidate
+#pragma unroll
+    for (int j = 0; j < G; ++j) group_mask |= 1u << (lane % kPerWarp + j * kPerWarp);
     double* xs = reinterpret_cast<double*>(smem_raw) + c;
     BestRec* warp_best = reinterpret_cast<BestRec*>(smem_raw + (size_t)n * D * C * sizeof(double));
 
@@ -259,11 +268,14 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
         if (active) s = score_group_design<D, R, G, MAXPRO>(xs, C, n, g);
         if (LOCK) token_pass(tok_out);
         if (G > 1) {
-            // fixed order (even lane + odd lane) so both lanes hold the same bits
-            const double other = __shfl_xor_sync(group_mask, s, kPerWarp);
-            if (MAXPRO) s = (g == 0) ? s + other : other + s;
-            else s = fmin(s, other);
-            __syncwarp(group_mask);  // partner is done reading before the design is overwritten
+            // fixed order (lower role + higher role at every level) so all lanes of the group hold the same bits
+#pragma unroll
+            for (int step = 1; step < G; step <<= 1) {
+                const double other = __shfl_xor_sync(group_mask, s, step * kPerWarp);
+                if (MAXPRO) s = ((g & step) == 0) ? s + other : other + s;
+                else s = fmin(s, other);
+            }
+            __syncwarp(group_mask);  // partners are done reading before the design is overwritten
         }
         if (!MAXPRO) s = sqrt(s);  // reference compares distances, not squares (ties)
         // idx grows along the loop, so ">= / <=" keeps the later index on ties
@@ -302,11 +314,14 @@ template <int D>
 static cudaError_t launch_d(const SearchLaunch& L, const SearchParams& p) {
     if constexpr (D <= 4) {
         const bool r5 = (p.n % 5 == 0);
+        if constexpr (D == 4) { if (L.group == 4) return r5 ? launch_drg<D, 5, 4>(L, p) : launch_drg<D, 4, 4>(L, p); }
         if (L.group == 2) return r5 ? launch_drg<D, 5, 2>(L, p) : launch_drg<D, 4, 2>(L, p);
         return r5 ? launch_drg<D, 5, 1>(L, p) : launch_drg<D, 4, 1>(L, p);
     } else if constexpr (D <= 6) {
+        if (L.group == 4) return launch_drg<D, 4, 4>(L, p);
         return L.group == 2 ? launch_drg<D, 4, 2>(L, p) : launch_drg<D, 4, 1>(L, p);
     } else {
+        if (L.group == 4) return launch_drg<D, 3, 4>(L, p);
         return L.group == 2 ? launch_drg<D, 3, 2>(L, p) : launch_drg<D, 3, 1>(L, p);
     }
 }
@@ -327,13 +342,29 @@ bool search_small_supported(unsigned long long n, unsigned long long d) {
 // every lane of a half-warp hits its own bank pair), at most 512 threads.
 void search_small_pick_config(unsigned long long n, unsigned long long d, int* group, int* threads) {
     int G = d >= 2 ? 2 : 1;
-    if (const char* e = getenv("MAXPRO_SMALL_GROUP")) { int v = atoi(e); if (v == 1 || v == 2) G = v; }
     size_t per = (size_t)n * d * sizeof(double);
-    size_t c = (kSmemBudget - 32 * sizeof(BestRec)) / per;
-    c = (c / 16) * 16;
-    if (c * G > 512) c = 512 / G;
-    if (const char* e = getenv("MAXPRO_SMALL_CANDS")) { size_t v = (size_t)atoi(e); if (v >= 16 && v <= c && v % 16 == 0) c = v; }
-    if (G == 1) c = (c / 32) * 32;
+    size_t cap = (kSmemBudget - 32 * sizeof(BestRec)) / per;
+    // Four lanes per candidate when shared memory leaves two lanes fewer than 10 warps (n*d above ~180
+    // elements) and there are four or more columns -- except d = 5 (2+1+1+1 columns per lane: the
+    // generation phase is as long as with two lanes, and the scoring tiles get smaller).  Measured,
+    // G = 2 -> 4 in algorithmic TFLOP/s: (50,4) 11.9 -> 13.9, (50,6) 10.5 -> 11.9, (50,8) 8.7 -> 10.1,
+    // (40,8) 6.8 -> 10.9, (100,4) 12.6 -> 13.8, (25,8) 7.6 -> 9.0, (60,7) 9.1 -> 10.9; against it
+    // (50,5) 11.6 -> 10.3, and the designs that already fill 10+ warps: (30,6) 10.2 -> 9.5, (40,4)
+    // 13.1 -> 12.5, (20,4) 10.0 -> 7.6.
+    if (d >= 4 && d != 5 && (cap / 16) * 16 * 2 < 320) G = 4;
+    if (const char* e = getenv("MAXPRO_SMALL_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || (v == 4 && d >= 4)) G = v; }
+    size_t c;
+    if (G == 4) {
+        c = cap >= 8 ? ((cap - 8) / 16) * 16 + 8 : 0;  // 8 (mod 16): see the lane layout note in the kernel
+        if (c > 120) c = 120;                           // 480 threads
+        if (c == 0) { G = 2; }
+    }
+    if (G != 4) {
+        c = (cap / 16) * 16;
+        if (c * G > 512) c = 512 / G;
+        if (const char* e = getenv("MAXPRO_SMALL_CANDS")) { size_t v = (size_t)atoi(e); if (v >= 16 && v <= c && v % 16 == 0) c = v; }
+        if (G == 1) c = (c / 32) * 32;
+    }
     *group = G;
     *threads = (int)(c * G);
 }
