@@ -107,7 +107,7 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
             } else {
 #pragma unroll
                 for (int c = 0; c < SB; ++c)
-                    if (s0 + c <= my_smax) mn = fmin(mn, q[c]);
+                    if (s0 + c <= my_smax) mn = min_sqdist(mn, q[c]);
             }
         }
     }

@@ -55,6 +55,16 @@ __device__ __forceinline__ double warp_reduce_min(double v) {
     return v;
 }
 
+// Minimum of two squared distances on their bit patterns.  For values >= +0 the unsigned integer
+// order is the numeric order; a NaN pattern sorts above +inf and is never taken, which is what the
+// reference does with it (`dist < min_dist` is false, src/maximin_utils.rs:61).  The comparison then
+// runs on the integer pipes: fmin(double) costs a DSETP on the FP64 pipe plus four select/logic
+// instructions, and the FP64 pipe is what the maximin kernels are short of.
+__device__ __forceinline__ double min_sqdist(double a, double b) {
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+    return __longlong_as_double((long long)(ub < ua ? ub : ua));
+}
+
 // 1/x for normal, positive x: MUFU.RCP64H seed (>= 20 good bits) + two Newton
 // steps (20 -> 40 -> 80 bits).  Relative error ~1 ulp; no special-case branch.
 __device__ __forceinline__ double fast_rcp(double x) {

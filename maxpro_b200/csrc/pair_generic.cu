@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairParams p) {
                     double pr = fma(q, q, kEps);  // src/maxpro_utils.rs:50-53
                     if (valid) t += 1.0 / pr;     // :54
                 } else if (valid) {
-                    t = fmin(t, acc[r][c]);
+                    t = min_sqdist(t, acc[r][c]);
                 }
             }
         t = MAXPRO ? warp_reduce_sum(t) : warp_reduce_min(t);

@@ -151,8 +151,8 @@ __device__ __forceinline__ void cta_score_item(const double* xs, int n, int d, i
 #pragma unroll
         for (int c = 0; c < kJB; ++c) {
             const int j = j0 + c;
-            if (full || (j < n && i0 < j)) st.mn = fmin(st.mn, prod[0][c]);
-            if (ROWS == 2 && (full || (j < n && i1 < j))) st.mn = fmin(st.mn, prod[1][c]);
+            if (full || (j < n && i0 < j)) st.mn = min_sqdist(st.mn, prod[0][c]);
+            if (ROWS == 2 && (full || (j < n && i1 < j))) st.mn = min_sqdist(st.mn, prod[1][c]);
         }
     }
 }

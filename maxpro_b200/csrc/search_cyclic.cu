@@ -144,7 +144,7 @@ __device__ __forceinline__ void cyc_tile_window(const unsigned char* cand, unsig
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xj[r + c]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c])); }
-            else mins[r] = fmin(mins[r], cyc_sqdist_term<D>(xi[r], xj[r + c]));
+            else mins[r] = min_sqdist(mins[r], cyc_sqdist_term<D>(xi[r], xj[r + c]));
         }
 }
 
@@ -208,7 +208,7 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
                 if (live) { if (SAFE) acc += 1.0 / pterm; else ch[j % R].push(pterm); }
             } else {
                 const double dterm = cyc_sqdist_term<D>(xa, xb);
-                if (live) mins[j % R] = fmin(mins[j % R], dterm);
+                if (live) mins[j % R] = min_sqdist(mins[j % R], dterm);
             }
         }
     }
@@ -226,7 +226,7 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
     if (MAXPRO) return acc;
     double m = mins[0];
 #pragma unroll
-    for (int r = 1; r < R; ++r) m = fmin(m, mins[r]);
+    for (int r = 1; r < R; ++r) m = min_sqdist(m, mins[r]);
     return m;
 }
 

@@ -136,7 +136,7 @@ __device__ __forceinline__ double score_group_design(const double* xs, int strid
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (MAXPRO) ch[r].push(maxpro_term<D>(xi[r], xj[u]));
-                    else mins[r] = fmin(mins[r], sqdist_term<D>(xi[r], xj[u]));
+                    else mins[r] = min_sqdist(mins[r], sqdist_term<D>(xi[r], xj[u]));
                 }
             if (MAXPRO) pushed += U;
         }
@@ -149,7 +149,7 @@ __device__ __forceinline__ double score_group_design(const double* xs, int strid
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (MAXPRO) ch[r].push(maxpro_term<D>(xi[r], xj));
-                    else mins[r] = fmin(mins[r], sqdist_term<D>(xi[r], xj));
+                    else mins[r] = min_sqdist(mins[r], sqdist_term<D>(xi[r], xj));
                 }
             }
             if (MAXPRO) pushed += 1;
@@ -166,7 +166,7 @@ __device__ __forceinline__ double score_group_design(const double* xs, int strid
 #pragma unroll
             for (int r2 = r + 1; r2 < R; ++r2) {
                 if (MAXPRO) ch[(r + r2) % R].push(maxpro_term<D>(xi[r], xi[r2]));
-                else mins[(r + r2) % R] = fmin(mins[(r + r2) % R], sqdist_term<D>(xi[r], xi[r2]));
+                else mins[(r + r2) % R] = min_sqdist(mins[(r + r2) % R], sqdist_term<D>(xi[r], xi[r2]));
             }
         if (MAXPRO) pushed += R / 2 + 1;
     }
@@ -181,7 +181,7 @@ __device__ __forceinline__ double score_group_design(const double* xs, int strid
                 double xj[D];
                 load_row(xj, j);
                 if (MAXPRO) ch[0].push(maxpro_term<D>(xi, xj));
-                else mins[0] = fmin(mins[0], sqdist_term<D>(xi, xj));
+                else mins[0] = min_sqdist(mins[0], sqdist_term<D>(xi, xj));
             }
             if (MAXPRO) pushed += 1;
         }
@@ -192,7 +192,7 @@ __device__ __forceinline__ double score_group_design(const double* xs, int strid
     }
     double m = mins[0];
 #pragma unroll
-    for (int r = 1; r < R; ++r) m = fmin(m, mins[r]);
+    for (int r = 1; r < R; ++r) m = min_sqdist(m, mins[r]);
     return m;
 }
 

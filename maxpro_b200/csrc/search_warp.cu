@@ -176,12 +176,12 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
             } else {
                 if (whole) {
 #pragma unroll
-                    for (int c = 0; c < kWarpSB; ++c) mn = fmin(mn, fmin(pr[0][c], pr[1][c]));
+                    for (int c = 0; c < kWarpSB; ++c) mn = min_sqdist(mn, min_sqdist(pr[0][c], pr[1][c]));
                 } else {
 #pragma unroll
                     for (int c = 0; c < kWarpSB; ++c) {
-                        if (s0 + c <= smax0) mn = fmin(mn, pr[0][c]);
-                        if (s0 + c <= smax1) mn = fmin(mn, pr[1][c]);
+                        if (s0 + c <= smax0) mn = min_sqdist(mn, pr[0][c]);
+                        if (s0 + c <= smax1) mn = min_sqdist(mn, pr[1][c]);
                     }
                 }
             }
