@@ -178,8 +178,10 @@ __device__ __forceinline__ void cta_score_item_any(int chunk, const double* xs, 
 __device__ __forceinline__ void cta_stage_candidate(double* xs, unsigned short* jst, int n, int d, int ns, uint32_t s_lo, uint32_t s_hi,
                                                     double c1, double c0, int tid, int nthreads) {
     const int nb = (n + 1) / 2;
-    for (int q = tid; q < d * nb; q += nthreads) {
-        const int k = q / nb, b = q - k * nb;
+    // block q <-> (column k, element pair b), walked without a division
+    int k = 0, b = tid;
+    while (b >= nb && k < d) { b -= nb; ++k; }
+    while (k < d) {
         Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
         const int i = 2 * b;
         xs[k * ns + i] = stratum_value((uint32_t)i, w.x, c1, c0);
@@ -188,6 +190,8 @@ __device__ __forceinline__ void cta_stage_candidate(double* xs, unsigned short* 
             xs[k * ns + i + 1] = stratum_value((uint32_t)i + 1u, w.z, c1, c0);
             jst[k * ns + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
         }
+        b += nthreads;
+        while (b >= nb && k < d) { b -= nb; ++k; }
     }
 }
 
