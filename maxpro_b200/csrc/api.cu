@@ -310,6 +310,7 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
         CUDA_TRY(mp::launch_generate(n, d, seed, c0, cnt, w.designs, stream));
         mp::ScoreLaunch S{};
         S.designs = w.designs; S.b = cnt; S.n = n; S.d = d; S.metric = metric;
+        S.in_cube = 1;  // generate_lhd values lie in [0, 1)
         S.scores = w.scores; S.partial = w.partial; S.block_best = w.block_best;
         S.done_counter = w.counter; S.result = w.chunk_result; S.stream = stream;
         CUDA_TRY(mp::launch_score_batch(S));

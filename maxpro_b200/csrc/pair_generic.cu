@@ -15,9 +15,12 @@
 // (S/pairs)^(1/d) or sqrt, and does the argbest with the reference tie rule, so
 // the result does not depend on scheduling.
 //
-// Arithmetic: maxpro terms use an IEEE divide (designs may lie outside the unit
-// cube, so the reciprocal-chain trick of the search kernels is not range-safe
-// here); maximin uses separate multiply and add in the reference's k order and
+// Arithmetic: maxpro terms use an IEEE divide when the designs come from the caller
+// (they may lie outside the unit cube, where the reciprocal chains of the search
+// kernels are not range-safe); when the search itself generated them (chunked
+// path for designs above 227 KB) the launch says so and the 16 terms of a thread
+// go through four reciprocal chains: 3 FP64 instructions per term instead of
+// ~12.  Maximin uses separate multiply and add in the reference's k order and
 // is bit-exact with src/maximin_utils.rs:39-44.
 #include "common.cuh"
 #include "reduce.cuh"
@@ -36,7 +39,7 @@ struct PairParams {
     double* partial;            // [b * items]
 };
 
-template <bool MAXPRO>
+template <bool MAXPRO, bool IN_CUBE>
 __global__ void __launch_bounds__(256) pair_tile_kernel(PairParams p) {
     __shared__ double xi_s[kKC][kLd];
     __shared__ double xj_s[kKC][kLd];
@@ -88,6 +91,11 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairParams p) {
         }
 
         double t = MAXPRO ? 0.0 : CUDART_INF;
+        RecipChain ch[4];
+        if (MAXPRO && IN_CUBE) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) ch[r].reset();
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -97,11 +105,16 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairParams p) {
                 if (MAXPRO) {
                     double q = acc[r][c];
                     double pr = fma(q, q, kEps);  // src/maxpro_utils.rs:50-53
-                    if (valid) t += 1.0 / pr;     // :54
+                    if (IN_CUBE) { if (valid) ch[r].push(pr); }
+                    else if (valid) t += 1.0 / pr;  // :54
                 } else if (valid) {
                     t = min_sqdist(t, acc[r][c]);
                 }
             }
+        if (MAXPRO && IN_CUBE) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) t = ch[r].flush_into(t);  // empty chains add 0
+        }
         t = MAXPRO ? warp_reduce_sum(t) : warp_reduce_min(t);
         if ((tid & 31) == 0) warp_part[tid >> 5] = t;
         __syncthreads();
@@ -174,8 +187,12 @@ cudaError_t launch_score_batch(const ScoreLaunch& L) {
     unsigned long long work = L.b * (unsigned long long)p.items;
     int grid = (int)(work < 148ull * 16 ? work : 148ull * 16);
     if (grid == 0) return cudaSuccess;
-    if (L.metric == 0) pair_tile_kernel<true><<<grid, 256, 0, L.stream>>>(p);
-    else pair_tile_kernel<false><<<grid, 256, 0, L.stream>>>(p);
+    if (L.metric == 0) {
+        if (L.in_cube) pair_tile_kernel<true, true><<<grid, 256, 0, L.stream>>>(p);
+        else pair_tile_kernel<true, false><<<grid, 256, 0, L.stream>>>(p);
+    } else {
+        pair_tile_kernel<false, false><<<grid, 256, 0, L.stream>>>(p);
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
