@@ -1,4 +1,4 @@
-"""Multi-GPU sharding of the random search.
+"""Multi-GPU sharding of the random search and of the annealing chains.
 
 Candidates are independent (src/lib.rs:65-75: candidate i depends on seed+i only),
 so rank r of W scores the contiguous GLOBAL index block [r*N/W, (r+1)*N/W) with no
@@ -61,3 +61,43 @@ def build_lhd_sharded(n: int, d: int, n_iterations: int, metric: int, seed: int,
     fn = search_fn or engine.search_range
     score, index = fn(n, d, metric, seed, lo, hi)
     return allgather_minloc(score, index, metric, device=device, group=group)
+
+
+def anneal_lhd_sharded(design, n_iterations: int, initial_temp: float, cooling_rate: float, metric: int,
+                       minimize: bool, seed: int, swap: bool, n_chains: int,
+                       anneal_fn: Callable = None, device=None, group=None):
+    """n_chains independent chains of anneal_lhd (src/anneal.rs:56-143) over all ranks.
+
+    Chain c draws from stream seed + c whatever the world size (rank r runs the contiguous block
+    [r*C/W, (r+1)*C/W) by passing seed + lo as its seed), so the result is identical for any
+    world size.  One all-gather of (metric, global chain) per rank -- strictly better metric wins,
+    the lowest chain index on ties, as on one GPU -- and one broadcast of the winning design
+    (n*d doubles) from the rank that owns it.  Returns (design, metric, chain) on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_range(n_chains, rank, world)
+    fn = anneal_fn or engine.anneal_lhd
+    x = np.ascontiguousarray(design, dtype=np.float64)
+    if hi > lo:
+        out, best, chain = fn(x, n_iterations, initial_temp, cooling_rate, metric, minimize,
+                              (seed + lo) & 0xFFFFFFFFFFFFFFFF, swap, hi - lo)
+        chain += lo
+    else:  # more ranks than chains: this rank contributes the identity
+        out, best, chain = x.copy(), (np.inf if minimize else -np.inf), 2 ** 63 - 1
+    rec = torch.tensor([np.float64(best).view(np.int64).item(), int(chain)], dtype=torch.int64, device=device)
+    allrec = torch.empty(world * 2, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allrec, rec, group=group)
+    flat = allrec.cpu().numpy().reshape(world, 2)
+    metrics = flat[:, 0].copy().view(np.float64)
+    chains = flat[:, 1]
+    owner = 0
+    for r in range(1, world):
+        better = metrics[r] < metrics[owner] if minimize else metrics[r] > metrics[owner]
+        if better or (metrics[r] == metrics[owner] and chains[r] < chains[owner]):
+            owner = r
+    t = torch.from_numpy(np.ascontiguousarray(out)).to(device) if device is not None else torch.from_numpy(np.ascontiguousarray(out))
+    dist.broadcast(t, src=owner if group is None else dist.get_global_rank(group, owner), group=group)
+    return t.cpu().numpy(), float(metrics[owner]), int(chains[owner])

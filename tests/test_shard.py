@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: the N>1 path of the search -- contiguous global shards, one
-16-byte all-gather, fold with the reference tie rule.  The per-rank scorer here is the CPU
+"""CPU, world_size 2 over gloo: the N>1 paths -- the search (contiguous global shards, one 16-byte
+all-gather, fold with the reference tie rule) and the annealing chains (contiguous chain blocks,
+one all-gather, one broadcast of the winning design).  The per-rank scorer here is the CPU
 oracle (tests may use it); on GPUs the same code runs with engine.search_range over NCCL."""
 import socket
 
@@ -37,6 +38,50 @@ def _worker(rank, world, port, q):
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
+
+
+def _anneal_worker(rank, world, port, q):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        x = oracle.generate_lhd(12, 2, 3)
+
+        def chains_on_cpu(design, iters, t0, cooling, metric, minimize, seed, swap, n_chains):
+            # what engine.anneal_lhd does on a GPU: chain c uses stream seed + c, best chain wins, lowest index on ties
+            runs = [oracle.anneal_lhd(design, iters, t0, cooling, metric, minimize, seed + c, swap) for c in range(n_chains)]
+            best = 0
+            for c in range(1, n_chains):
+                if (runs[c][1] < runs[best][1]) if minimize else (runs[c][1] > runs[best][1]):
+                    best = c
+            return runs[best][0], runs[best][1], best
+
+        res = {}
+        for chains in (5, 1):  # 1 chain on 2 ranks: one rank contributes the identity
+            res[chains] = shard.anneal_lhd_sharded(x, 150, 1.0, 0.98, oracle.MAXPRO, True, 77, True, chains,
+                                                   anneal_fn=chains_on_cpu)
+        res["ref5"] = chains_on_cpu(x, 150, 1.0, 0.98, oracle.MAXPRO, True, 77, True, 5)
+        res["ref1"] = chains_on_cpu(x, 150, 1.0, 0.98, oracle.MAXPRO, True, 77, True, 1)
+        q.put((rank, {k: (np.asarray(v[0]).tolist(), float(v[1]), int(v[2])) for k, v in res.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_anneal_world2_gloo():
+    """Chains split over two ranks give the single-process answer: same best chain, same design."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_anneal_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert got[r][5] == got[r]["ref5"]
+        assert got[r][1] == got[r]["ref1"]
+    assert got[0][5] == got[1][5]
 
 
 def test_shard_range_partitions():
