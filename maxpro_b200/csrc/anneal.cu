@@ -27,10 +27,11 @@
 #include "anneal.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace mp {
 
-template <bool MAXPRO, int PLACE>
+template <bool MAXPRO, int PLACE, bool SWAP>
 __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     extern __shared__ __align__(16) double smem_d[];
     const int n = (int)p.n, d = (int)p.d, nd = n * d;
@@ -49,8 +50,8 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     // choice between shared and global turns the scoring loads into generic ones: 15 % slower).
     double* const scratch = PLACE != 0 ? p.cur_global + (size_t)blockIdx.x * (PLACE == 2 ? 2 : 1) * dns : nullptr;
     double* cur = PLACE != 0 ? scratch : smem_d;   // [k][i]
-    double* cand = PLACE == 2 ? (p.swap ? cur : scratch + dns) : (PLACE == 1 ? smem_d : (p.swap ? cur : smem_d + dns));
-    double* part = smem_d + (PLACE == 2 ? 0 : ((PLACE == 1 || p.swap) ? dns : 2 * dns));   // 32 doubles: warp partials of a reduction
+    double* cand = PLACE == 2 ? (SWAP ? cur : scratch + dns) : (PLACE == 1 ? smem_d : (SWAP ? cur : smem_d + dns));
+    double* part = smem_d + (PLACE == 2 ? 0 : ((PLACE == 1 || SWAP) ? dns : 2 * dns));   // 32 doubles: warp partials of a reduction
     Decision* dec = reinterpret_cast<Decision*>(part + 32);
     uint4* draws = reinterpret_cast<uint4*>(part + 34);   // kDrawBatch swap draws
     double2* rows = reinterpret_cast<double2*>(draws + kDrawBatch);  // [d] {x[r1][k], x[r2][k]} of the move
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
             double mine, u = 0.0;
             int r1 = 0, r2 = 0, c = 0;
             bool incremental = false, applied = false;
-            if (p.swap) {
+            if (SWAP) {
                 const unsigned int slot = (unsigned int)t & (kDrawBatch - 1);
                 if (slot == 0) {
                     // every reader of the previous batch is past a barrier of iteration t-1
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                         cur[c * ns + r1] = v2; cur[c * ns + r2] = v1;  // anneal.rs:34-39
                     }
                     __syncthreads();
-                    publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
+                    publish_partial<MAXPRO>(n >= kTileScoreMinN ? full_score_tiles<MAXPRO>(cur, n, d, ns, in_cube)
+                                                                : full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
                 }
             } else {
                 // jitter: element e = i*d + k (row-major, the reference's iteration order,
@@ -157,7 +159,8 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 }
                 // every coordinate of the proposal has just been clamped into [0, 1]
                 const bool cand_in_cube = __syncthreads_and(jok) != 0;
-                publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cand, n, d, ns, cand_in_cube), part);
+                publish_partial<MAXPRO>(n >= kTileScoreMinN ? full_score_tiles<MAXPRO>(cand, n, d, ns, cand_in_cube)
+                                                            : full_score_partial<MAXPRO>(cand, n, d, ns, cand_in_cube), part);
             }
             __syncthreads();  // partials are in; nobody reads cur / cand for scoring any more
 
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 if (!p.minimize) diff *= -1.0;
                 const double p_acc = diff < 0.0 ? 1.0 : exp(-diff / temp);
                 const bool accept = u < p_acc;
-                if (p.swap && accept != applied && lane == 0) {
+                if (SWAP && accept != applied && lane == 0) {
                     // apply an accepted incremental move / undo a rejected applied one
                     double v1 = cur[c * ns + r1], v2 = cur[c * ns + r2];
                     cur[c * ns + r1] = v2; cur[c * ns + r2] = v1;
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 if (accept) { cur_metric = new_metric; raw_cur = raw_new; }
                 const bool improves = (p.minimize && cur_metric < global_best) || (!p.minimize && cur_metric > global_best);
                 int best_mode = 0;
-                if (accept && p.swap) {
+                if (accept && SWAP) {
                     if (log_n < kLogCap) {
                         if (lane == 0) mlog[log_n] = make_ushort4((unsigned short)r1, (unsigned short)r2, (unsigned short)c, 0);
                         ++log_n;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                     }
                 }
                 if (improves) {
-                    best_mode = (p.swap && materialized && !overflow) ? 1 : 2;
+                    best_mode = (SWAP && materialized && !overflow) ? 1 : 2;
                     if (lane == 0) { dec->log_n = log_n; }
                     global_best = cur_metric;
                     materialized = true; overflow = false; log_n = 0;
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
             }
             __syncthreads();
             const int accept = dec->accept, best_mode = dec->best_mode;
-            if (accept && !p.swap) {
+            if (accept && !SWAP) {
                 for (int e = threadIdx.x; e < dns; e += blockDim.x) cur[e] = cand[e];
                 __syncthreads();
             }
@@ -241,7 +244,8 @@ __global__ void __launch_bounds__(512) anneal_raw0_kernel(const double* design, 
         cur[k * ns + i] = v;
     }
     const bool in_cube = __syncthreads_and(ok) != 0;
-    publish_partial<MAXPRO>(full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
+    publish_partial<MAXPRO>(n >= kTileScoreMinN ? full_score_tiles<MAXPRO>(cur, n, d, ns, in_cube)
+                                                : full_score_partial<MAXPRO>(cur, n, d, ns, in_cube), part);
     __syncthreads();
     if (threadIdx.x < 32) {
         const double raw = warp_total<MAXPRO>(part, (blockDim.x + 31) >> 5);
@@ -298,7 +302,7 @@ size_t anneal_jitter_scratch_bytes(unsigned long long n, unsigned long long d, i
     if (place == 0) return 0;
     const unsigned long long ns = (n + 1) & ~1ull;
     const unsigned long long grid = n_chains < kHbmGrid ? n_chains : kHbmGrid;
-    return (size_t)(grid * ns * d * (place == 2 ? 2 : 1)) * sizeof(double);
+    return (size_t)(grid * ns * d * (place == 2 ? 2 : 1)) * sizeof(double) + 64;  // + the masked over-read of the last column block
 }
 
 // Every design the 16-bit row indices can address is supported: what does not fit shared memory is annealed out of HBM.
@@ -345,8 +349,14 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) kernel<<<(unsigned int)grid, threads, smem, L.stream>>>(p);
     };
-    if (L.metric == 0) { if (place == 2) go(anneal_kernel<true, 2>); else if (place == 1) go(anneal_kernel<true, 1>); else go(anneal_kernel<true, 0>); }
-    else { if (place == 2) go(anneal_kernel<false, 2>); else if (place == 1) go(anneal_kernel<false, 1>); else go(anneal_kernel<false, 0>); }
+    auto pick = [&](auto mp_tag) {
+        constexpr bool MP = decltype(mp_tag)::value;
+        if (L.swap) { if (place == 2) go(anneal_kernel<MP, 2, true>); else go(anneal_kernel<MP, 0, true>); }
+        else if (place == 2) go(anneal_kernel<MP, 2, false>);
+        else if (place == 1) go(anneal_kernel<MP, 1, false>);
+        else go(anneal_kernel<MP, 0, false>);
+    };
+    if (L.metric == 0) pick(std::true_type{}); else pick(std::false_type{});
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();

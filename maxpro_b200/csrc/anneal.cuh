@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "kernels.h"
+#include "tile_score.cuh"
 
 namespace mp {
 
@@ -117,6 +118,35 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
     }
     return MAXPRO ? acc : mn;  // this thread's share; the caller reduces
 }
+
+// The same criterion over work items of 64 rows x 8 columns (tile_score.cuh), dealt round-robin to the
+// warps: 8 shared-memory wavefronts per dimension for 16 pairs per lane, where the cyclic items above
+// take 18 for 8 -- and the full re-score is bound by exactly that (16 warps x 18 wavefronts against
+// 132 cycles of FP64 issue per dimension step).  Worth it from n ~ 256 up; below that the 64-row
+// tiles are mostly padding.  xs must be 16-byte aligned with an even row stride; the last column
+// block may read up to 6 doubles past row n - 1 of the last dimension (masked), so the buffer needs
+// that much slack behind it.
+template <bool MAXPRO>
+__device__ __forceinline__ double full_score_tiles(const double* xs, int n, int d, int ns, bool in_cube) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tiles = (n + kTileRows - 1) / kTileRows;
+    const int chunk = cta_dim_chunk(d);
+    CtaScore st;
+    st.reset();
+    int t = 0, jb = warp;
+    int nblk = (n + kJB - 1) / kJB;  // column blocks from the tile's first row
+    while (true) {
+        while (t < tiles && jb >= nblk) { jb -= nblk; ++t; nblk = (n - t * kTileRows + kJB - 1) / kJB; }
+        if (t >= tiles) break;
+        if (!MAXPRO || in_cube) cta_score_item_any<MAXPRO, false>(chunk, xs, n, d, ns, t * kTileRows, t * kTileRows + jb * kJB, lane, st);
+        else cta_score_item_any<MAXPRO, true>(chunk, xs, n, d, ns, t * kTileRows, t * kTileRows + jb * kJB, lane, st);
+        jb += nw;
+    }
+    if (MAXPRO) st.flush();
+    return MAXPRO ? st.acc : st.mn;  // this thread's share; the caller reduces
+}
+
+constexpr int kTileScoreMinN = 256;  // designs from this size up take full_score_tiles
 
 template <bool MAXPRO>
 __device__ __forceinline__ double metric_from_raw(double raw, int n, double n_pairs, double inv_d) {
