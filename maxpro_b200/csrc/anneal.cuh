@@ -122,7 +122,7 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
 // The same criterion over work items of 64 rows x 8 columns (tile_score.cuh), dealt round-robin to the
 // warps: 8 shared-memory wavefronts per dimension for 16 pairs per lane, where the cyclic items above
 // take 18 for 8 -- and the full re-score is bound by exactly that (16 warps x 18 wavefronts against
-// 132 cycles of FP64 issue per dimension step).  Worth it from n ~ 256 up; below that the 64-row
+// 132 cycles of FP64 issue per dimension step).  Worth it from n ~ 100 up; below that the 64-row
 // tiles are mostly padding.  xs must be 16-byte aligned with an even row stride; the last column
 // block may read up to 6 doubles past row n - 1 of the last dimension (masked), so the buffer needs
 // that much slack behind it.
@@ -146,7 +146,13 @@ __device__ __forceinline__ double full_score_tiles(const double* xs, int n, int 
     return MAXPRO ? st.acc : st.mn;  // this thread's share; the caller reduces
 }
 
-constexpr int kTileScoreMinN = 256;  // designs from this size up take full_score_tiles
+// Designs from this size up take full_score_tiles.  Measured with 1,184 jitter chains (algorithmic TFLOP/s,
+// cyclic items -> tiles): (100,5) 5.4 -> 6.9, (128,8) 8.7 -> 10.3, (200,10) 7.6 -> 11.5, (250,4) 8.2 -> 11.5,
+// (1000,20) 10.6 -> 18.9; (64,6) 5.7 -> 5.4.  A single (100,5) chain: 5.5 -> 4.9 us per step.
+#ifndef MAXPRO_TILE_SCORE_MIN_N
+#define MAXPRO_TILE_SCORE_MIN_N 96
+#endif
+constexpr int kTileScoreMinN = MAXPRO_TILE_SCORE_MIN_N;
 
 template <bool MAXPRO>
 __device__ __forceinline__ double metric_from_raw(double raw, int n, double n_pairs, double inv_d) {

@@ -5,7 +5,7 @@
 // the engine's schedules in shared-memory bandwidth, which is what the annealer's full re-score
 // (one row x 8 cyclic shifts per item: 18 wavefronts for 8 pairs) is bound by.
 // Used by the CTA-per-candidate search (search_cta.cu) and by the annealer's full re-score of
-// designs with n >= 256 (anneal.cuh).
+// designs with n >= 96 (anneal.cuh).
 #pragma once
 #include "common.cuh"
 
