@@ -415,6 +415,24 @@ def test_anneal_design_outside_unit_cube(swap):
     assert np.array_equal(got, ref) and math.isclose(best, ref_best, rel_tol=REL)
 
 
+@pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)])
+@pytest.mark.parametrize("n,d", [(96, 3), (130, 5), (257, 4), (200, 10)])
+def test_anneal_jitter_tile_rescore_matches_oracle(n, d, metric, minimize):
+    """From n = 96 up the full re-score runs on 64 x 8 broadcast tiles (tile_score.cuh) instead of cyclic
+    items -- partial last tiles, odd n, chunked dimension loops.  Jitter moves, oracle trajectory; then a
+    design outside the unit cube (IEEE-divide epilogue of the tiles) for the first step before the clamp."""
+    x = oracle.generate_lhd(n, d, 19)
+    ref, ref_best = oracle.anneal_lhd(x, 60, 1.0, 0.95, metric, minimize, 5, False)
+    got, best, _ = engine.anneal_lhd(x, 60, 1.0, 0.95, metric, minimize, 5, False, n_chains=1)
+    assert np.array_equal(got, ref)
+    assert math.isclose(best, ref_best, rel_tol=REL) if metric == METRIC_MAXPRO else best == ref_best
+    y = x * 3.0 - 1.0
+    ref, ref_best = oracle.anneal_lhd(y, 4, 1.0, 0.95, metric, minimize, 6, True)   # swap: stays outside the cube
+    got, best, _ = engine.anneal_lhd(y, 4, 1.0, 0.95, metric, minimize, 6, True, n_chains=1)
+    assert np.array_equal(got, ref)
+    assert math.isclose(best, ref_best, rel_tol=REL) if metric == METRIC_MAXPRO else best == ref_best
+
+
 def test_anneal_many_chains_large_design_properties():
     """C4 shape at a bounded size: every chain starts from the same design, so the best of 296
     chains is never worse than the start, is an LHD (swaps permute columns), re-scores to the
