@@ -649,7 +649,9 @@ int maxpro_order_design(const double* design, uint64_t n, uint64_t d, int metric
     mp::OrderLaunch L{};
     L.design = dx.as<double>(); L.n = n; L.d = d; L.metric = metric; L.minimize = minimize ? 1 : 0;
     L.perm = dp.as<unsigned long long>(); L.acc = da.as<double>(); L.pool = dpool.as<unsigned int>(); L.stream = st;
-    if (mp::order_cluster_supported(n, d) && !getenv("MAXPRO_NO_ORDER_CLUSTER")) CUDA_TRY(mp::launch_order_cluster(L));
+    const bool no_cluster = getenv("MAXPRO_NO_ORDER_CLUSTER") != nullptr;
+    if (!no_cluster && mp::order_cluster_async_supported(n, d) && !getenv("MAXPRO_ORDER_CLUSTER_SYNC")) CUDA_TRY(mp::launch_order_cluster_async(L));
+    else if (!no_cluster && mp::order_cluster_supported(n, d)) CUDA_TRY(mp::launch_order_cluster(L));
     else CUDA_TRY(mp::launch_order(L));
     std::vector<unsigned long long> hp(n);
     CUDA_TRY(cudaMemcpyAsync(hp.data(), dp.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

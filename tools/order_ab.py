@@ -1,0 +1,29 @@
+"""A/B of the cluster ordering kernels: order_cluster_async.cu variants (MAXPRO_OAS_VARIANT=threads,exchange,loop)
+against order_cluster.cu (two cluster barriers per step)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine
+
+shapes = [(5000, 8), (500, 5), (1000, 20), (10000, 2)]
+variants = [("sync", {"MAXPRO_ORDER_CLUSTER_SYNC": "1"})]
+for thr in (256, 512):
+    for xch in (0, 1, 2):
+        for lv in (0, 1):
+            variants.append((f"{thr},{xch},{lv}", {"MAXPRO_OAS_VARIANT": f"{thr},{xch},{lv}"}))
+only = sys.argv[1:] 
+for n, d in shapes:
+    x = engine.generate_lhd(n, d, 42)
+    for metric, mn, name in ((METRIC_MAXPRO, True, "maxpro"), (METRIC_MAXIMIN, False, "maximin")):
+        ref = None
+        out = []
+        for label, env in variants:
+            if only and label != "sync" and label not in only: continue
+            os.environ.update(env)
+            engine.order_design(x, metric, mn)
+            best = 1e9
+            for _ in range(4):
+                t0 = time.perf_counter(); _, p = engine.order_design(x, metric, mn); best = min(best, time.perf_counter() - t0)
+            for k in env: del os.environ[k]
+            if ref is None: ref = p.tolist()
+            out.append(f"{label}: {best/n*1e6:.2f}{'' if p.tolist() == ref else ' MISMATCH'}")
+        print(f"n={n} d={d} {name} us/step | " + " | ".join(out), flush=True)
