@@ -1,15 +1,12 @@
-"""A/B of the cluster ordering kernels: order_cluster_async.cu variants (MAXPRO_OAS_VARIANT=threads,exchange,loop)
-against order_cluster.cu (two cluster barriers per step)."""
+"""A/B of the cluster ordering kernels: order_cluster_async.cu (mbarriers, st.async, remote loads) against
+order_cluster.cu (two cluster barriers per step)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine
 
 shapes = [(5000, 8), (500, 5), (1000, 20), (10000, 2)]
 variants = [("sync", {"MAXPRO_ORDER_CLUSTER_SYNC": "1"})]
-for thr in (256, 512):
-    for xch in (0, 1, 2):
-        for lv in (0, 1):
-            variants.append((f"{thr},{xch},{lv}", {"MAXPRO_OAS_VARIANT": f"{thr},{xch},{lv}"}))
+variants.append(("async", {}))
 only = sys.argv[1:] 
 for n, d in shapes:
     x = engine.generate_lhd(n, d, 42)

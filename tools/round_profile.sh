@@ -31,6 +31,7 @@ $NCU --set full --import-source on -k regex:search_warp -s 1 -c 1 -o $O/${TAG}_s
     python tools/search_prof.py 100 10 1000000 > $O/${TAG}_ncu_warp.log 2>&1
 $NCU --set full --import-source on -k regex:search_small -s 1 -c 1 -o $O/${TAG}_search_small \
     python tools/search_prof.py 50 8 8000000 > $O/${TAG}_ncu_small.log 2>&1
+python tools/order_ab.py > $O/${TAG}_order_ab.txt 2>&1
 python tools/shape_sweep.py > $O/${TAG}_shape_sweep_maxpro.txt 2>&1
 python tools/shape_sweep.py maximin > $O/${TAG}_shape_sweep_maximin.txt 2>&1
 ls -la $O | tail -20
