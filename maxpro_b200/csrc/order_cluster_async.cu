@@ -23,6 +23,7 @@
 // latency.  No thread ever waits for a thread of another CTA except through those two.
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -34,7 +35,6 @@ namespace mp {
 
 namespace {
 
-constexpr int kCl = 8;          // CTAs per cluster (portable maximum)
 constexpr unsigned int kNone = 0xFFFFFFFFu;
 
 struct __align__(16) CandRec {
@@ -152,8 +152,11 @@ __device__ __forceinline__ void warp_argmin_key(unsigned long long& key, unsigne
 
 // THR threads per CTA: THR - 32 workers own the slots, the last warp serves the hole.  SPP = slots a worker
 // evaluates per pass (independent dependency chains side by side).
-template <bool MAXPRO, bool MINIMIZE, int THR, int SPP>
-__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams p) {
+// CL = CTAs per cluster (launch attribute): 8, or 16 (non-portable size) for pools large enough to pay for the
+// doubled record table.
+template <bool MAXPRO, bool MINIMIZE, int THR, int SPP, int CL>
+__global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams p) {
+    constexpr unsigned int kCl = CL;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int rank = cluster.block_rank();
     const unsigned int n = p.n, d = p.d, ds = p.ds, slots = p.slots;
@@ -370,41 +373,65 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(THR, 1) order_clus
     cluster.sync();  // nobody leaves while its shared memory can still be addressed
 }
 
-size_t order_async_smem(unsigned long long n, unsigned long long d, int thr) {
-    const unsigned long long slots = (n + kCl - 1) / kCl;
-    const unsigned long long nrec = kCl * (thr / 32);
+size_t order_async_smem(unsigned long long n, unsigned long long d, int thr, int cl) {
+    const unsigned long long slots = (n + cl - 1) / cl;
+    const unsigned long long nrec = (unsigned long long)cl * (thr / 32);
     return (size_t)(2 * nrec * sizeof(CandRec) + 4 * 8 + slots * (d | 1ull) * 8 + slots * 8 + (d + 1) * 8 + (d + 2) * 8 + slots * 4 + 16);
 }
+
+constexpr int kOasThreads = 256;  // 7 worker warps + the hole warp
+constexpr int kOasSlotsPerPass = 2;
+// Measured against 384 / 512 threads and three / four slots per pass on (5000,8), (500,5), (1000,20), (10000,2):
+// all within 5 %, this one ahead on three of the four shapes (profiles/r1j_order_ab.txt).
 
 }  // namespace
 
 bool order_cluster_async_supported(unsigned long long n, unsigned long long d) {
-    return n >= 64 && n < (1ull << 31) && d >= 1 && d + 2 <= 224 && order_async_smem(n, d, 256) + 1024 <= kSmemBudget;
+    return n >= 64 && n < (1ull << 31) && d >= 1 && d + 2 <= 224 && order_async_smem(n, d, kOasThreads, 8) + 1024 <= kSmemBudget;
 }
 
-template <int THR, int SPP>
-static cudaError_t launch_variant(const OrderLaunch& L) {
+template <int CL>
+static cudaError_t launch_cluster(const OrderLaunch& L) {
     OrdAsParams p;
     p.x = L.design; p.n = (unsigned int)L.n; p.d = (unsigned int)L.d; p.ds = (unsigned int)(L.d | 1ull);
-    p.slots = (unsigned int)((L.n + kCl - 1) / kCl);
+    p.slots = (unsigned int)((L.n + CL - 1) / CL);
     p.perm = L.perm;
-    const size_t smem = order_async_smem(L.n, L.d, THR);
+    const size_t smem = order_async_smem(L.n, L.d, kOasThreads, CL);
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<kCl, THR, smem, L.stream>>>(p);  // one cluster (compile-time __cluster_dims__)
-        count_launch();
-        return cudaGetLastError();
+        if (CL > 8) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CL); cfg.blockDim = dim3(kOasThreads); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kernel, p);  // one cluster
+        if (e == cudaSuccess) count_launch();
+        return e;
     };
-    if (L.metric == 0) return L.minimize ? go(order_cluster_async_kernel<true, true, THR, SPP>) : go(order_cluster_async_kernel<true, false, THR, SPP>);
-    return L.minimize ? go(order_cluster_async_kernel<false, true, THR, SPP>) : go(order_cluster_async_kernel<false, false, THR, SPP>);
+    if (L.metric == 0)
+        return L.minimize ? go(order_cluster_async_kernel<true, true, kOasThreads, kOasSlotsPerPass, CL>)
+                          : go(order_cluster_async_kernel<true, false, kOasThreads, kOasSlotsPerPass, CL>);
+    return L.minimize ? go(order_cluster_async_kernel<false, true, kOasThreads, kOasSlotsPerPass, CL>)
+                      : go(order_cluster_async_kernel<false, false, kOasThreads, kOasSlotsPerPass, CL>);
 }
 
 cudaError_t launch_order_cluster_async(const OrderLaunch& L) {
-    // 256 threads (7 worker warps + the hole warp), two slots per pass: measured against 384 / 512 threads and
-    // three / four slots per pass on (5000,8), (500,5), (1000,20), (10000,2) -- all within 5 %, this one ahead
-    // on three of the four shapes (profiles/r1j_order_ab.txt).
-    return launch_variant<256, 2>(L);
+    // 16 CTAs halve the slots of a worker; worth the doubled record table (128 records folded by every warp)
+    // once a worker of an 8-CTA cluster would hold three or more slots.
+    int cl = (L.n + 7) / 8 > 2ull * (kOasThreads - 32) ? 16 : 8;
+    if (const char* v = getenv("MAXPRO_ORDER_CLUSTER_CTAS")) cl = atoi(v) == 16 ? 16 : 8;
+    if (cl == 16) {
+        cudaError_t e = launch_cluster<16>(L);
+        if (e == cudaSuccess) return e;
+        (void)cudaGetLastError();  // a 16-CTA cluster could not be placed: the portable size always can
+    }
+    return launch_cluster<8>(L);
 }
 
 }  // namespace mp

@@ -4,17 +4,17 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine
 
-shapes = [(5000, 8), (500, 5), (1000, 20), (10000, 2)]
+shapes = [(5000, 8), (500, 5), (1000, 20), (10000, 2), (2000, 4), (3000, 10), (20000, 3)]
 variants = [("sync", {"MAXPRO_ORDER_CLUSTER_SYNC": "1"})]
+variants.append(("async8", {"MAXPRO_ORDER_CLUSTER_CTAS": "8"}))
+variants.append(("async16", {"MAXPRO_ORDER_CLUSTER_CTAS": "16"}))
 variants.append(("async", {}))
-only = sys.argv[1:] 
 for n, d in shapes:
     x = engine.generate_lhd(n, d, 42)
     for metric, mn, name in ((METRIC_MAXPRO, True, "maxpro"), (METRIC_MAXIMIN, False, "maximin")):
         ref = None
         out = []
         for label, env in variants:
-            if only and label != "sync" and label not in only: continue
             os.environ.update(env)
             engine.order_design(x, metric, mn)
             best = 1e9
