@@ -35,13 +35,20 @@ struct MinArg {
     __device__ __forceinline__ void take(double w, int b) { if (w < v) { v = w; a = b; } }
 };
 
+// Warp minimum of (squared distance, row), smaller row on equal distances.  A squared distance is >= +0, so its
+// bit pattern orders like the number: three REDUX.MIN (high word, low word among the lanes that hold the high
+// minimum, row among the lanes that hold both) instead of five shuffle levels of two-DSETP compares -- the
+// shuffle tree of such a pair costs ~600 cycles of latency per call (measured in order_cluster_async.cu) and
+// its compares run on the FP64 pipe, which is what this kernel is short of.
 __device__ __forceinline__ MinArg warp_minarg(MinArg m) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double w = __shfl_xor_sync(0xffffffffu, m.v, off);
-        const int b = __shfl_xor_sync(0xffffffffu, m.a, off);
-        if (w < m.v || (w == m.v && b < m.a)) { m.v = w; m.a = b; }
-    }
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(m.v);
+    const unsigned int hi = (unsigned int)(bits >> 32), lo = (unsigned int)bits;
+    const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned int mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    const bool mine = hi == mhi && lo == mlo;
+    const unsigned int ma = __reduce_min_sync(0xffffffffu, mine ? (unsigned int)m.a : 0xFFFFFFFFu);
+    m.v = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    m.a = (int)ma;
     return m;
 }
 

@@ -49,10 +49,16 @@ __device__ __forceinline__ double warp_reduce_sum(double v) {
     return v;
 }
 
+// Warp minimum of values that are >= +0 (squared distances, every caller's case): the bit pattern orders like
+// the number, so two REDUX.MIN (high word, then low word among the lanes that hold the high minimum) replace
+// five shuffle levels of fmin.  A NaN pattern sorts above +inf and is returned only if every lane holds one,
+// which is what the fmin tree gives.
 __device__ __forceinline__ double warp_reduce_min(double v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned int hi = (unsigned int)(bits >> 32), lo = (unsigned int)bits;
+    const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned int mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
 }
 
 // Minimum of two squared distances on their bit patterns.  For values >= +0 the unsigned integer
