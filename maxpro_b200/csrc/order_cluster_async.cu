@@ -7,20 +7,23 @@
 // kernel pays two `cluster.sync` per greedy step (~380 cycles each, every thread of 8 CTAs) plus a
 // remote store in front of each.  Here a step is
 //
-//   1  every CTA updates its slots against the point just placed and finds its best (value, position);
-//      eight lanes send that 16-byte record to the candidate table of every CTA with st.async, which
-//      counts the bytes on the DESTINATION's mbarrier; each CTA waits on its own mbarrier only
-//      (tables and mbarriers double-buffered by step parity);
-//   2  every CTA folds the 8 records (same answer everywhere: position q wins) and PULLS the winner's
-//      coordinates (and running value) out of its owner's shared memory with d + 1 remote loads;
+//   1  the worker warps update the CTA's slots against the point just placed; every WARP finds its best
+//      (value, position) with three REDUX.MIN on integer keys and sends that 16-byte record to the table of
+//      every CTA of the cluster with st.async, which counts the bytes on the DESTINATION's mbarrier; each
+//      CTA waits on its own mbarrier only (tables and mbarriers double-buffered by step parity, every phase
+//      armed in advance).  A complete table also says that every warp of the cluster is past its slots;
+//   2  every warp folds the records (same answer everywhere: position q wins) and warp 0 PULLS the winner's
+//      coordinates (and running value) out of its owner's shared memory with d + 1 remote loads; one
+//      __syncthreads makes them the CTA's;
 //   3  off the critical path: the owner of the last position L mails its entry to the owner of q
 //      (Vec::swap_remove moves the last element into the hole, order.rs:63,101) with st.async on the
-//      owner's `hole` mbarrier, and every CTA arrives on that mbarrier once its pull has landed.  The
-//      owner fills the hole when the mbarrier completes (mail in, nobody still reading the slot) --
-//      one thread does it after its regular slots of the NEXT step, so the wait is normally over.
+//      owner's `hole` mbarrier, and every CTA arrives on that mbarrier once its pull has landed.  Warp 0 of
+//      the owner, which has no slots of its own, fills the hole in the NEXT step when the mbarrier completes
+//      (mail in, nobody still reading the slot) and evaluates the entry straight out of the mailbox.
 //
-// Critical path per step: update loop, block argbest, one DSMEM store latency, fold, one DSMEM load
-// latency.  No thread ever waits for a thread of another CTA except through those two.
+// Critical path per step: slot update, warp argbest, one DSMEM store latency, fold, one DSMEM load latency,
+// one CTA barrier.  No thread waits for a thread of another CTA except through those two transfers.
+// Pools above 3,584 points take a 16-CTA cluster (non-portable size, launch attribute), the others 8.
 #include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
@@ -142,15 +145,15 @@ __device__ __forceinline__ void warp_argmin_key(unsigned long long& key, unsigne
 }
 
 #ifndef OAS_PROFILE
-#define OAS_PROFILE 0  // 1: per-phase clock64 sums printed by two threads of two CTAs (make EXTRA=-DOAS_PROFILE=1)
+#define OAS_PROFILE 0  // 1: when each warp of one CTA reaches each point of the step, cycles since the step's barrier (make EXTRA=-DOAS_PROFILE=1)
 #endif
 #if OAS_PROFILE
-#define OAS_T(i) { const long long now_ = clock64(); tsum[i] += now_ - tprev; tprev = now_; }
+#define OAS_T(i) { tsum[i] += clock64() - *t_ref; }  // time since the previous step's barrier, as thread 0 saw it
 #else
 #define OAS_T(i)
 #endif
 
-// THR threads per CTA: THR - 32 workers own the slots, the last warp serves the hole.  SPP = slots a worker
+// THR threads per CTA: warp 0 is the service warp (hole, pull, bookkeeping), the other THR - 32 threads own the slots.  SPP = slots a worker
 // evaluates per pass (independent dependency chains side by side).
 // CL = CTAs per cluster (launch attribute): 8, or 16 (non-portable size) for pools large enough to pay for the
 // doubled record table.
@@ -181,6 +184,11 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         mbar_init(cand_bar0 + 8, 1);
         mbar_init(hole_bar, kCl);      // one arrival per CTA (pull finished) + the mailed entry as transaction bytes
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // Every phase is ARMED IN ADVANCE with this CTA's own arrival and the bytes it will receive (they never
+        // change): arrive.expect_tx costs its thread ~300 cycles, which would otherwise sit in front of a wait.
+        mbar_arrive_expect_tx(cand_bar0, NREC * (unsigned int)sizeof(CandRec));
+        mbar_arrive_expect_tx(cand_bar0 + 8, NREC * (unsigned int)sizeof(CandRec));
+        mbar_arrive_expect_tx(hole_bar, (d + 2) * 8u);
     }
     // ---- load this CTA's slots: position p = slot*8 + rank holds point p at the start
     for (unsigned int s = tid; s < slots; s += T) {
@@ -197,6 +205,10 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
     double cur_min = CUDART_INF;
 #if OAS_PROFILE
     long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __shared__ long long t_ref_s;
+    volatile long long* t_ref = &t_ref_s;
+    if (tid == 0) t_ref_s = clock64();
+    __syncthreads();
 #endif
 
     // One greedy step.  CENTRE = the first point: distance to the centre of the cube, smaller wins, first
@@ -204,9 +216,6 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
     auto greedy_step = [&](auto centre_tag) {
         constexpr bool CENTRE = decltype(centre_tag)::value;
         constexpr bool MINI = CENTRE ? true : MINIMIZE;
-#if OAS_PROFILE
-        long long tprev = clock64();
-#endif
         // values of N entries side by side: coordinates x[u], old running values a[u] -> v[u].  Every entry is
         // computed in the reference's order (products and sums walk the dimensions one by one).
         auto eval_n = [&](auto n_tag, const double* const (&x)[SPP], const double (&a)[SPP], double (&v)[SPP]) {
@@ -262,8 +271,8 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         // ---- 1a. the worker warps update this CTA's slots, up to SPP per pass.  A worker whose pass holds the
         //          hole evaluates the stale entry with the others and drops the result.
         const unsigned int live = pool_n > rank ? (pool_n - rank + kCl - 1) / kCl : 0;  // slots with position < pool_n
-        if (tid < TW) {
-            for (unsigned int s0 = tid; s0 < live; s0 += SPP * TW) {
+        if (tid >= 32) {
+            for (unsigned int s0 = tid - 32; s0 < live; s0 += SPP * TW) {
                 const double* x[SPP];
                 double a[SPP], v[SPP];
                 unsigned int cnt = 0;
@@ -287,11 +296,11 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
             }
         }
         OAS_T(0)
-        // ---- 1b. the last warp has no slots of its own: it fills the hole left by the previous winner once the
+        // ---- 1b. warp 0 has no slots of its own: it fills the hole left by the previous winner once the
         //          mail is in and every CTA has pulled the winner's coordinates out of the slot.  Lane 0 evaluates
         //          the entry straight out of the mailbox while the other lanes copy it into the slot.
         if (hole_slot != kNone) {
-            if (tid >= TW) {
+            if (tid < 32) {
                 mbar_wait(hole_bar, hole_phase);
                 double* xc = coords + (size_t)hole_slot * ds;
                 for (unsigned int k = lane; k < d; k += 32) xc[k] = __longlong_as_double((long long)mail[k]);
@@ -312,9 +321,9 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         warp_argmin_key(bk, bp);
         if (lane < kCl)
             st_async_v2(map_rank(smem_u32(&cand[par * NREC + rank * NW + warp]), lane), bk, (unsigned long long)bp, map_rank(cbar, lane));
-        // The arrival this step's records are counted against (~300 cycles for arrive.expect_tx): by the warp
-        // that has no slots, after its own record is on the way.  The phase cannot complete before it.
-        if (tid == TW) mbar_arrive_expect_tx(cbar, NREC * (unsigned int)sizeof(CandRec));
+        // the hole mbarrier's phase has been consumed: arm the next one (any order with the next mail is fine --
+        // a phase cannot complete before this arrival)
+        if (hole_slot != kNone && tid == 0) mbar_arrive_expect_tx(hole_bar, (d + 2) * 8u);
         OAS_T(1)
         // ---- 2. wait for the records of all warps of the cluster, fold them (same answer in every warp), pull
         //         the winner.  A complete table also says that every warp of the cluster is past its slots.
@@ -330,6 +339,10 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         }
         warp_argmin_key(bk, bp);
         const unsigned int q = bp;
+        // this table's phase is consumed by this warp: arm the phase of step + 2.  The warps still waiting look
+        // for the parity of the completed phase, which cannot change before every warp of the cluster has sent
+        // the records of step + 2.
+        if (tid == 0) mbar_arrive_expect_tx(cbar, NREC * (unsigned int)sizeof(CandRec));
         OAS_T(3)
         const unsigned int L = pool_n - 1;
         const unsigned int q_owner = q % kCl, q_slot = q / kCl;
@@ -350,12 +363,12 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         OAS_T(4)
         __syncthreads();  // last_s complete: the pull of this CTA has landed
         OAS_T(5)
-        if (tid == T - 1) {
+#if OAS_PROFILE
+        if (tid == 0) t_ref_s = clock64();
+#endif
+        if (tid == 31) {
             if (rank == q_owner) p.perm[m] = ids[q_slot];
-            if (L != q) {
-                if (rank == q_owner) mbar_arrive_expect_tx(hole_bar, (d + 2) * 8u);
-                else mbar_arrive_remote(map_rank(hole_bar, q_owner));
-            }
+            if (L != q && rank != q_owner) mbar_arrive_remote(map_rank(hole_bar, q_owner));  // the owner's own arrival is armed
         }
         hole_slot = (L != q && rank == q_owner) ? q_slot : kNone;
         if (!MAXPRO && !CENTRE) cur_min = fmin(cur_min, last_s[d]);
@@ -366,9 +379,9 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
     greedy_step(std::true_type{});
     while (pool_n > 0) greedy_step(std::false_type{});
 #if OAS_PROFILE
-    if ((tid == 0 || tid == 40 || tid == T - 1) && rank == 5)
-        printf("rank %u tid %u steps %u: slots %lld hole+argmin+send %lld wait %lld fold %lld pull+mail %lld sync %lld tail %lld\n", rank, tid, step,
-               tsum[0] / step, tsum[1] / step, tsum[2] / step, tsum[3] / step, tsum[4] / step, tsum[5] / step, tsum[6] / step);
+    if (lane == 0 && rank == 5)
+        printf("warp %u steps %u: slots done %lld, record sent %lld, table complete %lld, folded %lld, pull/mail issued %lld, (barrier passed: next step) , tail %lld\n",
+               warp, step, tsum[0] / step, tsum[1] / step, tsum[2] / step, tsum[3] / step, tsum[4] / step, tsum[6] / step);
 #endif
     cluster.sync();  // nobody leaves while its shared memory can still be addressed
 }
