@@ -534,7 +534,12 @@ def test_order_cluster_path(n, d, monkeypatch):
     x = oracle.generate_lhd(n, d, 5)
     for metric, minimize in ((METRIC_MAXPRO, True), (METRIC_MAXIMIN, False), (METRIC_MAXIMIN, True), (METRIC_MAXPRO, False)):
         _, p_ref = oracle.order_design(x, metric, minimize, incremental=True)
+        monkeypatch.setenv("MAXPRO_ORDER_CLUSTER_CTAS", "8")
         _, p = engine.order_design(x, metric, minimize)
+        monkeypatch.setenv("MAXPRO_ORDER_CLUSTER_CTAS", "16")  # the non-portable cluster size large pools take
+        _, p16 = engine.order_design(x, metric, minimize)
+        monkeypatch.delenv("MAXPRO_ORDER_CLUSTER_CTAS")
+        assert p16.tolist() == p.tolist(), "16-CTA cluster against 8"
         monkeypatch.setenv("MAXPRO_ORDER_CLUSTER_SYNC", "1")
         _, p2 = engine.order_design(x, metric, minimize)
         monkeypatch.delenv("MAXPRO_ORDER_CLUSTER_SYNC")
