@@ -25,6 +25,16 @@
 
 #include <cstdlib>
 
+#ifndef AMX_PROFILE
+#define AMX_PROFILE 0  // 1: clock64 sums per phase of the step, printed by thread 0 of CTA 0 (make EXTRA=-DAMX_PROFILE=1)
+#endif
+#if AMX_PROFILE
+#include <cstdio>
+#define AMX_T(i) { const long long now_ = clock64(); tsum[i] += now_ - tprev; tprev = now_; }
+#else
+#define AMX_T(i)
+#endif
+
 namespace mp {
 
 constexpr int kMaxDirty = 6;  // dirty rows re-scored per pass
@@ -166,6 +176,10 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
         double* best_out = p.best_design + chain * (unsigned long long)nd;
         __syncthreads();
 
+#if AMX_PROFILE
+        long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#endif
         for (unsigned long long t = 0; t < p.iters; ++t) {
             const unsigned int slot = (unsigned int)t & (kDrawBatch - 1);
             if (slot == 0) {
@@ -192,6 +206,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
             // [3 + q] the dirty rows of the current chunk.  Who attains a minimum is written afterwards
             // by every warp whose partial equals it -- the decision needs the values only.
             constexpr unsigned long long kInfBits = 0x7FF0000000000000ull;
+            AMX_T(0)
             double fin_all = CUDART_INF, g1 = CUDART_INF, g2 = CUDART_INF, d12 = CUDART_INF;
             if (moved) {
                 // ---- stage the two rows as they are AFTER the exchange, list the dirty rows
@@ -209,6 +224,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                 }
                 if (threadIdx.x < 3 + kMaxDirty) lmin[threadIdx.x] = kInfBits;
                 __syncthreads();
+                AMX_T(1)
                 const int nd_rows = dirty_n[0];
                 if (warp == 0) {
                     // the pair (r1, r2) itself: its squares summed in the reference's order
@@ -243,6 +259,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                         case 5: maximin_row_pass<5>(cur, rowsx, n, d, ns, r1, r2, first, rm, ra, rm_new, ra_new, di, all, m1, m2, dm); break;
                         default: maximin_row_pass<6>(cur, rowsx, n, d, ns, r1, r2, first, rm, ra, rm_new, ra_new, di, all, m1, m2, dm); break;
                     }
+                    AMX_T(2)
                     // ---- warp minima, then the block minima by atomicMin
                     if (first) {
                         all = warp_minarg(all); m1 = warp_minarg(m1); m2 = warp_minarg(m2);
@@ -259,7 +276,9 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                             if (lane == 0) atomicMin(&lmin[3 + q], (unsigned long long)__double_as_longlong(dm[q].v));
                         }
                     }
+                    AMX_T(3)
                     __syncthreads();
+                    AMX_T(4)
                     // the dirty rows of this chunk: value and a neighbour that attains it
 #pragma unroll
                     for (int q = 0; q < kMaxDirty; ++q) {
@@ -281,6 +300,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                 }
             }
 
+            AMX_T(5)
             // ---- Metropolis (anneal.rs:110-128) and the global best (:131-136), warp 0 only
             if (warp == 0) {
                 double raw_new = raw_cur;
@@ -321,7 +341,9 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                 if (lane == 0) { dec->accept = (accept && moved) ? 1 : 0; dec->best_mode = best_mode; }
                 temp *= p.cooling;  // anneal.rs:139
             }
+            AMX_T(6)
             __syncthreads();
+            AMX_T(7)
             if (dec->accept) sel ^= 1;  // the tentative row minima become the committed ones
             const int best_mode = dec->best_mode;
             if (best_mode == 1) {
@@ -342,6 +364,12 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
             p.best_metric[chain] = global_best;
             p.improved[chain] = materialized ? 1u : 0u;
         }
+#if AMX_PROFILE
+        if ((threadIdx.x == 0 || threadIdx.x == 200) && chain == 0)
+            printf("tid %d, %llu steps, cycles per step: draws+decode %lld, stage+dirty list+barrier %lld, row pass %lld, warp minima+atomics %lld, barrier %lld, dirty rows+r1/r2 %lld, metropolis %lld, barrier %lld\n",
+                   (int)threadIdx.x, p.iters, tsum[0] / (long long)p.iters, tsum[1] / (long long)p.iters, tsum[2] / (long long)p.iters, tsum[3] / (long long)p.iters,
+                   tsum[4] / (long long)p.iters, tsum[5] / (long long)p.iters, tsum[6] / (long long)p.iters, tsum[7] / (long long)p.iters);
+#endif
     }
 }
 
