@@ -42,7 +42,11 @@ constexpr int kMaxDirty = 6;  // dirty rows re-scored per pass
 struct MinArg {
     double v;
     int a;
-    __device__ __forceinline__ void take(double w, int b) { if (w < v) { v = w; a = b; } }
+    // strict "<" on the bit patterns: squared distances are >= +0, so the integer order is the numeric order, and
+    // the compare runs on the integer pipes instead of a DSETP on the FP64 pipe (8 of these per row of the pass)
+    __device__ __forceinline__ void take(double w, int b) {
+        if ((unsigned long long)__double_as_longlong(w) < (unsigned long long)__double_as_longlong(v)) { v = w; a = b; }
+    }
 };
 
 // Warp minimum of (squared distance, row), smaller row on equal distances.  A squared distance is >= +0, so its

