@@ -29,6 +29,16 @@
 #include <cstdlib>
 #include <type_traits>
 
+#ifndef ANN_PROFILE
+#define ANN_PROFILE 0  // 1: clock64 sums per phase of a jitter step, printed by thread 0 of chain 0 (make EXTRA=-DANN_PROFILE=1)
+#endif
+#if ANN_PROFILE
+#include <cstdio>
+#define ANN_T(i) { const long long now_ = clock64(); tsum[i] += now_ - tprev; tprev = now_; }
+#else
+#define ANN_T(i)
+#endif
+
 namespace mp {
 
 template <bool MAXPRO, int PLACE, bool SWAP>
@@ -86,6 +96,10 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
         double* best_out = p.best_design + chain * (unsigned long long)nd;
         unsigned long long until_resync = p.resync;  // iterations until the next full re-sum of S
 
+#if ANN_PROFILE
+        long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#endif
         for (unsigned long long t = 0; t < p.iters; ++t) {
             // ---- propose and score: every thread ends up with its share `mine` of the reduction
             double mine, u = 0.0;
@@ -139,17 +153,18 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 for (int blk = threadIdx.x; blk * 4 < nd; blk += blockDim.x) {
                     Philox4 w = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)blk, kDomainJit, key0, key1);
                     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                    int i = (blk * 4) / d, k = blk * 4 - i * d;  // one division per block; the elements walk on from there
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         int e = blk * 4 + q;
                         if (e < nd) {
-                            int i = e / d, k = e - i * d;
                             double uu = (double)ws[q] * 0x1p-32;
                             double delta = __dsub_rn(__dmul_rn(uu, two_step), p.step);
                             double v = __dadd_rn(cur[k * ns + i], delta);
                             jok &= (v == v) ? 1 : 0;  // clamp passes NaN through
                             v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);  // clamp(0.0, 1.0)
                             cand[k * ns + i] = v;
+                            if (++k == d) { k = 0; ++i; }
                         }
                     }
                 }
@@ -157,12 +172,18 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                     Philox4 wa = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0u, kDomainJacc, key0, key1);
                     u = (double)wa.x * 0x1p-32;
                 }
+                ANN_T(0)
                 // every coordinate of the proposal has just been clamped into [0, 1]
                 const bool cand_in_cube = __syncthreads_and(jok) != 0;
-                publish_partial<MAXPRO>(n >= kTileScoreMinN ? full_score_tiles<MAXPRO>(cand, n, d, ns, cand_in_cube)
-                                                            : full_score_partial<MAXPRO>(cand, n, d, ns, cand_in_cube), part);
+                ANN_T(1)
+                const double sc = n >= kTileScoreMinN ? full_score_tiles<MAXPRO>(cand, n, d, ns, cand_in_cube)
+                                                      : full_score_partial<MAXPRO>(cand, n, d, ns, cand_in_cube);
+                ANN_T(2)
+                publish_partial<MAXPRO>(sc, part);
             }
+            ANN_T(3)
             __syncthreads();  // partials are in; nobody reads cur / cand for scoring any more
+            ANN_T(4)
 
             // ---- Metropolis (anneal.rs:110-128) and the global best (:131-136), warp 0 only
             if (warp == 0) {
@@ -198,7 +219,9 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 if (lane == 0) { dec->accept = accept ? 1 : 0; dec->best_mode = best_mode; }
                 temp *= p.cooling;  // anneal.rs:139
             }
+            ANN_T(5)
             __syncthreads();
+            ANN_T(6)
             const int accept = dec->accept, best_mode = dec->best_mode;
             if (accept && !SWAP) {
                 for (int e = threadIdx.x; e < dns; e += blockDim.x) cur[e] = cand[e];
@@ -218,11 +241,18 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                     best_out[e] = cur[k * ns + i];
                 }
             }
+            ANN_T(7)
         }
         if (threadIdx.x == 0) {
             p.best_metric[chain] = global_best;
             p.improved[chain] = materialized ? 1u : 0u;
         }
+#if ANN_PROFILE
+        if (!SWAP && (threadIdx.x == 0 || threadIdx.x == 40) && chain == 0)
+            printf("tid %d, %llu jitter steps, cycles per step: propose %lld, barrier %lld, score %lld, warp sum+publish %lld, barrier %lld, metropolis %lld, barrier %lld, rest (copy, best) %lld\n",
+                   (int)threadIdx.x, p.iters, tsum[0] / (long long)p.iters, tsum[1] / (long long)p.iters, tsum[2] / (long long)p.iters, tsum[3] / (long long)p.iters,
+                   tsum[4] / (long long)p.iters, tsum[5] / (long long)p.iters, tsum[6] / (long long)p.iters, tsum[7] / (long long)p.iters);
+#endif
     }
 }
 
@@ -336,8 +366,14 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
         // incremental steps: one thread per two partner rows
         threads = round_up_32((L.n + 1) / 2);
     } else {
-        // full re-score every iteration: one thread per row
+        // full re-score every iteration.  Designs on broadcast tiles (n >= kTileScoreMinN): one thread per row.
+        // Smaller ones: one thread per work item (row, kShiftBlock shifts) of full_score_partial -- a chain of a
+        // 50 x 2 design on 64 threads spent 3,000 of its 7,250 cycles per step walking four items per thread.
         threads = round_up_32(L.n);
+        if ((int)L.n < kTileScoreMinN) {
+            const unsigned long long smax = (L.n - 1) / 2 + ((L.n & 1) == 0 ? 1 : 0);
+            threads = round_up_32(L.n * ((smax + kShiftBlock - 1) / kShiftBlock));
+        }
     }
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;

@@ -61,9 +61,15 @@ __device__ __forceinline__ double full_score_partial(const double* xs, int n, in
     const int half = (n - 1) / 2;
     const bool even = (n & 1) == 0;
     const int smax = half + (even ? 1 : 0);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // Work items (row i, SB consecutive shifts from s0), dealt row-major to the threads: consecutive threads take
+    // consecutive rows of the same shift block, and a block of more than n threads works on several shift blocks
+    // at once (a 50-row design has 200 items: one per thread instead of four per row-thread in sequence).
+    const int nitems = (smax + SB - 1) / SB;
+    for (int w = threadIdx.x; w < n * nitems; w += blockDim.x) {
+        const int it = w / n, i = w - it * n;
         const int my_smax = half + ((even && i < n / 2) ? 1 : 0);
-        for (int s0 = 1; s0 <= smax; s0 += SB) {
+        {
+            const int s0 = 1 + it * SB;
             int jj[SB];
 #pragma unroll
             for (int c = 0; c < SB; ++c) {
@@ -156,7 +162,15 @@ constexpr int kTileScoreMinN = MAXPRO_TILE_SCORE_MIN_N;
 
 template <bool MAXPRO>
 __device__ __forceinline__ double metric_from_raw(double raw, int n, double n_pairs, double inv_d) {
-    if (MAXPRO) return n < 2 ? 0.0 : pow(raw / n_pairs, inv_d);  // maxpro_utils.rs:75-82
+    if (MAXPRO) {  // maxpro_utils.rs:75-82
+        if (n < 2) return 0.0;
+        const double m = raw / n_pairs;
+        // pow costs ~800 cycles of dependent latency on the one warp that decides (tools/micro/lat.cu).  x^1 is x;
+        // x^0.5 is sqrt(x), the correctly rounded value of what powf(0.5) approximates.  d = 2 is the CLI's own case.
+        if (inv_d == 1.0) return m;
+        if (inv_d == 0.5) return sqrt(m);
+        return pow(m, inv_d);
+    }
     return sqrt(raw);                                              // maximin_utils.rs:44
 }
 
