@@ -150,28 +150,45 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
                 // anneal.rs:102-107) takes word e%4 of block e/4
                 const double two_step = __dadd_rn(p.step, p.step);
                 int jok = 1;
-                for (int blk = threadIdx.x; blk * 4 < nd; blk += blockDim.x) {
-                    Philox4 w = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)blk, kDomainJit, key0, key1);
-                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-                    int i = (blk * 4) / d, k = blk * 4 - i * d;  // one division per block; the elements walk on from there
+                // the accept draw first: its Philox call overlaps the proposal's instead of following it
+                Philox4 wa{0u, 0u, 0u, 0u};
+                if (warp == 0) wa = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0u, kDomainJacc, key0, key1);
+                auto jitter_element = [&](uint32_t word, int i, int k) {
+                    const double uu = (double)word * 0x1p-32;
+                    const double delta = __dsub_rn(__dmul_rn(uu, two_step), p.step);
+                    double v = __dadd_rn(cur[k * ns + i], delta);
+                    jok &= (v == v) ? 1 : 0;  // clamp passes NaN through
+                    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);  // clamp(0.0, 1.0)
+                    cand[k * ns + i] = v;
+                };
+                if (nd <= (int)blockDim.x) {
+                    // A design with no more elements than the block has threads: one element per thread.  The (up
+                    // to) four threads that share a Philox block each repeat its call -- the lanes are idle
+                    // otherwise, and a thread's walk over four elements one after the other was most of the
+                    // proposal's latency on a single small chain (the CLI's case).
+                    const int e = threadIdx.x;
+                    if (e < nd) {
+                        const Philox4 w = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)(e >> 2), kDomainJit, key0, key1);
+                        const int q = e & 3;
+                        const uint32_t word = q == 0 ? w.x : (q == 1 ? w.y : (q == 2 ? w.z : w.w));
+                        const int i = e / d;
+                        jitter_element(word, i, e - i * d);
+                    }
+                } else {
+                    for (int blk = threadIdx.x; blk * 4 < nd; blk += blockDim.x) {
+                        const Philox4 w = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)blk, kDomainJit, key0, key1);
+                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                        int i = (blk * 4) / d, k = blk * 4 - i * d;  // one division per block; the elements walk on from there
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int e = blk * 4 + q;
-                        if (e < nd) {
-                            double uu = (double)ws[q] * 0x1p-32;
-                            double delta = __dsub_rn(__dmul_rn(uu, two_step), p.step);
-                            double v = __dadd_rn(cur[k * ns + i], delta);
-                            jok &= (v == v) ? 1 : 0;  // clamp passes NaN through
-                            v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);  // clamp(0.0, 1.0)
-                            cand[k * ns + i] = v;
-                            if (++k == d) { k = 0; ++i; }
+                        for (int q = 0; q < 4; ++q) {
+                            if (blk * 4 + q < nd) {
+                                jitter_element(ws[q], i, k);
+                                if (++k == d) { k = 0; ++i; }
+                            }
                         }
                     }
                 }
-                if (warp == 0) {
-                    Philox4 wa = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0u, kDomainJacc, key0, key1);
-                    u = (double)wa.x * 0x1p-32;
-                }
+                if (warp == 0) u = (double)wa.x * 0x1p-32;
                 ANN_T(0)
                 // every coordinate of the proposal has just been clamped into [0, 1]
                 const bool cand_in_cube = __syncthreads_and(jok) != 0;
