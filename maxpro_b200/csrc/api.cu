@@ -47,7 +47,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // Device scratch with a small per-thread cache: the host-facing calls are made in tight
 // loops (bench.py's e2e leg, the CLI pipeline) and cudaMalloc/cudaFree take driver-wide
-// locks, so blocks up to 64 MB are kept for the next call on the same thread and device.
+// locks, so blocks up to 1 GB (4 GB in total; a B200 has 180) are kept for the next call on the same thread and
+// device -- the per-chain best designs of a 1,184-chain anneal at n=1000, d=20 are 189 MB, and a cudaMalloc /
+// cudaFree pair of that size was seen to take 0.2-0.7 s now and then (profiles/r1l_configs.jsonl).
 // Every call synchronises its stream before returning, so a cached block is never in use.
 struct CachedBlock { void* p; size_t bytes; int device; };
 struct BlockCache {
@@ -56,7 +58,7 @@ struct BlockCache {
     ~BlockCache() { for (auto& b : free_blocks) cudaFree(b.p); }
 };
 thread_local BlockCache g_cache;
-constexpr size_t kCacheBlockMax = 64ull << 20, kCacheTotalMax = 512ull << 20;
+constexpr size_t kCacheBlockMax = 1ull << 30, kCacheTotalMax = 4ull << 30;
 
 struct DevBuf {
     void* p = nullptr;
