@@ -64,6 +64,11 @@ MAXPRO_API int maxpro_set_device(int device);
 MAXPRO_API int maxpro_get_device(int *device);
 /* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
 MAXPRO_API uint64_t maxpro_kernel_launch_count(void);
+/* The library keeps the device blocks of finished calls for the next call of the same host thread (blocks up to
+ * 1 GB, 4 GB in total per thread; every call synchronises before it returns, so a kept block is never in use).
+ * This returns them to the driver; *bytes (may be NULL) receives how much was released.  The reference has no
+ * counterpart: its Vec<Vec<f64>> temporaries go back to the allocator when a call returns. */
+MAXPRO_API int maxpro_release_device_cache(uint64_t *bytes);
 
 /* ---- reference public functions (host buffers) ------------------------ */
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "maxpro_search_range", "maxpro_reduce_best", "maxpro_anneal_lhd", "maxpro_order_design",
     "maxpro_search_workspace_bytes", "maxpro_search_range_device",
     "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe",
+    "maxpro_release_device_cache",
 ]
 
 
@@ -59,6 +60,7 @@ def lib() -> C.CDLL:
         "maxpro_set_device": (i32, [i32]),
         "maxpro_get_device": (i32, [C.POINTER(i32)]),
         "maxpro_kernel_launch_count": (u64, []),
+        "maxpro_release_device_cache": (i32, [u64p]),
         "maxpro_generate_lhd": (i32, [u64, u64, u64, dp]),
         "maxpro_generate_batch": (i32, [u64, u64, u64, u64, u64, dp]),
         "maxpro_criterion": (i32, [dp, u64, u64, dp]),
@@ -110,3 +112,10 @@ def set_device(device: int) -> None:
 
 def kernel_launch_count() -> int:
     return int(lib().maxpro_kernel_launch_count())
+
+
+def release_device_cache() -> int:
+    """Give the device blocks the library kept from finished calls of this thread back to the driver; returns the bytes."""
+    b = C.c_uint64(0)
+    check(lib().maxpro_release_device_cache(C.byref(b)))
+    return int(b.value)

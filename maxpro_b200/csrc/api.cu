@@ -404,6 +404,15 @@ const char* maxpro_last_error(void) { return g_err.c_str(); }
 const char* maxpro_version(void) { return "maxpro_b200 0.1.0 (sm_100a; LHD-Philox v1)"; }
 uint64_t maxpro_kernel_launch_count(void) { return mp::g_launches.load(std::memory_order_relaxed); }
 
+int maxpro_release_device_cache(uint64_t* bytes) {
+    uint64_t released = 0;
+    for (auto& b : g_cache.free_blocks) { released += b.bytes; cudaFree(b.p); }
+    g_cache.free_blocks.clear();
+    g_cache.cached_bytes = 0;
+    if (bytes) *bytes = released;
+    return MAXPRO_OK;
+}
+
 int maxpro_device_count(int* count) {
     if (!count) return fail(MAXPRO_ERR_INVALID, "null pointer");
     int c = 0;

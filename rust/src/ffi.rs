@@ -9,6 +9,7 @@ pub const METRIC_MAXIMIN: c_int = 1;
 
 unsafe extern "C" {
     pub fn maxpro_last_error() -> *const c_char;
+    pub fn maxpro_release_device_cache(bytes: *mut u64) -> c_int;
     pub fn maxpro_generate_lhd(n: u64, d: u64, seed: u64, out: *mut f64) -> c_int;
     pub fn maxpro_criterion(design: *const f64, n: u64, d: u64, out: *mut f64) -> c_int;
     pub fn maxpro_maximin_criterion(design: *const f64, n: u64, d: u64, out: *mut f64) -> c_int;

@@ -574,6 +574,19 @@ def test_order_structured_ties(r_golden):
         assert p.tolist() == p_ref.tolist()
 
 
+def test_release_device_cache_between_calls():
+    """Blocks of finished calls are kept for the next call; releasing them must leave the library usable."""
+    from maxpro_b200 import _lib
+    x = oracle.generate_lhd(300, 6, 3)
+    a = engine.maxpro_criterion(x)
+    _, p0 = engine.order_design(x, METRIC_MAXPRO, True)
+    assert _lib.release_device_cache() > 0
+    assert _lib.release_device_cache() == 0
+    assert engine.maxpro_criterion(x) == a
+    _, p1 = engine.order_design(x, METRIC_MAXPRO, True)
+    assert p0.tolist() == p1.tolist()
+
+
 def test_order_c5_shape_runs():
     x = oracle.generate_lhd(5000, 8, 42)
     got, p = engine.order_design(x, METRIC_MAXPRO, True)
