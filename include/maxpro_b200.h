@@ -17,7 +17,8 @@
  *   - No C++ exception crosses the boundary.  There is NO CPU fallback: without
  *     a CUDA device every compute entry point returns MAXPRO_ERR_NO_DEVICE.
  *   - Re-entrant and thread-safe; each call uses the calling thread's current
- *     engine device (maxpro_set_device, default 0).
+ *     engine device (maxpro_set_device, default 0), or -- build_lhd, search_range and
+ *     anneal_lhd -- every device the thread selected with maxpro_set_devices.
  *   - metric: MAXPRO_METRIC_MAXPRO minimises, MAXPRO_METRIC_MAXIMIN maximises
  *     (src/lib.rs:54-63, src/main.rs:65-68).
  */
@@ -62,13 +63,32 @@ MAXPRO_API const char *maxpro_version(void);
 MAXPRO_API int maxpro_device_count(int *count);
 MAXPRO_API int maxpro_set_device(int device);
 MAXPRO_API int maxpro_get_device(int *device);
+/* The reference's build_lhd spreads its candidates over every core of the machine through rayon
+ * (src/lib.rs:65-98; src/main.rs:71 gets that for free).  The counterpart here: the devices that the
+ * host-facing maxpro_build_lhd[_ex], maxpro_search_range and maxpro_anneal_lhd calls of this thread spread
+ * their candidates / chains over.  Device g takes the g-th contiguous block of GLOBAL candidate (chain) indices,
+ * so the result is the same for any device list; the per-device winners are folded on the host with the
+ * reference's tie rule (maxpro_reduce_best).  count == 0 selects every device of the box.  The first device
+ * of the list also serves the calls that do not shard (criteria, ordering, winner regeneration).
+ * maxpro_set_device(d) is maxpro_set_devices(&d, 1). */
+MAXPRO_API int maxpro_set_devices(const int *devices, int count);
+/* *count = devices selected; the first min(capacity, *count) go to devices[] (may be NULL). */
+MAXPRO_API int maxpro_get_devices(int *devices, int capacity, int *count);
 /* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
 MAXPRO_API uint64_t maxpro_kernel_launch_count(void);
-/* The library keeps the device blocks of finished calls for the next call of the same host thread (blocks up to
- * 1 GB, 4 GB in total per thread; every call synchronises before it returns, so a kept block is never in use).
- * This returns them to the driver; *bytes (may be NULL) receives how much was released.  The reference has no
- * counterpart: its Vec<Vec<f64>> temporaries go back to the allocator when a call returns. */
+/* The library keeps the device blocks of finished calls for the next call of the same host thread: at most
+ * 256 MB per thread by default, no block above a quarter of the limit, and only blocks whose stream has nothing
+ * pending, so a kept block is never in use.  maxpro_release_device_cache returns them to the driver; *bytes (may
+ * be NULL) receives how much was released.  maxpro_set_device_cache_limit changes the per-thread limit for the
+ * whole process (0 = keep nothing).  The reference has no counterpart: its Vec<Vec<f64>> temporaries go back to
+ * the allocator when a call returns. */
 MAXPRO_API int maxpro_release_device_cache(uint64_t *bytes);
+MAXPRO_API int maxpro_set_device_cache_limit(uint64_t bytes);
+/* Device scratch one maxpro_anneal_lhd call allocates on the current device.  The chains' best designs are folded
+ * per CTA on the device, so this grows with the number of RESIDENT chains, not with n_chains (47 MB for 65,536
+ * chains of a 1000 x 20 design). */
+MAXPRO_API int maxpro_anneal_scratch_bytes(uint64_t n, uint64_t d, int metric, int swap,
+                                           uint64_t n_chains, size_t *bytes);
 
 /* ---- reference public functions (host buffers) ------------------------ */
 
@@ -171,6 +191,18 @@ MAXPRO_API int maxpro_score_batch_device(const double *d_designs, uint64_t b, ui
  * kernel (the roofline denominator; MEASURED_PEAKS.json has no FP64 figure).
  * tflops = 2 * DFMA/s / 1e12 (best of `repeats`). */
 MAXPRO_API int maxpro_fp64_peak_probe(int repeats, double *tflops, double *kernel_ms);
+
+/* ---- test and tooling entry points (not part of the reference's surface) ---- */
+
+/* Forces a kernel path or a launch shape (DESIGN.md section 6a lists the switches); value == NULL clears it.
+ * Which kernel serves a call never changes its result -- the parity tests use this to run every kernel on shapes
+ * another one normally takes.  MAXPRO_* environment variables are read once, at the first look-up of the process,
+ * as initial values; nothing on the call path reads the environment. */
+MAXPRO_API int maxpro_debug_set(const char *name, const char *value);
+
+/* out[i] = the device's pow(x[i], y[i]) as the kernels evaluate (S / pairs)^(1/d): the arithmetic of glibc's pow
+ * (maxpro_b200/csrc/pow_glibc.cuh), so that criteria tie exactly where the reference's do. */
+MAXPRO_API int maxpro_debug_pow(const double *x, const double *y, uint64_t count, double *out);
 
 #ifdef __cplusplus
 }

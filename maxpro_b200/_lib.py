@@ -27,7 +27,8 @@ EXPORTS = [
     "maxpro_search_range", "maxpro_reduce_best", "maxpro_anneal_lhd", "maxpro_order_design",
     "maxpro_search_workspace_bytes", "maxpro_search_range_device",
     "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe",
-    "maxpro_release_device_cache",
+    "maxpro_release_device_cache", "maxpro_set_device_cache_limit", "maxpro_set_devices", "maxpro_get_devices",
+    "maxpro_anneal_scratch_bytes", "maxpro_debug_set", "maxpro_debug_pow",
 ]
 
 
@@ -61,6 +62,12 @@ def lib() -> C.CDLL:
         "maxpro_get_device": (i32, [C.POINTER(i32)]),
         "maxpro_kernel_launch_count": (u64, []),
         "maxpro_release_device_cache": (i32, [u64p]),
+        "maxpro_set_device_cache_limit": (i32, [u64]),
+        "maxpro_set_devices": (i32, [C.POINTER(i32), i32]),
+        "maxpro_get_devices": (i32, [C.POINTER(i32), i32, C.POINTER(i32)]),
+        "maxpro_anneal_scratch_bytes": (i32, [u64, u64, i32, i32, u64, szp]),
+        "maxpro_debug_set": (i32, [C.c_char_p, C.c_char_p]),
+        "maxpro_debug_pow": (i32, [dp, dp, u64, dp]),
         "maxpro_generate_lhd": (i32, [u64, u64, u64, dp]),
         "maxpro_generate_batch": (i32, [u64, u64, u64, u64, u64, dp]),
         "maxpro_criterion": (i32, [dp, u64, u64, dp]),
@@ -108,6 +115,43 @@ def device_count() -> int:
 
 def set_device(device: int) -> None:
     check(lib().maxpro_set_device(device))
+
+
+def set_devices(devices=None) -> None:
+    """Devices the build_lhd / search_range / anneal_lhd calls of this thread spread over (None or [] = all)."""
+    devs = list(devices or [])
+    arr = (C.c_int * max(len(devs), 1))(*devs)
+    check(lib().maxpro_set_devices(arr, len(devs)))
+
+
+def get_devices() -> list:
+    n = C.c_int(0)
+    arr = (C.c_int * 64)()
+    check(lib().maxpro_get_devices(arr, 64, C.byref(n)))
+    return [arr[i] for i in range(min(n.value, 64))]
+
+
+def debug_set(name: str, value) -> None:
+    """Test / tooling switch; value None clears it."""
+    check(lib().maxpro_debug_set(name.encode(), None if value is None else str(value).encode()))
+
+
+def debug_pow(x, y) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(x)
+    check(lib().maxpro_debug_pow(dptr(x), dptr(y), x.size, dptr(out)))
+    return out
+
+
+def anneal_scratch_bytes(n: int, d: int, metric: int, swap: bool, n_chains: int) -> int:
+    b = C.c_size_t(0)
+    check(lib().maxpro_anneal_scratch_bytes(n, d, metric, 1 if swap else 0, n_chains, C.byref(b)))
+    return int(b.value)
+
+
+def set_device_cache_limit(nbytes: int) -> None:
+    check(lib().maxpro_set_device_cache_limit(nbytes))
 
 
 def kernel_launch_count() -> int:

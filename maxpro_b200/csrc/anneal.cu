@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
     ushort4* mlog = reinterpret_cast<ushort4*>(rows + d);            // kLogCap accepted moves {r1, r2, c}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    __shared__ CtaBest cta_best;  // per-CTA fold of the chains' global bests (anneal.cuh)
+    if (threadIdx.x == 0) cta_best_reset(&cta_best, p);
     for (unsigned long long chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
         const unsigned long long stream = p.seed + chain;
         const uint32_t key0 = (uint32_t)stream, key1 = (uint32_t)(stream >> 32);
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
             cur_metric = metric_from_raw<MAXPRO>(raw_cur, n, p.n_pairs, p.inv_d);       // :90
             global_best = cur_metric;                                                   // :94
         }
-        double* best_out = p.best_design + chain * (unsigned long long)nd;
+        double* best_out = cta_best_slot(p, &cta_best, nd);
         unsigned long long until_resync = p.resync;  // iterations until the next full re-sum of S
 
 #if ANN_PROFILE
@@ -260,10 +262,7 @@ __global__ void __launch_bounds__(512) anneal_kernel(AnnealParams p) {
             }
             ANN_T(7)
         }
-        if (threadIdx.x == 0) {
-            p.best_metric[chain] = global_best;
-            p.improved[chain] = materialized ? 1u : 0u;
-        }
+        if (threadIdx.x == 0) cta_best_commit(&cta_best, p, chain, global_best, materialized);
 #if ANN_PROFILE
         if (!SWAP && (threadIdx.x == 0 || threadIdx.x == 40) && chain == 0)
             printf("tid %d, %llu jitter steps, cycles per step: propose %lld, barrier %lld, score %lld, warp sum+publish %lld, barrier %lld, metropolis %lld, barrier %lld, rest (copy, best) %lld\n",
@@ -360,10 +359,11 @@ bool anneal_supported(unsigned long long n, unsigned long long d, int swap) {
 
 static int round_up_32(unsigned long long v) { return (int)((v + 31) / 32 * 32); }
 
-cudaError_t launch_anneal(const AnnealLaunch& L) {
-    if (cudaError_t e0 = launch_anneal_raw0(L); e0 != cudaSuccess) return e0;
-    if (anneal_pipe_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_pipe(L);
-    if (anneal_maximin_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_maximin(L);
+static cudaError_t launch_anneal_impl(const AnnealLaunch& L, int plan_sms, unsigned int* plan_grid) {
+    if (!plan_grid)
+        if (cudaError_t e0 = launch_anneal_raw0(L); e0 != cudaSuccess) return e0;
+    if (anneal_pipe_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_pipe(L, plan_sms, plan_grid);
+    if (anneal_maximin_supported(L.n, L.d, L.metric, L.swap)) return launch_anneal_maximin(L, plan_sms, plan_grid);
     AnnealParams p;
     p.design = L.design; p.n = L.n; p.d = L.d; p.iters = L.iters; p.seed = L.seed; p.n_chains = L.n_chains;
     p.t0 = L.t0; p.cooling = L.cooling; p.step = 0.01 / (double)L.n;  // anneal.rs:86-87
@@ -373,9 +373,10 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
+    p.cta_chain = L.cta_chain; p.cta_buf = L.cta_buf;
     p.rowmin0 = nullptr; p.rowarg0 = nullptr;
     const int place = anneal_place(L.n, L.d, L.swap);
-    if (place != 0 && !L.cur_scratch) return cudaErrorInvalidValue;
+    if (!plan_grid && place != 0 && !L.cur_scratch) return cudaErrorInvalidValue;
     p.cur_global = place != 0 ? L.cur_scratch : nullptr;
     size_t smem = anneal_smem_bytes(L.n, L.d, L.swap);
     int threads;
@@ -394,13 +395,15 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
     }
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
-    if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
-    unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
-    if (place != 0 && grid > kHbmGrid) grid = kHbmGrid;  // one scratch buffer per CTA; the chains are grid-strided
+    if (const char* e = cfg("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
+    const unsigned long long cap = place != 0 ? kHbmGrid : (1ull << 20);  // HBM placements: one scratch buffer per CTA
     cudaError_t e = cudaSuccess;
     auto go = [&](auto kernel) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) kernel<<<(unsigned int)grid, threads, smem, L.stream>>>(p);
+        if (e != cudaSuccess) return;
+        if (plan_grid) { e = anneal_resident_grid(kernel, threads, smem, plan_sms, L.n_chains, cap, plan_grid); return; }
+        if (L.grid == 0 || L.grid > L.n_chains || L.grid > cap) { e = cudaErrorInvalidValue; return; }
+        kernel<<<L.grid, threads, smem, L.stream>>>(p);
     };
     auto pick = [&](auto mp_tag) {
         constexpr bool MP = decltype(mp_tag)::value;
@@ -410,9 +413,13 @@ cudaError_t launch_anneal(const AnnealLaunch& L) {
         else go(anneal_kernel<MP, 0, false>);
     };
     if (L.metric == 0) pick(std::true_type{}); else pick(std::false_type{});
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || plan_grid) return e;
     count_launch();
     return cudaGetLastError();
 }
+
+cudaError_t launch_anneal(const AnnealLaunch& L) { return launch_anneal_impl(L, 0, nullptr); }
+
+cudaError_t anneal_plan_grid(const AnnealLaunch& L, int sms, unsigned int* grid) { return launch_anneal_impl(L, sms, grid); }
 
 }  // namespace mp

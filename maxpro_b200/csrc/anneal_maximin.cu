@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
     unsigned short* rarg0 = reinterpret_cast<unsigned short*>(mlog + kLogCap);  // [2][ns] their arguments
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    __shared__ CtaBest cta_best;  // per-CTA fold of the chains' global bests (anneal.cuh)
+    if (threadIdx.x == 0) cta_best_reset(&cta_best, p);
     for (unsigned long long chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
         const unsigned long long stream = p.seed + chain;
         const uint32_t key0 = (uint32_t)stream, key1 = (uint32_t)(stream >> 32);
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
             cur_metric = sqrt(raw_cur);                                                 // :90
             global_best = cur_metric;                                                   // :94
         }
-        double* best_out = p.best_design + chain * (unsigned long long)nd;
+        double* best_out = cta_best_slot(p, &cta_best, nd);
         __syncthreads();
 
 #if AMX_PROFILE
@@ -364,10 +366,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                 }
             }
         }
-        if (threadIdx.x == 0) {
-            p.best_metric[chain] = global_best;
-            p.improved[chain] = materialized ? 1u : 0u;
-        }
+        if (threadIdx.x == 0) cta_best_commit(&cta_best, p, chain, global_best, materialized);
 #if AMX_PROFILE
         if ((threadIdx.x == 0 || threadIdx.x == 200) && chain == 0)
             printf("tid %d, %llu steps, cycles per step: draws+decode %lld, stage+dirty list+barrier %lld, row pass %lld, warp minima+atomics %lld, barrier %lld, dirty rows+r1/r2 %lld, metropolis %lld, barrier %lld\n",
@@ -409,15 +408,17 @@ size_t anneal_maximin_smem_bytes(unsigned long long n, unsigned long long d) {
 }
 
 bool anneal_maximin_supported(unsigned long long n, unsigned long long d, int metric, int swap) {
-    if (const char* e = getenv("MAXPRO_NO_ANNEAL_MAXIMIN_INC")) if (atoi(e) != 0) return false;
+    if (const char* e = cfg("MAXPRO_NO_ANNEAL_MAXIMIN_INC")) if (atoi(e) != 0) return false;
     return metric == 1 && swap != 0 && n >= 2 && n <= 65535 && d >= 1 && d <= 65535 && anneal_maximin_smem_bytes(n, d) <= kSmemBudget;
 }
 
-cudaError_t launch_anneal_maximin(const AnnealLaunch& L) {
+cudaError_t launch_anneal_maximin(const AnnealLaunch& L, int plan_sms, unsigned int* plan_grid) {
     const int n = (int)L.n, d = (int)L.d;
-    anneal_rowmin0_kernel<<<(n + 7) / 8, 256, 0, L.stream>>>(L.design, n, d, L.rowmin0, L.rowarg0);
-    count_launch();
-    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+    if (!plan_grid) {
+        anneal_rowmin0_kernel<<<(n + 7) / 8, 256, 0, L.stream>>>(L.design, n, d, L.rowmin0, L.rowarg0);
+        count_launch();
+        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+    }
     AnnealParams p{};
     p.design = L.design; p.n = L.n; p.d = L.d; p.iters = L.iters; p.seed = L.seed; p.n_chains = L.n_chains;
     p.t0 = L.t0; p.cooling = L.cooling; p.step = 0.0;
@@ -425,15 +426,17 @@ cudaError_t launch_anneal_maximin(const AnnealLaunch& L) {
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
+    p.cta_chain = L.cta_chain; p.cta_buf = L.cta_buf;
     p.rowmin0 = L.rowmin0; p.rowarg0 = L.rowarg0;
     const size_t smem = anneal_maximin_smem_bytes(L.n, L.d);
     int threads = (int)((L.n + 31) / 32 * 32);
     if (threads > 512) threads = 512;
-    if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
-    const unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
+    if (const char* e = cfg("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     cudaError_t e = cudaFuncSetAttribute(anneal_maximin_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    anneal_maximin_swap_kernel<<<(unsigned int)grid, threads, smem, L.stream>>>(p);
+    if (plan_grid) return anneal_resident_grid(anneal_maximin_swap_kernel, threads, smem, plan_sms, L.n_chains, 1ull << 20, plan_grid);
+    if (L.grid == 0 || L.grid > L.n_chains) return cudaErrorInvalidValue;
+    anneal_maximin_swap_kernel<<<L.grid, threads, smem, L.stream>>>(p);
     count_launch();
     return cudaGetLastError();
 }

@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(PPT == 2 ? 320 : 480) anneal_swap_pipe_kernel(
     const int nwarps = blockDim.x >> 5, wwarps = nwarps - 2, workers = wwarps * 32;
     const bool worker = warp < wwarps, decider = warp == wwarps, specialist = warp == wwarps + 1;
 
+    __shared__ CtaBest cta_best;  // per-CTA fold of the chains' global bests (anneal.cuh)
+    if (threadIdx.x == 0) cta_best_reset(&cta_best, p);
     for (unsigned long long chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
         const unsigned long long stream = p.seed + chain;
         const uint32_t key0 = (uint32_t)stream, key1 = (uint32_t)(stream >> 32);
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(PPT == 2 ? 320 : 480) anneal_swap_pipe_kernel(
             cur_metric = metric_from_raw<true>(raw_cur, n, p.n_pairs, p.inv_d);         // :90
             global_best = cur_metric;                                                   // :94
         }
-        double* best_out = p.best_design + chain * (unsigned long long)nd;
+        double* best_out = cta_best_slot(p, &cta_best, nd);
         unsigned long long until_resync = p.resync;
         bool have_bulk = false, use_fix = false;
 
@@ -392,10 +394,7 @@ __global__ void __launch_bounds__(PPT == 2 ? 320 : 480) anneal_swap_pipe_kernel(
             have_bulk = next_ok;
             use_fix = next_ok && !m.noop;
         }
-        if (decider && lane == 0) {
-            p.best_metric[chain] = global_best;
-            p.improved[chain] = materialized ? 1u : 0u;
-        }
+        if (decider && lane == 0) cta_best_commit(&cta_best, p, chain, global_best, materialized);
     }
 }
 
@@ -407,11 +406,11 @@ size_t pipe_smem_bytes(unsigned long long n, unsigned long long d) {
 }  // namespace
 
 bool anneal_pipe_supported(unsigned long long n, unsigned long long d, int metric, int swap) {
-    if (const char* e = getenv("MAXPRO_NO_ANNEAL_PIPE")) if (atoi(e) != 0) return false;
+    if (const char* e = cfg("MAXPRO_NO_ANNEAL_PIPE")) if (atoi(e) != 0) return false;
     return metric == 0 && swap && n >= 4 && n <= 65535 && d >= 1 && d <= 65535 && pipe_smem_bytes(n, d) <= kSmemBudget;
 }
 
-cudaError_t launch_anneal_pipe(const AnnealLaunch& L) {
+cudaError_t launch_anneal_pipe(const AnnealLaunch& L, int plan_sms, unsigned int* plan_grid) {
     AnnealParams p;
     p.design = L.design; p.n = L.n; p.d = L.d; p.iters = L.iters; p.seed = L.seed; p.n_chains = L.n_chains;
     p.t0 = L.t0; p.cooling = L.cooling; p.step = 0.01 / (double)L.n;
@@ -421,6 +420,7 @@ cudaError_t launch_anneal_pipe(const AnnealLaunch& L) {
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.best_design = L.best_design; p.best_metric = L.best_metric; p.improved = L.improved; p.raw0 = L.raw0;
+    p.cta_chain = L.cta_chain; p.cta_buf = L.cta_buf;
     const size_t smem = pipe_smem_bytes(L.n, L.d);
     // worker warps: one thread per PPT pairs of partner rows; plus the decider and the specialist warp
     const int ppt = L.n >= 768 ? 2 : 1;
@@ -428,19 +428,18 @@ cudaError_t launch_anneal_pipe(const AnnealLaunch& L) {
     int wwarps = (int)((slots + 31) / 32);
     const int cap = ppt == 2 ? 8 : 13;
     if (wwarps > cap) wwarps = cap;
-    if (const char* e = getenv("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e) / 32; if (v >= 1 && v <= cap) wwarps = v; }
+    if (const char* e = cfg("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e) / 32; if (v >= 1 && v <= cap) wwarps = v; }
     const int threads = (wwarps + 2) * 32;
-    unsigned long long grid = L.n_chains < (1ull << 20) ? L.n_chains : (1ull << 20);
-    cudaError_t e;
-    if (ppt == 2) {
-        e = cudaFuncSetAttribute(anneal_swap_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        anneal_swap_pipe_kernel<2><<<(unsigned int)grid, threads, smem, L.stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(anneal_swap_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        anneal_swap_pipe_kernel<1><<<(unsigned int)grid, threads, smem, L.stream>>>(p);
-    }
+    cudaError_t e = cudaSuccess;
+    auto go = [&](auto kernel) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return;
+        if (plan_grid) { e = anneal_resident_grid(kernel, threads, smem, plan_sms, L.n_chains, 1ull << 20, plan_grid); return; }
+        if (L.grid == 0 || L.grid > L.n_chains) { e = cudaErrorInvalidValue; return; }
+        kernel<<<L.grid, threads, smem, L.stream>>>(p);
+    };
+    if (ppt == 2) go(anneal_swap_pipe_kernel<2>); else go(anneal_swap_pipe_kernel<1>);
+    if (e != cudaSuccess || plan_grid) return e;
     count_launch();
     return cudaGetLastError();
 }

@@ -11,10 +11,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "pow_glibc.cuh"
 
 namespace mp {
 static std::atomic<unsigned long long> g_launches{0};
@@ -27,6 +29,8 @@ using mp::BestRec;
 
 thread_local std::string g_err;
 thread_local int g_device = 0;
+// devices a host-facing call of this thread spreads its candidates / chains over (maxpro_set_devices); empty = g_device alone
+thread_local std::vector<int> g_devices;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -47,18 +51,25 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // Device scratch with a small per-thread cache: the host-facing calls are made in tight
 // loops (bench.py's e2e leg, the CLI pipeline) and cudaMalloc/cudaFree take driver-wide
-// locks, so blocks up to 1 GB (4 GB in total; a B200 has 180) are kept for the next call on the same thread and
-// device -- the per-chain best designs of a 1,184-chain anneal at n=1000, d=20 are 189 MB, and a cudaMalloc /
-// cudaFree pair of that size was seen to take 0.2-0.7 s now and then (profiles/r1l_configs.jsonl).
-// Every call synchronises its stream before returning, so a cached block is never in use.
+// locks, so the blocks of a finished call are kept for the next call on the same thread and
+// device: at most g_cache_limit bytes per thread (256 MB by default, maxpro_set_device_cache_limit),
+// no block above a quarter of that.  The largest working set of any call is the annealer's
+// 2 x resident-CTAs designs (47 MB at n=1000, d=20).  A block is kept only if the thread's stream
+// has nothing pending (a call that returns early on an error may leave work behind: its blocks are
+// freed, which synchronises), so a cached block is never in use.
 struct CachedBlock { void* p; size_t bytes; int device; };
 struct BlockCache {
     std::vector<CachedBlock> free_blocks;
     size_t cached_bytes = 0;
-    ~BlockCache() { for (auto& b : free_blocks) cudaFree(b.p); }
+    void drop_all() {
+        for (auto& b : free_blocks) cudaFree(b.p);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+    ~BlockCache() { drop_all(); }
 };
 thread_local BlockCache g_cache;
-constexpr size_t kCacheBlockMax = 1ull << 30, kCacheTotalMax = 4ull << 30;
+std::atomic<unsigned long long> g_cache_limit{256ull << 20};
 
 struct DevBuf {
     void* p = nullptr;
@@ -66,10 +77,12 @@ struct DevBuf {
     int device = 0;
     ~DevBuf() {
         if (!p) return;
-        if (bytes <= kCacheBlockMax && g_cache.cached_bytes + bytes <= kCacheTotalMax) {
+        const size_t limit = (size_t)g_cache_limit.load(std::memory_order_relaxed);
+        if (bytes <= limit / 4 && g_cache.cached_bytes + bytes <= limit && cudaStreamQuery(cudaStreamPerThread) == cudaSuccess) {
             g_cache.free_blocks.push_back({p, bytes, device});
             g_cache.cached_bytes += bytes;
         } else {
+            cudaGetLastError();  // cudaErrorNotReady of the query is not an error of the call
             cudaFree(p);
         }
     }
@@ -89,6 +102,12 @@ struct DevBuf {
         }
         bytes = want;
         cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaErrorMemoryAllocation && !fb.empty()) {
+            // the blocks this thread kept may be what is missing: give them back and try once more
+            cudaGetLastError();
+            g_cache.drop_all();
+            e = cudaMalloc(&p, want);
+        }
         if (e != cudaSuccess) { p = nullptr; bytes = 0; }
         return e;
     }
@@ -144,6 +163,12 @@ __global__ void fold_result_kernel(BestRec* total, const BestRec* chunk, unsigne
 
 __global__ void init_counter_kernel(unsigned int* c) { *c = 0u; }
 
+// maxpro_debug_pow: the device build of pow_glibc.cuh, element-wise (tests compare it with libm bit for bit)
+__global__ void debug_pow_kernel(const double* x, const double* y, unsigned long long count, double* out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = mp::pow_glibc(x[i], y[i]);
+}
+
 // ---- search dispatch -----------------------------------------------------------
 
 constexpr size_t kMaxBlockRecs = 4096;
@@ -159,10 +184,10 @@ unsigned long long generic_chunk(unsigned long long n, unsigned long long d) {
 
 // which fused kernel a shape takes (MAXPRO_NO_CTA=1 forces the chunked path; used by the tests)
 bool use_warp_kernel(unsigned long long n, unsigned long long d) {
-    return !mp::search_small_supported(n, d) && mp::search_warp_supported(n, d) && !getenv("MAXPRO_NO_CTA");
+    return !mp::search_small_supported(n, d) && mp::search_warp_supported(n, d) && !mp::cfg("MAXPRO_NO_CTA");
 }
 bool use_cta_kernel(unsigned long long n, unsigned long long d) {
-    return !mp::search_small_supported(n, d) && !use_warp_kernel(n, d) && mp::search_cta_supported(n, d) && !getenv("MAXPRO_NO_CTA");
+    return !mp::search_small_supported(n, d) && !use_warp_kernel(n, d) && mp::search_cta_supported(n, d) && !mp::cfg("MAXPRO_NO_CTA");
 }
 
 struct SearchWs {
@@ -363,7 +388,7 @@ int score_batch_device_impl(const double* d_designs, uint64_t b, uint64_t n, uin
     mp::count_launch();
     int cyc_cands = 0;
     if (mp::search_cyclic_supported(n, d, &cyc_cands) && (reinterpret_cast<uintptr_t>(d_designs) & 15u) == 0 &&
-        !getenv("MAXPRO_NO_FAST_SCORE")) {
+        !mp::cfg("MAXPRO_NO_FAST_SCORE")) {
         // headline shapes: the thread-group kernel of the fused search, fed from HBM instead of Philox
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
@@ -387,6 +412,164 @@ int score_batch_device_impl(const double* d_designs, uint64_t b, uint64_t n, uin
     return MAXPRO_OK;
 }
 
+// ---- spreading a host-facing call over the devices of maxpro_set_devices --------------------------
+// The reference's build_lhd uses the whole machine through rayon (src/lib.rs:65-98); here the whole machine is
+// the selected GPUs.  Candidates and chains are independent units keyed by GLOBAL index, so device g takes the
+// g-th contiguous block and the result does not depend on the device count.  One host thread per device (each
+// with its own stream and scratch); the per-device winners are 16-byte records folded on the host with the
+// reference's tie rule -- no data-path collective, no NCCL inside the library (shard.py keeps the NCCL
+// all-gather for the one-process-per-GPU launch under torchrun).
+std::vector<int> call_devices() {
+    if (g_devices.empty()) return std::vector<int>{g_device};
+    return g_devices;
+}
+
+template <class F>
+int run_on_devices(const std::vector<int>& devs, F&& shard) {  // shard(i, device) -> status; runs with g_device = device
+    if (devs.size() == 1) {
+        const int saved = g_device;
+        g_device = devs[0];
+        const int rc = shard(0, devs[0]);
+        g_device = saved;
+        return rc;
+    }
+    std::vector<int> rcs(devs.size(), MAXPRO_OK);
+    std::vector<std::string> errs(devs.size());
+    std::vector<std::thread> workers;
+    workers.reserve(devs.size());
+    for (size_t i = 0; i < devs.size(); ++i)
+        workers.emplace_back([&, i]() {
+            g_device = devs[i];
+            g_devices.clear();
+            rcs[i] = shard((int)i, devs[i]);
+            if (rcs[i] != MAXPRO_OK) errs[i] = g_err;
+        });
+    for (auto& w : workers) w.join();
+    for (size_t i = 0; i < devs.size(); ++i)
+        if (rcs[i] != MAXPRO_OK) return fail(rcs[i], "device " + std::to_string(devs[i]) + ": " + errs[i]);
+    return MAXPRO_OK;
+}
+
+// one device: candidates lo..hi-1, winner record to the host
+int search_range_one(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t flags,
+                     double* best_score, uint64_t* best_index) {
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    size_t ws_bytes = 0;
+    if (int rc = maxpro_search_workspace_bytes(n, d, &ws_bytes)) return rc;
+    DevBuf dr, dw;
+    CUDA_TRY(dr.alloc(sizeof(BestRec)));
+    CUDA_TRY(dw.alloc(ws_bytes));
+    cudaStream_t st = cudaStreamPerThread;
+    if (int rc = search_range_device_impl(n, d, metric, seed, lo, hi, flags, dr.p, dw.p, ws_bytes, st, sms)) return rc;
+    BestRec rec;
+    CUDA_TRY(cudaMemcpyAsync(&rec, dr.p, sizeof(rec), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *best_score = rec.score;
+    *best_index = rec.index;
+    return MAXPRO_OK;
+}
+
+// all selected devices: index blocks, host fold (src/lib.rs:76-98)
+int search_range_sharded(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t flags,
+                         double* best_score, uint64_t* best_index) {
+    std::vector<int> devs = call_devices();
+    const uint64_t total = hi - lo;
+    if (devs.size() > total) devs.resize(total ? (size_t)total : 1);
+    const uint64_t G = devs.size();
+    std::vector<double> scores(G);
+    std::vector<uint64_t> indices(G);
+    const int rc = run_on_devices(devs, [&](int g, int) {
+        // total * g / G without overflow: whole blocks plus the remainder spread over the first shards
+        const uint64_t q = total / G, r = total % G;
+        const uint64_t a = lo + q * (uint64_t)g + ((uint64_t)g < r ? (uint64_t)g : r);
+        const uint64_t b = a + q + ((uint64_t)g < r ? 1 : 0);
+        return search_range_one(n, d, metric, seed, a, b, flags, &scores[g], &indices[g]);
+    });
+    if (rc) return rc;
+    return maxpro_reduce_best(metric, scores.data(), indices.data(), G, best_score, best_index);
+}
+
+struct AnnealScratch {
+    size_t design, raw, best, metrics, improved, cta_chain, cta_buf, jitter;
+    size_t total() const { return design + raw + best + metrics + improved + cta_chain + cta_buf + jitter; }
+};
+
+// device scratch of one anneal call on the current device (the grid comes from the occupancy of the kernel that serves it)
+int anneal_scratch(uint64_t n, uint64_t d, int metric, int swap, uint64_t n_chains, int sms, unsigned int* grid, AnnealScratch* sc) {
+    mp::AnnealLaunch L{};
+    L.n = n; L.d = d; L.metric = metric; L.swap = swap ? 1 : 0; L.n_chains = n_chains;
+    CUDA_TRY(mp::anneal_plan_grid(L, sms, grid));
+    const size_t nd = n * d;
+    sc->design = nd * sizeof(double);
+    sc->raw = (2 * n + 2) * sizeof(double);  // raw0, then the nearest-neighbour table: n doubles, n 16-bit indices
+    sc->best = (size_t)*grid * 2 * nd * sizeof(double);
+    sc->metrics = n_chains * sizeof(double);
+    sc->improved = n_chains * sizeof(unsigned int);
+    sc->cta_chain = (size_t)*grid * sizeof(unsigned long long);
+    sc->cta_buf = (size_t)*grid * sizeof(int);
+    sc->jitter = mp::anneal_jitter_scratch_bytes(n, d, swap ? 1 : 0, n_chains);
+    return MAXPRO_OK;
+}
+
+// one device: chains 0..n_chains-1 of the stream family `seed` (chain c draws from seed + c)
+int anneal_one(const double* design, uint64_t n, uint64_t d, uint64_t n_iterations, double initial_temp, double cooling_rate,
+               int metric, int minimize, uint64_t seed, int swap, uint64_t n_chains, double* out_design, double* out_metric,
+               uint64_t* out_chain) {
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    const size_t nd = n * d;
+    unsigned int grid = 0;
+    AnnealScratch sc{};
+    if (int rc = anneal_scratch(n, d, metric, swap, n_chains, sms, &grid, &sc)) return rc;
+    DevBuf dx, db, dm, di, dr, dcur, dcc, dcb;
+    if (sc.jitter) CUDA_TRY(dcur.alloc(sc.jitter));
+    CUDA_TRY(dx.alloc(sc.design));
+    CUDA_TRY(dr.alloc(sc.raw));
+    CUDA_TRY(db.alloc(sc.best));  // per-CTA fold of the chains' bests: 2 designs per resident CTA, not one per chain
+    CUDA_TRY(dm.alloc(sc.metrics));
+    CUDA_TRY(di.alloc(sc.improved));
+    CUDA_TRY(dcc.alloc(sc.cta_chain));
+    CUDA_TRY(dcb.alloc(sc.cta_buf));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(cudaMemcpyAsync(dx.p, design, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    mp::AnnealLaunch L{};
+    L.design = dx.as<double>(); L.n = n; L.d = d; L.iters = n_iterations; L.seed = seed; L.n_chains = n_chains;
+    L.t0 = initial_temp; L.cooling = cooling_rate; L.metric = metric; L.minimize = minimize ? 1 : 0; L.swap = swap ? 1 : 0;
+    L.grid = grid; L.best_design = db.as<double>(); L.cta_chain = dcc.as<unsigned long long>(); L.cta_buf = dcb.as<int>();
+    L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.raw0 = dr.as<double>(); L.stream = st;
+    L.rowmin0 = dr.as<double>() + 1; L.rowarg0 = reinterpret_cast<unsigned short*>(dr.as<double>() + 1 + n);
+    L.cur_scratch = dcur.as<double>();
+    CUDA_TRY(mp::launch_anneal(L));
+    std::vector<double> metrics(n_chains);
+    std::vector<unsigned int> improved(n_chains);
+    CUDA_TRY(cudaMemcpyAsync(metrics.data(), dm.p, n_chains * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(improved.data(), di.p, n_chains * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // best chain: strictly better metric wins, the lowest chain index on ties
+    uint64_t best = 0;
+    for (uint64_t c = 1; c < n_chains; ++c)
+        if (minimize ? (metrics[c] < metrics[best]) : (metrics[c] > metrics[best])) best = c;
+    if (improved[best]) {
+        // chain c ran on CTA c mod grid, which kept it: a chain of that CTA with an equal metric and a lower index
+        // would have been picked above instead
+        const uint64_t cta = best % grid;
+        unsigned long long kept = mp::kNoIndex;
+        int buf = 0;
+        CUDA_TRY(cudaMemcpyAsync(&kept, dcc.as<unsigned long long>() + cta, sizeof(kept), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&buf, dcb.as<int>() + cta, sizeof(buf), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (kept != best || (buf != 0 && buf != 1)) return fail(MAXPRO_ERR_CUDA, "annealer: the best chain's design was not kept by its CTA");
+        CUDA_TRY(cudaMemcpyAsync(out_design, db.as<double>() + (cta * 2 + (uint64_t)buf) * nd, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        std::memcpy(out_design, design, nd * sizeof(double));  // never improved: the input is the global best (anneal.rs:93)
+    }
+    if (out_metric) *out_metric = metrics[best];
+    if (out_chain) *out_chain = best;
+    return MAXPRO_OK;
+}
+
 int criterion_host(const double* design, uint64_t n, uint64_t d, int metric, double* out) {
     if (!design || !out) return fail(MAXPRO_ERR_INVALID, "null pointer");
     if (n == 0) return fail(MAXPRO_ERR_INVALID, "Cannot pass an empty design");  // maxpro_utils.rs:74, maximin_utils.rs:56
@@ -405,11 +588,21 @@ const char* maxpro_version(void) { return "maxpro_b200 0.1.0 (sm_100a; LHD-Philo
 uint64_t maxpro_kernel_launch_count(void) { return mp::g_launches.load(std::memory_order_relaxed); }
 
 int maxpro_release_device_cache(uint64_t* bytes) {
-    uint64_t released = 0;
-    for (auto& b : g_cache.free_blocks) { released += b.bytes; cudaFree(b.p); }
-    g_cache.free_blocks.clear();
-    g_cache.cached_bytes = 0;
+    const uint64_t released = g_cache.cached_bytes;
+    g_cache.drop_all();
     if (bytes) *bytes = released;
+    return MAXPRO_OK;
+}
+
+int maxpro_set_device_cache_limit(uint64_t bytes) {
+    g_cache_limit.store(bytes, std::memory_order_relaxed);
+    if (g_cache.cached_bytes > bytes) g_cache.drop_all();
+    return MAXPRO_OK;
+}
+
+int maxpro_debug_set(const char* name, const char* value) {
+    if (!name || strncmp(name, "MAXPRO_", 7) != 0) return fail(MAXPRO_ERR_INVALID, "switch names start with MAXPRO_");
+    mp::cfg_set(name, value);
     return MAXPRO_OK;
 }
 
@@ -425,6 +618,36 @@ int maxpro_device_count(int* count) {
 int maxpro_set_device(int device) {
     if (device < 0) return fail(MAXPRO_ERR_INVALID, "device index out of range");
     g_device = device;
+    g_devices.clear();
+    return MAXPRO_OK;
+}
+
+int maxpro_set_devices(const int* devices, int count) {
+    if (count < 0 || (count > 0 && !devices)) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    int available = 0;
+    cudaError_t e = cudaGetDeviceCount(&available);
+    if (e != cudaSuccess) { cudaGetLastError(); available = 0; }
+    std::vector<int> devs;
+    if (count == 0) {  // every device of the box
+        for (int i = 0; i < available; ++i) devs.push_back(i);
+        if (devs.empty()) return fail(MAXPRO_ERR_NO_DEVICE, "no CUDA device available; maxpro_b200 has no CPU path");
+    }
+    for (int i = 0; i < count; ++i) {
+        if (devices[i] < 0 || devices[i] >= available) return fail(MAXPRO_ERR_INVALID, "device index out of range");
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) return fail(MAXPRO_ERR_INVALID, "device listed twice");
+        devs.push_back(devices[i]);
+    }
+    g_device = devs[0];
+    g_devices = devs;
+    return MAXPRO_OK;
+}
+
+int maxpro_get_devices(int* devices, int capacity, int* count) {
+    if (!count) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    const std::vector<int> devs = call_devices();
+    *count = (int)devs.size();
+    for (int i = 0; devices && i < capacity && i < (int)devs.size(); ++i) devices[i] = devs[i];
     return MAXPRO_OK;
 }
 
@@ -519,20 +742,12 @@ int maxpro_search_range(uint64_t n, uint64_t d, int metric, uint64_t seed, uint6
     if (n == 0) return fail(MAXPRO_ERR_INVALID, "n_samples must be positive and nonzero");
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");
     if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
-    int sms = 0;
-    if (int rc = ensure_device(&sms)) return rc;
-    size_t ws_bytes = 0;
-    if (int rc = maxpro_search_workspace_bytes(n, d, &ws_bytes)) return rc;
-    DevBuf dr, dw;
-    CUDA_TRY(dr.alloc(sizeof(BestRec)));
-    CUDA_TRY(dw.alloc(ws_bytes));
-    cudaStream_t st = cudaStreamPerThread;
-    if (int rc = search_range_device_impl(n, d, metric, seed, lo, hi, 0, dr.p, dw.p, ws_bytes, st, sms)) return rc;
-    BestRec rec;
-    CUDA_TRY(cudaMemcpyAsync(&rec, dr.p, sizeof(rec), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (best_score) *best_score = rec.score;
-    if (best_index) *best_index = rec.index;
+    if (hi < lo) return fail(MAXPRO_ERR_INVALID, "search range is inverted");
+    double s = 0.0;
+    uint64_t i = 0;
+    if (int rc = search_range_sharded(n, d, metric, seed, lo, hi, MAXPRO_FLAG_DEFAULT, &s, &i)) return rc;
+    if (best_score) *best_score = s;
+    if (best_index) *best_index = i;
     return MAXPRO_OK;
 }
 
@@ -565,21 +780,14 @@ int maxpro_build_lhd_ex(uint64_t n, uint64_t d, uint64_t n_iterations, int metri
         if (out_index) *out_index = 0;
         return maxpro_generate_lhd(n, d, seed, out_design);
     }
-    int sms = 0;
-    if (int rc = ensure_device(&sms)) return rc;
-    size_t ws_bytes = 0;
-    if (int rc = maxpro_search_workspace_bytes(n, d, &ws_bytes)) return rc;
-    DevBuf dr, dw, dx;
-    CUDA_TRY(dr.alloc(sizeof(BestRec)));
-    CUDA_TRY(dw.alloc(ws_bytes));
+    BestRec rec;
+    if (int rc = search_range_sharded(n, d, metric, seed, 0, n_iterations, flags, &rec.score, reinterpret_cast<uint64_t*>(&rec.index))) return rc;
+    if (rec.index == mp::kNoIndex) return fail(MAXPRO_ERR_CUDA, "search produced no winner (all scores NaN?)");
+    // only (score, index) left the chips: rebuild the winner from its index (lib.rs:70)
+    if (int rc = ensure_device()) return rc;
+    DevBuf dx;
     CUDA_TRY(dx.alloc(n * d * sizeof(double)));
     cudaStream_t st = cudaStreamPerThread;
-    if (int rc = search_range_device_impl(n, d, metric, seed, 0, n_iterations, flags, dr.p, dw.p, ws_bytes, st, sms)) return rc;
-    BestRec rec;
-    CUDA_TRY(cudaMemcpyAsync(&rec, dr.p, sizeof(rec), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (rec.index == mp::kNoIndex) return fail(MAXPRO_ERR_CUDA, "search produced no winner (all scores NaN?)");
-    // only (score, index) left the chip: rebuild the winner from its index (lib.rs:70)
     CUDA_TRY(mp::launch_generate(n, d, seed, rec.index, 1, dx.as<double>(), st));
     CUDA_TRY(cudaMemcpyAsync(out_design, dx.p, n * d * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -603,43 +811,34 @@ int maxpro_anneal_lhd(const double* design, uint64_t n, uint64_t d, uint64_t n_i
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "Must have finite, positive number of dimensions");
     if (n_chains == 0) return fail(MAXPRO_ERR_INVALID, "n_chains must be positive and nonzero");
     if (!design || !out_design) return fail(MAXPRO_ERR_INVALID, "null pointer");
-    if (int rc = ensure_device()) return rc;
     if (!mp::anneal_supported(n, d, swap))
         return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the annealer (at most 65535 points and ~14000 dimensions)");
-    const size_t nd = n * d;
-    DevBuf dx, db, dm, di, dr, dcur;
-    if (const size_t sb = mp::anneal_jitter_scratch_bytes(n, d, swap ? 1 : 0, n_chains)) CUDA_TRY(dcur.alloc(sb));
-    CUDA_TRY(dx.alloc(nd * sizeof(double)));
-    CUDA_TRY(dr.alloc((2 * n + 2) * sizeof(double)));  // raw0, then the nearest-neighbour table: n doubles, n 16-bit indices
-    CUDA_TRY(db.alloc(n_chains * nd * sizeof(double)));
-    CUDA_TRY(dm.alloc(n_chains * sizeof(double)));
-    CUDA_TRY(di.alloc(n_chains * sizeof(unsigned int)));
-    cudaStream_t st = cudaStreamPerThread;
-    CUDA_TRY(cudaMemcpyAsync(dx.p, design, nd * sizeof(double), cudaMemcpyHostToDevice, st));
-    mp::AnnealLaunch L{};
-    L.design = dx.as<double>(); L.n = n; L.d = d; L.iters = n_iterations; L.seed = seed; L.n_chains = n_chains;
-    L.t0 = initial_temp; L.cooling = cooling_rate; L.metric = metric; L.minimize = minimize ? 1 : 0; L.swap = swap ? 1 : 0;
-    L.best_design = db.as<double>(); L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.raw0 = dr.as<double>(); L.stream = st;
-    L.rowmin0 = dr.as<double>() + 1; L.rowarg0 = reinterpret_cast<unsigned short*>(dr.as<double>() + 1 + n);
-    L.cur_scratch = dcur.as<double>();
-    CUDA_TRY(mp::launch_anneal(L));
-    std::vector<double> metrics(n_chains);
-    std::vector<unsigned int> improved(n_chains);
-    CUDA_TRY(cudaMemcpyAsync(metrics.data(), dm.p, n_chains * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(improved.data(), di.p, n_chains * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    // best chain: strictly better metric wins, the lowest chain index on ties
-    uint64_t best = 0;
-    for (uint64_t c = 1; c < n_chains; ++c)
-        if (minimize ? (metrics[c] < metrics[best]) : (metrics[c] > metrics[best])) best = c;
-    if (improved[best]) {
-        CUDA_TRY(cudaMemcpyAsync(out_design, db.as<double>() + best * nd, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-    } else {
-        std::memcpy(out_design, design, nd * sizeof(double));  // never improved: the input is the global best (anneal.rs:93)
-    }
+    std::vector<int> devs = call_devices();
+    if (devs.size() > n_chains) devs.resize((size_t)n_chains);
+    if (devs.size() == 1)
+        return run_on_devices(devs, [&](int, int) {
+            return anneal_one(design, n, d, n_iterations, initial_temp, cooling_rate, metric, minimize, seed, swap, n_chains,
+                              out_design, out_metric, out_chain);
+        });
+    // chain blocks over the devices: chain c draws from stream seed + c wherever it runs
+    const uint64_t G = devs.size(), nd = n * d;
+    std::vector<std::vector<double>> designs(G, std::vector<double>(nd));
+    std::vector<double> metrics(G);
+    std::vector<uint64_t> chains(G), first(G);
+    const int rc = run_on_devices(devs, [&](int g, int) {
+        const uint64_t q = n_chains / G, r = n_chains % G;
+        const uint64_t c0 = q * (uint64_t)g + ((uint64_t)g < r ? (uint64_t)g : r), cnt = q + ((uint64_t)g < r ? 1 : 0);
+        first[g] = c0;
+        return anneal_one(design, n, d, n_iterations, initial_temp, cooling_rate, metric, minimize, seed + c0, swap, cnt,
+                          designs[g].data(), &metrics[g], &chains[g]);
+    });
+    if (rc) return rc;
+    uint64_t best = 0;  // strictly better wins: the lowest global chain index on ties (blocks are in chain order)
+    for (uint64_t g = 1; g < G; ++g)
+        if (minimize ? (metrics[g] < metrics[best]) : (metrics[g] > metrics[best])) best = g;
+    std::memcpy(out_design, designs[best].data(), nd * sizeof(double));
     if (out_metric) *out_metric = metrics[best];
-    if (out_chain) *out_chain = best;
+    if (out_chain) *out_chain = first[best] + chains[best];
     return MAXPRO_OK;
 }
 
@@ -660,8 +859,8 @@ int maxpro_order_design(const double* design, uint64_t n, uint64_t d, int metric
     mp::OrderLaunch L{};
     L.design = dx.as<double>(); L.n = n; L.d = d; L.metric = metric; L.minimize = minimize ? 1 : 0;
     L.perm = dp.as<unsigned long long>(); L.acc = da.as<double>(); L.pool = dpool.as<unsigned int>(); L.stream = st;
-    const bool no_cluster = getenv("MAXPRO_NO_ORDER_CLUSTER") != nullptr;
-    if (!no_cluster && mp::order_cluster_async_supported(n, d) && !getenv("MAXPRO_ORDER_CLUSTER_SYNC")) CUDA_TRY(mp::launch_order_cluster_async(L));
+    const bool no_cluster = mp::cfg("MAXPRO_NO_ORDER_CLUSTER") != nullptr;
+    if (!no_cluster && mp::order_cluster_async_supported(n, d) && !mp::cfg("MAXPRO_ORDER_CLUSTER_SYNC")) CUDA_TRY(mp::launch_order_cluster_async(L));
     else if (!no_cluster && mp::order_cluster_supported(n, d)) CUDA_TRY(mp::launch_order_cluster(L));
     else CUDA_TRY(mp::launch_order(L));
     std::vector<unsigned long long> hp(n);
@@ -743,6 +942,38 @@ int maxpro_fp64_peak_probe(int repeats, double* tflops, double* kernel_ms) {
     const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)grid;
     *tflops = flops / (best_ms * 1e-3) / 1e12;
     if (kernel_ms) *kernel_ms = best_ms;
+    return MAXPRO_OK;
+}
+
+int maxpro_anneal_scratch_bytes(uint64_t n, uint64_t d, int metric, int swap, uint64_t n_chains, size_t* bytes) {
+    if (!bytes) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (n == 0 || d == 0 || n_chains == 0 || !metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "n_samples, n_dim and n_chains must be positive and nonzero");
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    if (!mp::anneal_supported(n, d, swap)) return fail(MAXPRO_ERR_UNSUPPORTED, "design too large for the annealer (at most 65535 points and ~14000 dimensions)");
+    unsigned int grid = 0;
+    AnnealScratch sc{};
+    if (int rc = anneal_scratch(n, d, metric, swap, n_chains, sms, &grid, &sc)) return rc;
+    *bytes = sc.total();
+    return MAXPRO_OK;
+}
+
+int maxpro_debug_pow(const double* x, const double* y, uint64_t count, double* out) {
+    if (count == 0) return MAXPRO_OK;
+    if (!x || !y || !out) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (int rc = ensure_device()) return rc;
+    DevBuf dx, dy, dz;
+    CUDA_TRY(dx.alloc(count * sizeof(double)));
+    CUDA_TRY(dy.alloc(count * sizeof(double)));
+    CUDA_TRY(dz.alloc(count * sizeof(double)));
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(cudaMemcpyAsync(dx.p, x, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dy.p, y, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    debug_pow_kernel<<<(unsigned int)((count + 255) / 256 < 65535 ? (count + 255) / 256 : 65535), 256, 0, st>>>(dx.as<double>(), dy.as<double>(), count, dz.as<double>());
+    mp::count_launch();
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dz.p, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return MAXPRO_OK;
 }
 

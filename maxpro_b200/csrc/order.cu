@@ -18,6 +18,7 @@
 // a grid-wide barrier per step would cost more than the step.
 #include "common.cuh"
 #include "kernels.h"
+#include "order_psi.cuh"
 
 namespace mp {
 
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(512, 1) order_kernel(OrderParams p) {
     __shared__ double red_v[32];
     __shared__ unsigned int red_p[32];
     __shared__ unsigned int pick_s;
-    __shared__ double cur_min_s;
+    __shared__ double cur_min_s, best_v_s, s_prefix_s;
+    __shared__ unsigned int best_q_s;
     const unsigned int n = (unsigned int)p.n, d = (unsigned int)p.d;
     const unsigned int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
     double* last_s = reinterpret_cast<double*>(order_smem);                        // [d]
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(512, 1) order_kernel(OrderParams p) {
     // 16-byte loads need 16-byte aligned rows: even d and an aligned base
     const bool vec_ok = (d % 2 == 0) && ((reinterpret_cast<unsigned long long>(p.x) & 15ull) == 0);
 
-    auto block_argbest = [&](bool minimize_centre) {
+    // block-level argbest of the per-thread (bv, bp): the winning position lands in best_q_s, its value in best_v_s
+    auto block_reduce = [&](bool minimize_centre) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             double ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -101,9 +104,47 @@ __global__ void __launch_bounds__(512, 1) order_kernel(OrderParams p) {
                                             : cand_better<MINIMIZE>(red_v[w], red_p[w], v, q);
                 if (q == 0xFFFFFFFFu || take) { v = red_v[w]; q = red_p[w]; }
             }
+            best_v_s = v;
+            best_q_s = q;
+        }
+        __syncthreads();
+    };
+
+    auto block_argbest = [&](bool minimize_centre) {
+        block_reduce(minimize_centre);
+        if (MAXPRO && !minimize_centre) {
+            // The reference compares psi of prefix + candidate (order.rs:84-99), first position on equal psi.  Other
+            // pool points whose running value lies in the band where psi can coincide with the winner's?  Then
+            // the contenders are compared on psi itself (order_psi.cuh).
+            const double v = best_v_s, s_prefix = s_prefix_s;
+            const unsigned int q0 = best_q_s;
+            const double band = order_tie_band(s_prefix, v, d);
+            const double lim = MINIMIZE ? __dadd_rn(v, band) : __dsub_rn(v, band);
+            int contender = 0;
+            for (unsigned int pos = tid; pos < pool_n; pos += T) {
+                const double a = acc[pos];
+                contender |= (pos != q0 && (MINIMIZE ? a <= lim : a >= lim)) ? 1 : 0;
+            }
+            if (__syncthreads_or(contender)) {
+                const double n_pairs = order_pairs(m + 1), inv_d = 1.0 / (double)d;
+                bv = MINIMIZE ? CUDART_INF : -CUDART_INF;
+                bp = 0xFFFFFFFFu;
+                for (unsigned int pos = tid; pos < pool_n; pos += T) {
+                    const double a = acc[pos];
+                    if (MINIMIZE ? a <= lim : a >= lim) {
+                        const double psi = order_psi(s_prefix, a, n_pairs, inv_d);
+                        if (bp == 0xFFFFFFFFu || cand_better<MINIMIZE>(psi, pos, bv, bp)) { bv = psi; bp = pos; }
+                    }
+                }
+                block_reduce(false);
+            }
+        }
+        if (tid == 0) {
             // swap_remove(q): the last pool entry fills the hole (order.rs:63,101)
+            const unsigned int q = best_q_s;
             const unsigned int pick = pool[q];
             if (!MAXPRO && !minimize_centre) cur_min_s = fmin(cur_min_s, acc[q]);
+            if (MAXPRO && !minimize_centre) s_prefix_s = __dadd_rn(s_prefix_s, acc[q]);  // S of the ordered prefix, in pick order
             pool[q] = pool[pool_n - 1];
             acc[q] = acc[pool_n - 1];
             p.perm[m] = pick;
@@ -112,7 +153,7 @@ __global__ void __launch_bounds__(512, 1) order_kernel(OrderParams p) {
         __syncthreads();
     };
 
-    if (tid == 0) cur_min_s = CUDART_INF;
+    if (tid == 0) { cur_min_s = CUDART_INF; s_prefix_s = 0.0; }
     __syncthreads();
     block_argbest(true);
     --pool_n; ++m;

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "order_psi.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -65,6 +66,10 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
     unsigned int* cand_p = ids + slots;                               // [8]
     unsigned int* red_p = cand_p + kOrdCluster;                       // [NW]
     unsigned int* mail_id = red_p + NW;                               // [1]
+    unsigned int* cand_s = mail_id + 1;                               // [8]   second-best key (high word) of each CTA
+    unsigned int* red_s = cand_s + kOrdCluster;                       // [NW]
+    double* cand2_v = reinterpret_cast<double*>(ocl_smem + ((reinterpret_cast<unsigned char*>(red_s + NW) - ocl_smem + 7) / 8) * 8);  // [8]  psi round
+    unsigned int* cand2_p = reinterpret_cast<unsigned int*>(cand2_v + kOrdCluster);  // [8]
 
     // ---- load this CTA's slots: position p = slot*8 + rank holds point p at the start
     for (unsigned int s = tid; s < slots; s += T) {
@@ -80,31 +85,42 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
 
     unsigned int pool_n = n, m = 0;
     double cur_min = CUDART_INF;
+    double s_prefix = 0.0;  // MaxPro sum of the ordered prefix, in pick order (every thread keeps its copy)
 
-    // block-level argbest of (bv, bp) -> broadcast to every CTA's candidate table
-    auto publish_local_best = [&](double bv, unsigned int bp, bool centre) {
+    // block-level argbest of (bv, bp) -> broadcast to every CTA's candidate table (tv, tp).  s2 = high key word of
+    // the thread's second-best value (order_psi.cuh); the CTA's second-best goes to the table ts when it is given.
+    auto publish_local_best = [&](double bv, unsigned int bp, unsigned int s2, bool centre, double* tv, unsigned int* tp, unsigned int* ts) {
+        double bv0 = bv;
+        unsigned int bp0 = bp;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
             const unsigned int op = __shfl_xor_sync(0xffffffffu, bp, off);
             if (centre ? ocl_better<true>(ov, op, bv, bp) : ocl_better<MINIMIZE>(ov, op, bv, bp)) { bv = ov; bp = op; }
         }
-        if (lane == 0) { red_v[warp] = bv; red_p[warp] = bp; }
+        // a lane whose own best lost the warp's argbest offers it as a second-best
+        s2 = __reduce_min_sync(0xffffffffu, min(s2, (bp0 != 0xFFFFFFFFu && bp0 != bp) ? order_key_hi<MINIMIZE>(bv0) : kNoKeyHi));
+        if (lane == 0) { red_v[warp] = bv; red_p[warp] = bp; red_s[warp] = s2; }
         __syncthreads();
         if (warp == 0) {
             bv = lane < NW ? red_v[lane] : 0.0;
             bp = lane < NW ? red_p[lane] : 0xFFFFFFFFu;
+            s2 = lane < NW ? red_s[lane] : kNoKeyHi;
+            bv0 = bv; bp0 = bp;
 #pragma unroll
             for (int off = 4; off > 0; off >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
                 const unsigned int op = __shfl_xor_sync(0xffffffffu, bp, off);
                 if (centre ? ocl_better<true>(ov, op, bv, bp) : ocl_better<MINIMIZE>(ov, op, bv, bp)) { bv = ov; bp = op; }
             }
+            const unsigned int bpf = __shfl_sync(0xffffffffu, bp, 0);  // lanes 0..7 agree; the others never held a candidate
+            s2 = __reduce_min_sync(0xffffffffu, min(s2, (bp0 != 0xFFFFFFFFu && bp0 != bpf) ? order_key_hi<MINIMIZE>(bv0) : kNoKeyHi));
             if (lane < kOrdCluster) {  // lane r stores into CTA r
-                double* rv = cluster.map_shared_rank(cand_v, lane);
-                unsigned int* rp = cluster.map_shared_rank(cand_p, lane);
+                double* rv = cluster.map_shared_rank(tv, lane);
+                unsigned int* rp = cluster.map_shared_rank(tp, lane);
                 rv[rank] = bv;
                 rp[rank] = bp;
+                if (ts) cluster.map_shared_rank(ts, lane)[rank] = s2;
             }
         }
     };
@@ -118,6 +134,41 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
             if (centre ? ocl_better<true>(cand_v[r], cand_p[r], bv, q) : ocl_better<MINIMIZE>(cand_v[r], cand_p[r], bv, q)) {
                 bv = cand_v[r]; q = cand_p[r];
             }
+        if (MAXPRO && !centre) {
+            // The reference compares psi of prefix + candidate (order.rs:84-99), first position on equal psi.  Is there
+            // another pool point whose running value lies in the band where psi can coincide with the winner's?
+            // Every CTA reads the same table, so all of them take the branch together.
+            unsigned int second = kNoKeyHi;
+#pragma unroll
+            for (int r = 0; r < kOrdCluster; ++r) {
+                if (cand_p[r] == 0xFFFFFFFFu) continue;
+                second = min(second, cand_s[r]);
+                if (cand_p[r] != q) second = min(second, order_key_hi<MINIMIZE>(cand_v[r]));
+            }
+            const double band = order_tie_band(s_prefix, bv, d);
+            const double lim = MINIMIZE ? __dadd_rn(bv, band) : __dsub_rn(bv, band);
+            if (second <= order_key_hi<MINIMIZE>(lim)) {
+                const double n_pairs = order_pairs(m + 1), inv_d = 1.0 / (double)d;
+                double pv = MINIMIZE ? CUDART_INF : -CUDART_INF;
+                unsigned int pp = 0xFFFFFFFFu;
+                for (unsigned int s = tid; s < slots; s += T) {
+                    const unsigned int pos = s * kOrdCluster + rank;
+                    if (pos >= pool_n) break;
+                    const double a = acc[s];
+                    if (MINIMIZE ? a <= lim : a >= lim) {
+                        const double psi = order_psi(s_prefix, a, n_pairs, inv_d);
+                        if (ocl_better<MINIMIZE>(psi, pos, pv, pp)) { pv = psi; pp = pos; }
+                    }
+                }
+                publish_local_best(pv, pp, kNoKeyHi, false, cand2_v, cand2_p, nullptr);
+                cluster.sync();
+                q = cand2_p[0];
+                bv = cand2_v[0];
+#pragma unroll
+                for (int r = 1; r < kOrdCluster; ++r)
+                    if (ocl_better<MINIMIZE>(cand2_v[r], cand2_p[r], bv, q)) { bv = cand2_v[r]; q = cand2_p[r]; }
+            }
+        }
         const unsigned int L = pool_n - 1;
         const unsigned int q_owner = q % kOrdCluster, q_slot = q / kOrdCluster;
         const unsigned int l_owner = L % kOrdCluster, l_slot = L / kOrdCluster;
@@ -145,6 +196,7 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
             if (tid == 0) ids[q_slot] = mail_id[0];
         }
         if (!MAXPRO && !centre) cur_min = fmin(cur_min, last_s[d]);
+        if (MAXPRO && !centre) s_prefix = __dadd_rn(s_prefix, last_s[d]);
         __syncthreads();
         --pool_n; ++m;
     };
@@ -166,7 +218,7 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
             const double dist = sqrt(sq);
             if (ocl_better<true>(dist, pos, bv, bp)) { bv = dist; bp = pos; }
         }
-        publish_local_best(bv, bp, true);
+        publish_local_best(bv, bp, kNoKeyHi, true, cand_v, cand_p, cand_s);
         cluster.sync();
         settle(true);
     }
@@ -174,7 +226,7 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
     // ---- greedy steps
     while (pool_n > 0) {
         double bv = MINIMIZE ? CUDART_INF : -CUDART_INF;
-        unsigned int bp = 0xFFFFFFFFu;
+        unsigned int bp = 0xFFFFFFFFu, s2 = kNoKeyHi;
         for (unsigned int s = tid; s < slots; s += T) {
             const unsigned int pos = s * kOrdCluster + rank;
             if (pos >= pool_n) break;
@@ -199,9 +251,14 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
                 acc[s] = a;
                 v = fmin(a, cur_min);  // criterion of prefix + this point
             }
-            if (ocl_better<MINIMIZE>(v, pos, bv, bp)) { bv = v; bp = pos; }
+            if (ocl_better<MINIMIZE>(v, pos, bv, bp)) {
+                if (MAXPRO && bp != 0xFFFFFFFFu) s2 = min(s2, order_key_hi<MINIMIZE>(bv));
+                bv = v; bp = pos;
+            } else if (MAXPRO) {
+                s2 = min(s2, order_key_hi<MINIMIZE>(v));
+            }
         }
-        publish_local_best(bv, bp, false);
+        publish_local_best(bv, bp, s2, false, cand_v, cand_p, cand_s);
         cluster.sync();
         settle(false);
     }
@@ -210,7 +267,8 @@ __global__ void __cluster_dims__(kOrdCluster, 1, 1) __launch_bounds__(kOrdThread
 static size_t order_cluster_smem(unsigned long long n, unsigned long long d) {
     unsigned long long slots = (n + kOrdCluster - 1) / kOrdCluster;
     return (size_t)(slots * (d | 1ull) * 8 + slots * 8 + 2 * (d + 1) * 8 + kOrdCluster * 8 + (kOrdThreads / 32) * 8 +
-                    slots * 4 + kOrdCluster * 4 + (kOrdThreads / 32) * 4 + 16);
+                    slots * 4 + kOrdCluster * 4 + (kOrdThreads / 32) * 4 + 16 +
+                    kOrdCluster * 4 + (kOrdThreads / 32) * 4 + 8 + kOrdCluster * 12);  // second keys + the psi round's table
 }
 
 bool order_cluster_supported(unsigned long long n, unsigned long long d) {

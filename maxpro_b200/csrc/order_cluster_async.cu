@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "order_psi.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
 
     extern __shared__ __align__(16) unsigned char oas_smem[];
     CandRec* cand = reinterpret_cast<CandRec*>(oas_smem);                     // [2][NREC] candidate tables by step parity
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(cand + 2 * NREC);  // [4]  table mbarriers (2), hole mbarrier, pad
+    CandRec* cand_psi = cand + 2 * NREC;                                      // [NREC] table of the psi round (near-ties only)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(cand_psi + NREC);  // [4]  table mbarriers (2), hole mbarrier, pad
     double* coords = reinterpret_cast<double*>(bars + 4);                     // [slots][ds]
     double* acc = coords + (size_t)slots * ds;                                // [slots]
     double* last_s = acc + slots;                                             // [d + 1]  winner: coordinates + running value
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
 
     unsigned int pool_n = n, m = 0, step = 0, hole_phase = 0, hole_slot = kNone;
     double cur_min = CUDART_INF;
+    double s_prefix = 0.0;  // MaxPro sum of the ordered prefix, in pick order (every thread keeps its copy)
 #if OAS_PROFILE
     long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     __shared__ long long t_ref_s;
@@ -254,6 +257,8 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         };
         unsigned long long bk = ~0ull;
         unsigned int bp = kNone;
+        unsigned int k2 = kNoKeyHi;  // high key word of this thread's second-best (MaxPro steps: contender detection, order_psi.cuh)
+        constexpr bool PSI = MAXPRO && !CENTRE;
         // keep the running value, offer (value, position) to the argbest
         auto offer = [&](unsigned int s, double v) {
             double c = v;
@@ -263,7 +268,12 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
             }
             const unsigned long long k = value_key<MINI>(c);
             const unsigned int pos = s * kCl + rank;
-            if (k < bk || (k == bk && pos < bp)) { bk = k; bp = pos; }
+            if (k < bk || (k == bk && pos < bp)) {
+                if (PSI && bp != kNone) k2 = min(k2, (unsigned int)(bk >> 32));
+                bk = k; bp = pos;
+            } else if (PSI) {
+                k2 = min(k2, (unsigned int)(k >> 32));
+            }
         };
 
         const unsigned int par = step & 1u;
@@ -318,9 +328,13 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
             hole_phase ^= 1u;
         }
         // ---- 1c. argbest of the warp; its record goes to every CTA of the cluster (lane r stores into CTA r)
+        const unsigned long long own_k = bk;
+        const unsigned int own_p = bp;
         warp_argmin_key(bk, bp);
+        // second-best of the warp: a lane whose own best lost offers it (high key word only)
+        if (PSI) k2 = __reduce_min_sync(0xffffffffu, min(k2, (own_p != kNone && own_p != bp) ? (unsigned int)(own_k >> 32) : kNoKeyHi));
         if (lane < kCl)
-            st_async_v2(map_rank(smem_u32(&cand[par * NREC + rank * NW + warp]), lane), bk, (unsigned long long)bp, map_rank(cbar, lane));
+            st_async_v2(map_rank(smem_u32(&cand[par * NREC + rank * NW + warp]), lane), bk, ((unsigned long long)k2 << 32) | bp, map_rank(cbar, lane));
         // the hole mbarrier's phase has been consumed: arm the next one (any order with the next mail is fine --
         // a phase cannot complete before this arrival)
         if (hole_slot != kNone && tid == 0) mbar_arrive_expect_tx(hole_bar, (d + 2) * 8u);
@@ -329,16 +343,64 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         //         the winner.  A complete table also says that every warp of the cluster is past its slots.
         mbar_wait(cbar, (step >> 1) & 1u);
         OAS_T(2)
-        bk = ~0ull; bp = kNone;
+        bk = ~0ull; bp = kNone; k2 = kNoKeyHi;
 #pragma unroll
         for (unsigned int j = 0; j < PER_LANE; ++j) {
             const CandRec rec = cand[par * NREC + (lane + 32 * j) % NREC];
             const unsigned long long k = (unsigned long long)__double_as_longlong(rec.v);
             const unsigned int pos = (unsigned int)rec.p;
-            if (k < bk || (k == bk && pos < bp)) { bk = k; bp = pos; }
+            if (PSI) k2 = min(k2, (unsigned int)(rec.p >> 32));
+            if (k < bk || (k == bk && pos < bp)) {
+                if (PSI && bp != kNone) k2 = min(k2, (unsigned int)(bk >> 32));
+                bk = k; bp = pos;
+            } else if (PSI && pos != kNone && pos != bp) {
+                k2 = min(k2, (unsigned int)(k >> 32));
+            }
         }
+        const unsigned long long own_fk = bk;
+        const unsigned int own_fp = bp;
         warp_argmin_key(bk, bp);
-        const unsigned int q = bp;
+        unsigned int q = bp;
+        if (PSI) {
+            // The reference compares psi of prefix + candidate (order.rs:84-99), first position on equal psi.  Does any
+            // other pool point of the cluster lie in the band of running values where psi can coincide with the winner's?
+            // (Every warp of every CTA folds the same table, so all of them take the branch together.)
+            k2 = __reduce_min_sync(0xffffffffu, min(k2, (own_fp != kNone && own_fp != q) ? (unsigned int)(own_fk >> 32) : kNoKeyHi));
+            const double a_best = __longlong_as_double((long long)(MINI ? bk : ~bk));
+            const double band = order_tie_band(s_prefix, a_best, d);
+            const double lim = MINI ? __dadd_rn(a_best, band) : __dsub_rn(a_best, band);
+            if (k2 <= order_key_hi<MINI>(lim)) {
+                __syncthreads();  // the running values written by the other warps of this CTA
+                const double n_pairs = order_pairs(m + 1), inv_d = 1.0 / (double)d;
+                unsigned long long pk = ~0ull;
+                unsigned int pp = kNone;
+                for (unsigned int s = tid; s < live; s += T) {
+                    const double a = acc[s];
+                    if (MINI ? a <= lim : a >= lim) {
+                        const unsigned long long k = value_key<MINI>(order_psi(s_prefix, a, n_pairs, inv_d));
+                        const unsigned int pos = s * kCl + rank;
+                        if (k < pk || (k == pk && pos < pp)) { pk = k; pp = pos; }
+                    }
+                }
+                warp_argmin_key(pk, pp);
+                if (lane < kCl) {
+                    CandRec* dst = cluster.map_shared_rank(cand_psi, lane) + rank * NW + warp;
+                    dst->v = __longlong_as_double((long long)pk);
+                    dst->p = (unsigned long long)pp;
+                }
+                cluster.sync();
+                pk = ~0ull; pp = kNone;
+#pragma unroll
+                for (unsigned int j = 0; j < PER_LANE; ++j) {
+                    const CandRec rec = cand_psi[(lane + 32 * j) % NREC];
+                    const unsigned long long k = (unsigned long long)__double_as_longlong(rec.v);
+                    const unsigned int pos = (unsigned int)rec.p;
+                    if (k < pk || (k == pk && pos < pp)) { pk = k; pp = pos; }
+                }
+                warp_argmin_key(pk, pp);
+                q = pp;
+            }
+        }
         // this table's phase is consumed by this warp: arm the phase of step + 2.  The warps still waiting look
         // for the parity of the completed phase, which cannot change before every warp of the cluster has sent
         // the records of step + 2.
@@ -372,6 +434,7 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
         }
         hole_slot = (L != q && rank == q_owner) ? q_slot : kNone;
         if (!MAXPRO && !CENTRE) cur_min = fmin(cur_min, last_s[d]);
+        if (PSI) s_prefix = __dadd_rn(s_prefix, last_s[d]);
         --pool_n; ++m; ++step;
         OAS_T(6)
     };
@@ -389,7 +452,7 @@ __global__ void __launch_bounds__(THR, 1) order_cluster_async_kernel(OrdAsParams
 size_t order_async_smem(unsigned long long n, unsigned long long d, int thr, int cl) {
     const unsigned long long slots = (n + cl - 1) / cl;
     const unsigned long long nrec = (unsigned long long)cl * (thr / 32);
-    return (size_t)(2 * nrec * sizeof(CandRec) + 4 * 8 + slots * (d | 1ull) * 8 + slots * 8 + (d + 1) * 8 + (d + 2) * 8 + slots * 4 + 16);
+    return (size_t)(3 * nrec * sizeof(CandRec) + 4 * 8 + slots * (d | 1ull) * 8 + slots * 8 + (d + 1) * 8 + (d + 2) * 8 + slots * 4 + 16);
 }
 
 constexpr int kOasThreads = 256;  // 7 worker warps + the hole warp
@@ -438,7 +501,7 @@ cudaError_t launch_order_cluster_async(const OrderLaunch& L) {
     // 16 CTAs halve the slots of a worker; worth the doubled record table (128 records folded by every warp)
     // once a worker of an 8-CTA cluster would hold three or more slots.
     int cl = (L.n + 7) / 8 > 2ull * (kOasThreads - 32) ? 16 : 8;
-    if (const char* v = getenv("MAXPRO_ORDER_CLUSTER_CTAS")) cl = atoi(v) == 16 ? 16 : 8;
+    if (const char* v = cfg("MAXPRO_ORDER_CLUSTER_CTAS")) cl = atoi(v) == 16 ? 16 : 8;
     if (cl == 16) {
         cudaError_t e = launch_cluster<16>(L);
         if (e == cudaSuccess) return e;

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
             double sum = 0.0;
             for (unsigned int it = 0; it < p.items; ++it) sum += part[it];
             // n < 2 -> 0.0 (src/maxpro_utils.rs:75-77); else (S/pairs)^(1/d) (:81-82)
-            s = p.n < 2 ? 0.0 : pow(sum / p.n_pairs, p.inv_d);
+            s = p.n < 2 ? 0.0 : maxpro_psi(sum, p.n_pairs, p.inv_d);
         } else {
             double m = CUDART_INF;  // n == 1 -> +INF (src/maximin_utils.rs:57)
             for (unsigned int it = 0; it < p.items; ++it) m = fmin(m, part[it]);

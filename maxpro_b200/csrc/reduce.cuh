@@ -1,9 +1,48 @@
 // Block-level argbest + last-CTA fold shared by the search and scoring kernels.
 #pragma once
 #include "common.cuh"
+#include "pow_glibc.cuh"
 #include <math_constants.h>
 
 namespace mp {
+
+// psi = (S / n_pairs)^(1/d), src/maxpro_utils.rs:81-82, rounded like the libm pow the reference calls.
+__device__ __forceinline__ double maxpro_psi(double s, double n_pairs, double inv_d) { return pow_glibc(s / n_pairs, inv_d); }
+
+// A lane's running best under the fold of build_lhd (src/lib.rs:85-97).  The reference compares the
+// CRITERION -- psi after powf for MaxPro -- and keeps the later index when two criteria are equal.  Taking
+// the power of every candidate would cost more than scoring it, so a MaxPro lane keeps, beside its best
+// psi, a bound `thr` on the raw sum S above which psi is certainly larger: psi(S (1 + t)) ~ psi(S) (1 + t/d),
+// so t = (4 d + 4) 2^-52 puts psi(S (1 + t)) at least two ulp above psi(S), beyond anything the rounding of
+// pow (< 1 ulp, monotone to that accuracy) can undo.  Only a candidate with S <= thr -- a new best of the
+// lane or a near-tie with it, a handful per lane and launch -- pays for pow_glibc and is compared on psi
+// exactly as the reference does.  Maximin criteria are compared as they are (sqrt of the minimum: exact ties).
+template <bool MAXPRO>
+struct LaneBest {
+    double best, thr, tie;
+    unsigned long long idx;
+    __device__ __forceinline__ void init(double inv_d) {
+        best = MAXPRO ? CUDART_INF : -CUDART_INF;
+        thr = CUDART_INF;
+        tie = fma(4.0 / inv_d + 4.0, 0x1p-52, 1.0);
+        idx = kNoIndex;
+    }
+    // MaxPro: s = raw sum S.  Maximin: s = the criterion itself.
+    __device__ __forceinline__ void offer(double s, unsigned long long i, double n_pairs, double inv_d) {
+        if (MAXPRO) {
+            if (s <= thr) {  // false for NaN, as `m1 < m2` is in the reference
+                const double psi = maxpro_psi(s, n_pairs, inv_d);
+                if (psi < best || (psi == best && (idx == kNoIndex || i > idx))) { best = psi; idx = i; thr = s * tie; }
+            }
+        } else {
+            offer_criterion(s, i);
+        }
+    }
+    // c = the criterion itself (psi or the maximin distance); smaller wins for MaxPro, larger for maximin
+    __device__ __forceinline__ void offer_criterion(double c, unsigned long long i) {
+        if ((MAXPRO ? c < best : c > best) || (c == best && (idx == kNoIndex || i > idx))) { best = c; idx = i; }
+    }
+};
 
 // Block-level argbest, then the last CTA to finish folds the per-CTA records:
 // only 16 bytes per CTA ever reach HBM.

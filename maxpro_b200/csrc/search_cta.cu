@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
     const int tiles = (n + kTileRows - 1) / kTileRows;
     const int chunk = cta_dim_chunk(d);
 
-    double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by thread 0
-    unsigned long long best_idx = kNoIndex;
+    LaneBest<MAXPRO> lb;  // fold of src/lib.rs:85-97 on the criterion (reduce.cuh); kept by thread 0
+    lb.init(p.inv_d);
 
     for (unsigned long long idx = p.lo + blockIdx.x; idx < p.hi; idx += gridDim.x) {
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
@@ -114,12 +114,10 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
 #pragma unroll
             for (int w = 1; w < 4; ++w) s = MAXPRO ? s + red[w] : fmin(s, red[w]);
             if (!MAXPRO) s = sqrt(s);
-            if (MAXPRO ? (s <= best) : (s >= best)) { best = s; best_idx = idx; }  // later index on ties
+            lb.offer(s, idx, p.n_pairs, p.inv_d);
         }
     }
-    if (tid == 0 && MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
-    if (tid != 0) { best = MAXPRO ? CUDART_INF : -CUDART_INF; best_idx = kNoIndex; }
-    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+    block_publish_best<MAXPRO>(lb.best, lb.idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
 // ---- pipelined variant ---------------------------------------------------------------------------
@@ -148,8 +146,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
     const int tiles = (n + kTileRows - 1) / kTileRows;
     const int chunk = cta_dim_chunk(d);
 
-    double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by thread 0
-    unsigned long long best_idx = kNoIndex;
+    LaneBest<MAXPRO> lb;  // fold of src/lib.rs:85-97 on the criterion (reduce.cuh); kept by thread 0
+    lb.init(p.inv_d);
 
     unsigned long long idx = p.lo + blockIdx.x;
     if (idx < p.hi) {  // prologue: the first candidate, nothing to overlap it with
@@ -196,12 +194,10 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
 #pragma unroll
             for (int w = 1; w < kWarps; ++w) s = MAXPRO ? s + red[w] : fmin(s, red[w]);
             if (!MAXPRO) s = sqrt(s);
-            if (MAXPRO ? (s <= best) : (s >= best)) { best = s; best_idx = idx; }  // later index on ties
+            lb.offer(s, idx, p.n_pairs, p.inv_d);
         }
     }
-    if (tid == 0 && MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
-    if (tid != 0) { best = MAXPRO ? CUDART_INF : -CUDART_INF; best_idx = kNoIndex; }
-    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+    block_publish_best<MAXPRO>(lb.best, lb.idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
 static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) {
@@ -217,7 +213,7 @@ static size_t cta_pipe_smem_bytes(unsigned long long n, unsigned long long d) {
 // The pipelined kernel pays for its second buffer with occupancy; it is used while two CTAs of
 // eight warps still fit one SM (the single-buffer kernel then runs four CTAs of four warps).
 static bool cta_use_pipe(unsigned long long n, unsigned long long d) {
-    if (const char* e = getenv("MAXPRO_CTA_PIPE")) return atoi(e) != 0 && cta_pipe_smem_bytes(n, d) + 1024 <= kSmemBudget;
+    if (const char* e = cfg("MAXPRO_CTA_PIPE")) return atoi(e) != 0 && cta_pipe_smem_bytes(n, d) + 1024 <= kSmemBudget;
     return 2 * (cta_pipe_smem_bytes(n, d) + 2048) <= kSmemBudget;
 }
 

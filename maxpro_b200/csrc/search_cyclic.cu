@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
     const unsigned long long total = p.list ? p.list_count : p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
 
-    double best = MAXPRO ? CUDART_INF : -CUDART_INF;
-    unsigned long long best_idx = kNoIndex;
+    LaneBest<MAXPRO> lb;  // fold of src/lib.rs:85-97 on the criterion (reduce.cuh)
+    lb.init(p.inv_d);
 
     // token ring: barrier 1 + smsp*ring + q is the token INTO ring position q
     const int ring = p.ring, smsp = wid & 3, q = wid >> 2;
@@ -340,15 +340,16 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
         __syncwarp(group_mask);
         if (!MAXPRO) s = sqrt(s);
         if (SUPPLIED) {
-            // every score leaves the chip, and the fold compares criteria exactly as lib.rs:85-97 does
-            if (MAXPRO) s = pow(s / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
+            // every score leaves the chip
+            if (MAXPRO) s = maxpro_psi(s, p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
             if (active && g == 0) p.scores[idx] = s;
+            if (active) lb.offer_criterion(s, idx);
+        } else if (active) {
+            lb.offer(s, idx, p.n_pairs, p.inv_d);
         }
-        if (active && (MAXPRO ? (s <= best) : (s >= best))) { best = s; best_idx = idx; }
     }
     if (in_ring && q == 0) cyc_token_wait(tok_in);  // take the last token so no arrival is left pending
-    if (!SUPPLIED && MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
-    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+    block_publish_best<MAXPRO>(lb.best, lb.idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
 template <int N, int D, int C>
@@ -368,7 +369,7 @@ static cudaError_t launch_cyclic_nd(const SearchLaunch& L, const CyclicParams& p
 
 // Shapes with a specialised instantiation; *cands = candidates per CTA.
 bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* cands) {
-    if (const char* e = getenv("MAXPRO_NO_CYCLIC")) if (atoi(e) != 0) return false;
+    if (const char* e = cfg("MAXPRO_NO_CYCLIC")) if (atoi(e) != 0) return false;
     int c = 0;
     if (n == 50 && d == 3) c = 192;
     else if (n == 50 && d == 2) c = 256;
@@ -379,7 +380,7 @@ bool search_cyclic_supported(unsigned long long n, unsigned long long d, int* ca
 cudaError_t launch_search_cyclic(const SearchLaunch& L) {
     CyclicParams p;
     p.ring = 0;  // measured: turn-taking does not pay (generation and scoring cost their sum either way)
-    if (const char* e = getenv("MAXPRO_CYCLIC_RING")) { int v = atoi(e); if (v == 0 || v == 2 || v == 3) p.ring = v; }
+    if (const char* e = cfg("MAXPRO_CYCLIC_RING")) { int v = atoi(e); if (v == 0 || v == 2 || v == 3) p.ring = v; }
     if (p.ring > (L.threads / 32) / 4) p.ring = 0;
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.list = L.list; p.list_count = L.list_count;

@@ -247,9 +247,8 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
     const int tok_in = 1 + smsp * ring + q, tok_out = 1 + smsp * ring + (q + 1 == ring ? 0 : q + 1);
     if (LOCK && q == ring - 1) token_pass(tok_out);  // position 0 scores first
 
-    // MAXPRO minimises S (psi is monotone in S); maximin maximises the distance.
-    double best = MAXPRO ? CUDART_INF : -CUDART_INF;
-    unsigned long long best_idx = kNoIndex;
+    LaneBest<MAXPRO> lb;  // fold of src/lib.rs:85-97 on the criterion (reduce.cuh)
+    lb.init(p.inv_d);
 
     for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
         const unsigned long long off = gcid + rnd * gstep;
@@ -278,12 +277,10 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
             __syncwarp(group_mask);  // partners are done reading before the design is overwritten
         }
         if (!MAXPRO) s = sqrt(s);  // reference compares distances, not squares (ties)
-        // idx grows along the loop, so ">= / <=" keeps the later index on ties
-        if (active && (MAXPRO ? (s <= best) : (s >= best))) { best = s; best_idx = idx; }
+        if (active) lb.offer(s, idx, p.n_pairs, p.inv_d);
     }
     if (LOCK && q == 0) token_wait(tok_in);  // consume the last token so no arrival is left pending
-    if (MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
-    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+    block_publish_best<MAXPRO>(lb.best, lb.idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
 // ---- host side -------------------------------------------------------------
@@ -303,7 +300,7 @@ static cudaError_t launch_drg(const SearchLaunch& L, const SearchParams& p) {
     // the token ring needs whole rings: warps a multiple of 4, 2 or 3 warps per sub-partition
     const int warps = L.threads / 32;
     bool lock = (L.threads % 128 == 0) && (warps / 4 == 2 || warps / 4 == 3);
-    if (const char* e = getenv("MAXPRO_SMALL_LOCK")) lock = lock && atoi(e) != 0;
+    if (const char* e = cfg("MAXPRO_SMALL_LOCK")) lock = lock && atoi(e) != 0;
     if (L.metric == 0) return lock ? launch_one<D, R, G, true, true>(L, p, smem) : launch_one<D, R, G, true, false>(L, p, smem);
     return lock ? launch_one<D, R, G, false, true>(L, p, smem) : launch_one<D, R, G, false, false>(L, p, smem);
 }
@@ -333,7 +330,7 @@ static cudaError_t launch_d(const SearchLaunch& L, const SearchParams& p) {
 // 12.7 vs 14.0, (75,8) 7.9 vs 9.6).
 bool search_small_supported(unsigned long long n, unsigned long long d) {
     unsigned long long min_cands = 64;
-    if (const char* e = getenv("MAXPRO_SMALL_MIN_CANDS")) { int v = atoi(e); if (v >= 16 && v <= 512 && v % 16 == 0) min_cands = (unsigned long long)v; }
+    if (const char* e = cfg("MAXPRO_SMALL_MIN_CANDS")) { int v = atoi(e); if (v >= 16 && v <= 512 && v % 16 == 0) min_cands = (unsigned long long)v; }
     return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * min_cands + 32 * sizeof(BestRec) <= kSmemBudget;
 }
 
@@ -352,7 +349,7 @@ void search_small_pick_config(unsigned long long n, unsigned long long d, int* g
     // (50,5) 11.6 -> 10.3, and the designs that already fill 10+ warps: (30,6) 10.2 -> 9.5, (40,4)
     // 13.1 -> 12.5, (20,4) 10.0 -> 7.6.
     if (d >= 4 && d != 5 && (cap / 16) * 16 * 2 < 320) G = 4;
-    if (const char* e = getenv("MAXPRO_SMALL_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || (v == 4 && d >= 4)) G = v; }
+    if (const char* e = cfg("MAXPRO_SMALL_GROUP")) { int v = atoi(e); if (v == 1 || v == 2 || (v == 4 && d >= 4)) G = v; }
     size_t c;
     if (G == 4) {
         c = cap >= 8 ? ((cap - 8) / 16) * 16 + 8 : 0;  // 8 (mod 16): see the lane layout note in the kernel
@@ -362,7 +359,7 @@ void search_small_pick_config(unsigned long long n, unsigned long long d, int* g
     if (G != 4) {
         c = (cap / 16) * 16;
         if (c * G > 512) c = 512 / G;
-        if (const char* e = getenv("MAXPRO_SMALL_CANDS")) { size_t v = (size_t)atoi(e); if (v >= 16 && v <= c && v % 16 == 0) c = v; }
+        if (const char* e = cfg("MAXPRO_SMALL_CANDS")) { size_t v = (size_t)atoi(e); if (v >= 16 && v <= c && v % 16 == 0) c = v; }
         if (G == 1) c = (c / 32) * 32;
     }
     *group = G;

@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
     const int wrap = kWarpSB * nblk + 2;       // copied rows behind each column
     const int ns2 = ns / 2;                    // row stride in 16-byte units
 
-    double best = MAXPRO ? CUDART_INF : -CUDART_INF;  // kept by lane 0 of each warp
-    unsigned long long best_idx = kNoIndex;
+    LaneBest<MAXPRO> lb;  // fold of src/lib.rs:85-97 on the criterion (reduce.cuh); every lane of the warp holds the same state
+    lb.init(p.inv_d);
 
     const unsigned long long wstep = (unsigned long long)gridDim.x * (kWarpCtaThreads / 32);
     for (unsigned long long idx = p.lo + (unsigned long long)blockIdx.x * (kWarpCtaThreads / 32) + warp; idx < p.hi; idx += wstep) {
@@ -195,11 +195,10 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
         }
         double s = MAXPRO ? warp_reduce_sum(acc) : warp_reduce_min(mn);
         if (!MAXPRO) s = sqrt(s);
-        if (MAXPRO ? (s <= best) : (s >= best)) { best = s; best_idx = idx; }  // later index on ties
+        lb.offer(s, idx, p.n_pairs, p.inv_d);
     }
-    if (MAXPRO && best_idx != kNoIndex) best = pow(best / p.n_pairs, p.inv_d);  // maxpro_utils.rs:81-82
-    if (lane != 0) { best = MAXPRO ? CUDART_INF : -CUDART_INF; best_idx = kNoIndex; }
-    block_publish_best<MAXPRO>(best, best_idx, warp_best, p.block_best, p.done_counter, p.result);
+    if (lane != 0) lb.init(p.inv_d);  // one record per warp
+    block_publish_best<MAXPRO>(lb.best, lb.idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
 static unsigned long long warp_row_stride(unsigned long long n) {
@@ -224,9 +223,9 @@ static int warp_ctas_per_sm(unsigned long long n, unsigned long long d) {
 // (3 CTAs of 4 warps) fit the shared memory of one SM -- below that the Fisher-Yates walks are no
 // longer hidden and the CTA-per-candidate kernel does better.
 bool search_warp_supported(unsigned long long n, unsigned long long d) {
-    if (const char* e = getenv("MAXPRO_NO_WARP")) if (atoi(e) != 0) return false;
+    if (const char* e = cfg("MAXPRO_NO_WARP")) if (atoi(e) != 0) return false;
     int need = 3;
-    if (const char* e = getenv("MAXPRO_WARP_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4) need = v; }
+    if (const char* e = cfg("MAXPRO_WARP_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4) need = v; }
     return n >= 2 && n <= 65535 && d >= 1 && d <= 65535 && warp_ctas_per_sm(n, d) >= need;
 }
 

@@ -3,7 +3,8 @@
 //   -s/--samples <u64>  -i/--iterations <u64>  -n/--ndims <u64>  -m/--metric <max-pro|maxi-min>
 //   --seed <u64>  --anneal-iterations <u64>=100000  --anneal-cooling <f64>=0.99  --anneal-t <f64>=1.0
 //   -p/--plot  -o/--output-path <str>
-// Extra (not in the reference): --anneal-chains <u64>=1, --devices is not needed (one GPU).
+// Extra (not in the reference): --anneal-chains <u64>=1 (independent chains, best returned) and --gpus <N>=1 (the
+// search and the chains are spread over the first N devices of the box, 0 = all; the reference spreads over all cores).
 #include <charconv>
 #include <cstdio>
 #include <cstdlib>
@@ -74,6 +75,7 @@ void print_help() {
                  "      --anneal-cooling <ANNEAL_COOLING>        [default: 0.99]\n"
                  "      --anneal-t <ANNEAL_T>                    [default: 1]\n"
                  "      --anneal-chains <N>                      [default: 1]  (B200 engine only: independent chains, best returned)\n"
+                 "      --gpus <N>                               [default: 1]  (B200 engine only: devices to spread over, 0 = all)\n"
                  "  -h, --help                                   Print help\n";
 }
 
@@ -110,7 +112,7 @@ void print_design_debug(const maxpro::Design& d) {
 int main(int argc, char** argv) {
     using maxpro::enums::Metrics;
     bool has_samples = false, has_iters = false, has_ndims = false, has_seed = false, plot = false, has_out = false;
-    uint64_t samples = 0, iterations = 0, ndims = 0, seed = 0, anneal_iterations = 100000, anneal_chains = 1;
+    uint64_t samples = 0, iterations = 0, ndims = 0, seed = 0, anneal_iterations = 100000, anneal_chains = 1, gpus = 1;
     double anneal_cooling = 0.99, anneal_t = 1.0;
     Metrics metric = Metrics::MaxPro;
     std::string output_path;
@@ -149,6 +151,7 @@ int main(int argc, char** argv) {
         else if (arg == "--anneal-cooling") anneal_cooling = parse_f64("--anneal-cooling <ANNEAL_COOLING>", next());
         else if (arg == "--anneal-t") anneal_t = parse_f64("--anneal-t <ANNEAL_T>", next());
         else if (arg == "--anneal-chains") anneal_chains = parse_u64("--anneal-chains <N>", next());
+        else if (arg == "--gpus") gpus = parse_u64("--gpus <N>", next());
         else usage_error("unexpected argument '" + arg + "' found");
     }
     if (!has_samples || !has_iters || !has_ndims) {
@@ -175,6 +178,11 @@ int main(int argc, char** argv) {
         return minimize ? maxpro::maxpro_utils::maxpro_criterion(d) : maxpro::maximin_utils::maximin_criterion(d);
     };
     try {
+        if (gpus != 1) {  // 0 = every device of the box
+            std::vector<int> devs;
+            for (uint64_t g = 0; g < gpus; ++g) devs.push_back((int)g);
+            maxpro::set_devices(devs);
+        }
         maxpro::Design lhd = maxpro::build_lhd(samples, ndims, iterations, metric, seed);   // main.rs:71
         double metric_value = metric_fn(lhd);                                               // main.rs:73
         const uint64_t swap_iters = anneal_iterations / 5;                                  // main.rs:77

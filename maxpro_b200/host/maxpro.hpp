@@ -50,6 +50,12 @@ inline Design unflatten(const std::vector<double>& flat, uint64_t n, uint64_t di
 inline int metric_id(enums::Metrics m) { return m == enums::Metrics::MaxPro ? MAXPRO_METRIC_MAXPRO : MAXPRO_METRIC_MAXIMIN; }
 }  // namespace detail
 
+// Devices the build_lhd / anneal_lhd calls of this thread spread over (empty = every device of the box): the
+// counterpart of rayon's global pool in the reference (src/lib.rs:65-98).  Not calling it keeps device 0.
+inline void set_devices(const std::vector<int>& devices) {
+    detail::check(maxpro_set_devices(devices.empty() ? nullptr : devices.data(), (int)devices.size()));
+}
+
 namespace lhd {
 // src/lhd.rs:97-132.  The reference takes &mut StdRng; every call site seeds it from a u64
 // (lib.rs:44,70, lhd.rs:211), so the seed is the argument here.

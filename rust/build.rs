@@ -4,7 +4,7 @@ use std::path::PathBuf;
 use std::process::Command;
 
 const SOURCES: &[&str] = &[
-    "api.cu", "search_small.cu", "search_cyclic.cu", "search_screen.cu", "search_cta.cu", "search_warp.cu",
+    "api.cu", "config.cu", "search_small.cu", "search_cyclic.cu", "search_screen.cu", "search_cta.cu", "search_warp.cu",
     "pair_generic.cu", "generate.cu", "anneal.cu", "anneal_pipe.cu", "anneal_maximin.cu", "order.cu", "order_cluster.cu", "order_cluster_async.cu", "probe.cu",
 ];
 

@@ -10,6 +10,8 @@ pub const METRIC_MAXIMIN: c_int = 1;
 unsafe extern "C" {
     pub fn maxpro_last_error() -> *const c_char;
     pub fn maxpro_release_device_cache(bytes: *mut u64) -> c_int;
+    /// Devices the build_lhd / anneal_lhd calls of this thread spread over (count == 0: every device of the box).
+    pub fn maxpro_set_devices(devices: *const c_int, count: c_int) -> c_int;
     pub fn maxpro_generate_lhd(n: u64, d: u64, seed: u64, out: *mut f64) -> c_int;
     pub fn maxpro_criterion(design: *const f64, n: u64, d: u64, out: *mut f64) -> c_int;
     pub fn maxpro_maximin_criterion(design: *const f64, n: u64, d: u64, out: *mut f64) -> c_int;

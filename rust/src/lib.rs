@@ -38,6 +38,13 @@ pub fn build_lhd(
     ffi::unflatten(&flat, n_samples, n_dim)
 }
 
+/// Devices the `build_lhd` / `anneal_lhd` calls of this thread spread over (empty slice = every device of the box):
+/// the counterpart of rayon's global pool in the reference (src/lib.rs:65-98).  Not calling it keeps device 0.
+pub fn set_devices(devices: &[i32]) {
+    let ptr = if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() };
+    ffi::check(unsafe { ffi::maxpro_set_devices(ptr, devices.len() as c_int) });
+}
+
 /// Which of the two criteria is this closure?  Decided on the reference's own known-answer
 /// designs (src/maxpro_utils.rs:117-133, src/maximin_utils.rs:85-101):
 /// [[0,1],[1,0]] -> MaxPro 1, maximin sqrt 2;  [[0,2],[1,0]] -> MaxPro 0.5, maximin sqrt 5.

@@ -37,6 +37,9 @@ struct Args {
     plot: bool,
     #[arg(short, long)]
     output_path: Option<String>,
+    /// B200 engine only: devices the search and the chains are spread over (0 = all)
+    #[arg(long, default_value_t = 1)]
+    gpus: u32,
 }
 
 fn main() {
@@ -52,6 +55,9 @@ fn main() {
         Metrics::MaxPro => (maxpro_criterion as fn(&Vec<Vec<f64>>) -> f64, true),
         Metrics::MaxiMin => (maximin_criterion as fn(&Vec<Vec<f64>>) -> f64, false),
     };
+    if args.gpus != 1 {
+        maxpro::set_devices(&(0..args.gpus as i32).collect::<Vec<i32>>());
+    }
     let lhd = build_lhd(args.samples, args.ndims, args.iterations, Some(args.metric.clone()), seed);
     let metric_value = metric_fn(&lhd);
     let swap_iterations = args.anneal_iterations / 5;

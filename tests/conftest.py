@@ -29,6 +29,34 @@ def pymaxpro_golden():
     return g
 
 
+class _Switches:
+    """Test switches of the library (maxpro_debug_set): force a kernel path for one test."""
+
+    def __init__(self):
+        self._touched = set()
+
+    def set(self, name, value):
+        from maxpro_b200 import _lib
+        _lib.debug_set(name, value)
+        self._touched.add(name)
+
+    def clear(self, name):
+        from maxpro_b200 import _lib
+        _lib.debug_set(name, None)
+
+    def reset(self):
+        for name in self._touched:
+            self.clear(name)
+        self._touched.clear()
+
+
+@pytest.fixture
+def switches():
+    s = _Switches()
+    yield s
+    s.reset()
+
+
 def random_lhd(rng, n, d):
     """Random LHD of the reference's shape (src/lhd.rs:117-128), NumPy-generated."""
     x = np.empty((n, d))

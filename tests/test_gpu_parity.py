@@ -114,7 +114,7 @@ def test_score_batch_tie_rule(metric):
 
 @pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
-def test_score_batch_headline_shapes_fast_path(n, d, metric, monkeypatch):
+def test_score_batch_headline_shapes_fast_path(n, d, metric, switches):
     """n=50 batches take the thread-group kernel fed from HBM: odd batch sizes, designs outside
     the unit cube (IEEE-divide fallback), boundary coordinates, coincident points, ties; and the
     same batch through the generic tiled kernel must give the same argbest."""
@@ -130,9 +130,9 @@ def test_score_batch_headline_shapes_fast_path(n, d, metric, monkeypatch):
         got, arg = engine.score_batch(designs, metric)
         assert arg == ref_arg
         assert rel_err(got, ref) < REL if metric == METRIC_MAXPRO else np.array_equal(got, ref)
-        monkeypatch.setenv("MAXPRO_NO_FAST_SCORE", "1")
+        switches.set("MAXPRO_NO_FAST_SCORE", "1")
         got2, arg2 = engine.score_batch(designs, metric)
-        monkeypatch.delenv("MAXPRO_NO_FAST_SCORE")
+        switches.clear("MAXPRO_NO_FAST_SCORE")
         assert arg2 == arg and rel_err(got2, got) < REL
     dup = np.concatenate([designs, designs[arg:arg + 1]])
     assert engine.score_batch(dup, metric)[1] == len(designs)  # later index on ties
@@ -202,9 +202,9 @@ def test_search_warp_and_cta_paths(n, d, iters):
 
 
 @pytest.mark.parametrize("n,d", [(40, 9), (130, 10), (300, 4), (33, 12), (100, 5)])
-def test_search_cta_path_on_medium_shapes(n, d, monkeypatch):
+def test_search_cta_path_on_medium_shapes(n, d, switches):
     """The CTA kernel must still serve the shapes the warp kernel normally takes."""
-    monkeypatch.setenv("MAXPRO_NO_WARP", "1")
+    switches.set("MAXPRO_NO_WARP", "1")
     iters, seed = 3000, 7
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
@@ -215,16 +215,15 @@ def test_search_cta_path_on_medium_shapes(n, d, monkeypatch):
 
 
 @pytest.mark.parametrize("pipe", ["0", "1"])
-@pytest.mark.parametrize("n,d,iters", [(500, 10, 2500), (130, 10, 3000), (65, 9, 2000), (66, 7, 2000), (700, 3, 1200), (64, 1, 900), (9, 33, 700)])
-def test_search_cta_single_and_double_buffered(n, d, iters, pipe, monkeypatch):
+@pytest.mark.parametrize("n,d,iters", [(500, 10, 2500), (130, 10, 3000), (65, 9, 2000), (66, 7, 2000), (700, 3, 1200), (64, 1, 900), (9, 33, 700),
+                                       (130, 20, 1500), (500, 20, 600), (60, 16, 2000)])
+def test_search_cta_single_and_double_buffered(n, d, iters, pipe, switches):
     """Both CTA kernels (one design buffer with a barrier around the Fisher-Yates walk; two buffers
     with the walk of the next candidate overlapped with the scoring of this one) find the oracle's
-    winner; more candidates than CTAs, so every CTA runs its pipeline for several rounds.  (Shapes with
-    d >~ 15 are left out on purpose: there every product of squared differences is far below the
-    reference's eps = 1e-12, all candidates score (1/eps)^(1/d) to the last few ulps, and the winner is
-    decided by the summation order -- DESIGN.md section 2, difference (3).)"""
-    monkeypatch.setenv("MAXPRO_NO_WARP", "1")
-    monkeypatch.setenv("MAXPRO_CTA_PIPE", pipe)
+    winner; more candidates than CTAs, so every CTA runs its pipeline for several rounds.  The fold compares
+    the criterion after the 1/d-th power, as src/lib.rs:85-97 does, so the d = 16 and d = 20 shapes belong here too."""
+    switches.set("MAXPRO_NO_WARP", "1")
+    switches.set("MAXPRO_CTA_PIPE", pipe)
     seed = 11
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         s_ref, i_ref = oracle.search_range(n, d, metric, seed, 5, 5 + iters)
@@ -247,9 +246,9 @@ def test_search_warp_path_winner(n, d, metric):
 
 
 @pytest.mark.parametrize("n,d", [(40, 9), (130, 10), (300, 4)])
-def test_search_generic_path(n, d, monkeypatch):
+def test_search_generic_path(n, d, switches):
     """Chunked generate -> tiled score path (what remains for shapes no fused kernel covers)."""
-    monkeypatch.setenv("MAXPRO_NO_CTA", "1")
+    switches.set("MAXPRO_NO_CTA", "1")
     iters, seed = 3000, 7
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, iters)
@@ -344,7 +343,7 @@ def test_anneal_chains_and_contract():
 
 
 @pytest.mark.parametrize("n,d,iters,cooling", [(200, 4, 600, 0.99), (120, 6, 500, 0.97), (64, 3, 2500, 0.995)])
-def test_anneal_swap_pipeline_matches_oracle(n, d, iters, cooling, monkeypatch):
+def test_anneal_swap_pipeline_matches_oracle(n, d, iters, cooling, switches):
     """Swap moves on MaxPro run as a two-stage pipeline (anneal_pipe.cu): speculative wide half,
     special terms for the rows of the previous move, log-threshold acceptance, series for small
     changes of S.  The trajectory must still be the oracle's (full re-score + pow + exp), and
@@ -353,25 +352,27 @@ def test_anneal_swap_pipeline_matches_oracle(n, d, iters, cooling, monkeypatch):
     ref, ref_best = oracle.anneal_lhd(x, iters, 1.0, cooling, METRIC_MAXPRO, True, 99, True)
     got, best, _ = engine.anneal_lhd(x, iters, 1.0, cooling, METRIC_MAXPRO, True, 99, True, n_chains=1)
     assert np.array_equal(got, ref) and math.isclose(best, ref_best, rel_tol=REL)
-    monkeypatch.setenv("MAXPRO_NO_ANNEAL_PIPE", "1")
+    switches.set("MAXPRO_NO_ANNEAL_PIPE", "1")
     got2, best2, _ = engine.anneal_lhd(x, iters, 1.0, cooling, METRIC_MAXPRO, True, 99, True, n_chains=1)
     assert np.array_equal(got2, ref) and math.isclose(best2, ref_best, rel_tol=REL)
 
 
 @pytest.mark.parametrize("n,d,iters,minimize", [(200, 4, 1500, False), (121, 6, 1200, False), (64, 3, 3000, False), (2, 3, 50, False),
                                                  (3, 1, 200, False), (33, 1, 800, False), (40, 35, 600, False), (90, 2, 1500, True),
-                                                 (700, 5, 250, False)])
-def test_anneal_maximin_swap_incremental_matches_oracle(n, d, iters, minimize, monkeypatch):
+                                                 (700, 5, 250, False), (1000, 20, 120, False)])
+def test_anneal_maximin_swap_incremental_matches_oracle(n, d, iters, minimize, switches):
     """Swap moves on maximin keep an exact nearest-neighbour table (anneal_maximin.cu) instead of
     re-scoring all pairs: the criterion of every step is the reference's bit for bit, so the chain
     must end in the oracle's design; the full re-score kernel (MAXPRO_NO_ANNEAL_MAXIMIN_INC=1)
-    must agree as well.  minimize=True walks the other way (towards clustered points, many dirty rows)."""
+    must agree as well.  minimize=True walks the other way (towards clustered points, many dirty rows).
+    (1000, 20) is the shape of BASELINE config C4, where maximin is the meaningful criterion: at d = 20 every
+    product of squared differences is below the reference's eps and MaxPro scores every design 3.981."""
     x = oracle.generate_lhd(n, d, 31)
     ref, ref_best = oracle.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True)
     got, best, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
     assert np.array_equal(got, ref) and best == ref_best
     assert best == oracle.maximin_criterion(got)  # the returned design is the global best of the chain
-    monkeypatch.setenv("MAXPRO_NO_ANNEAL_MAXIMIN_INC", "1")
+    switches.set("MAXPRO_NO_ANNEAL_MAXIMIN_INC", "1")
     got2, best2, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
     assert np.array_equal(got2, ref) and best2 == ref_best
 
@@ -525,8 +526,8 @@ def test_order_large(metric, minimize):
     assert abs(oracle.maxpro_criterion(x) - oracle.maxpro_criterion(got)) < 1e-10 * oracle.maxpro_criterion(x)
 
 
-@pytest.mark.parametrize("n,d", [(64, 2), (65, 3), (71, 1), (200, 6), (1000, 3), (513, 4), (2049, 2), (300, 33)])
-def test_order_cluster_path(n, d, monkeypatch):
+@pytest.mark.parametrize("n,d", [(64, 2), (65, 3), (71, 1), (200, 6), (1000, 3), (513, 4), (2049, 2), (300, 33), (200, 20), (1000, 20), (100, 40)])
+def test_order_cluster_path(n, d, switches):
     """n >= 64 runs on a thread-block cluster (pool in distributed shared memory): the kernel that
     exchanges through mbarriers / st.async / remote loads (order_cluster_async.cu, the default) and the
     one with two cluster barriers per step (order_cluster.cu) must pick exactly what the single-CTA
@@ -534,23 +535,23 @@ def test_order_cluster_path(n, d, monkeypatch):
     x = oracle.generate_lhd(n, d, 5)
     for metric, minimize in ((METRIC_MAXPRO, True), (METRIC_MAXIMIN, False), (METRIC_MAXIMIN, True), (METRIC_MAXPRO, False)):
         _, p_ref = oracle.order_design(x, metric, minimize, incremental=True)
-        monkeypatch.setenv("MAXPRO_ORDER_CLUSTER_CTAS", "8")
+        switches.set("MAXPRO_ORDER_CLUSTER_CTAS", "8")
         _, p = engine.order_design(x, metric, minimize)
-        monkeypatch.setenv("MAXPRO_ORDER_CLUSTER_CTAS", "16")  # the non-portable cluster size large pools take
+        switches.set("MAXPRO_ORDER_CLUSTER_CTAS", "16")  # the non-portable cluster size large pools take
         _, p16 = engine.order_design(x, metric, minimize)
-        monkeypatch.delenv("MAXPRO_ORDER_CLUSTER_CTAS")
+        switches.clear("MAXPRO_ORDER_CLUSTER_CTAS")
         assert p16.tolist() == p.tolist(), "16-CTA cluster against 8"
-        monkeypatch.setenv("MAXPRO_ORDER_CLUSTER_SYNC", "1")
+        switches.set("MAXPRO_ORDER_CLUSTER_SYNC", "1")
         _, p2 = engine.order_design(x, metric, minimize)
-        monkeypatch.delenv("MAXPRO_ORDER_CLUSTER_SYNC")
-        monkeypatch.setenv("MAXPRO_NO_ORDER_CLUSTER", "1")
+        switches.clear("MAXPRO_ORDER_CLUSTER_SYNC")
+        switches.set("MAXPRO_NO_ORDER_CLUSTER", "1")
         _, p1 = engine.order_design(x, metric, minimize)
-        monkeypatch.delenv("MAXPRO_NO_ORDER_CLUSTER")
+        switches.clear("MAXPRO_NO_ORDER_CLUSTER")
         assert p.tolist() == p1.tolist() == p2.tolist(), "the three kernels disagree"
         # MaxPro at large d: the reference compares psi = ((S + acc)/pairs)^(1/d), in which near-equal running values
-        # collapse into exact ties; the kernels compare the running values themselves.
-        if metric == METRIC_MAXIMIN or d <= 16:
-            assert p.tolist() == p_ref.tolist(), "kernels against the oracle"
+        # collapse into exact ties that go to the first pool position (order.rs:84-99) -- at (300, 33) from step 13 on.
+        # The kernels resolve such contenders on psi itself, with pow rounded like libm's (order_psi.cuh).
+        assert p.tolist() == p_ref.tolist(), "kernels against the oracle"
 
 
 def test_order_cluster_async_repeatable(r_golden):
@@ -593,6 +594,112 @@ def test_order_c5_shape_runs():
     assert sorted(p.tolist()) == list(range(5000))
     _, p_ref = oracle.order_design(x, METRIC_MAXPRO, True, incremental=True)
     assert p.tolist() == p_ref.tolist()
+
+
+def test_order_small_high_d_single_cta():
+    """n < 64 runs on one CTA (order.cu); d = 40 makes nearly every step a psi tie (first pool position wins)."""
+    for n, d in ((40, 40), (63, 33), (20, 64)):
+        x = oracle.generate_lhd(n, d, 17)
+        for minimize in (True, False):
+            _, p_ref = oracle.order_design(x, METRIC_MAXPRO, minimize, incremental=True)
+            _, p = engine.order_design(x, METRIC_MAXPRO, minimize)
+            assert p.tolist() == p_ref.tolist(), (n, d, minimize)
+            if n <= 40:
+                _, p_full = oracle.order_design(x, METRIC_MAXPRO, minimize)  # the O(n^4 d) restatement of order.rs
+                assert p_full.tolist() == p_ref.tolist()
+
+
+# ---------------------------------------------------------------- pow, psi ties
+
+def test_pow_glibc_device():
+    """The device build of pow_glibc.cuh against this host's libm, bit for bit, on the arguments the kernels
+    use ((S / pairs)^(1/d)) and on wider ranges; tests/test_pow_glibc.py does the same for the host build."""
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    d = rng.integers(1, 65, n).astype(np.float64)
+    x = np.exp2(rng.uniform(-10.0, 70.0, n))
+    y = 1.0 / d
+    x2 = np.exp2(rng.uniform(-1000.0, 1000.0, n))
+    y2 = 1.0 / rng.integers(1, 4097, n).astype(np.float64)
+    x3 = 1.0 + (rng.random(n) - 0.5) * np.exp2(-rng.integers(0, 50, n).astype(np.float64))
+    y3 = rng.random(n) * 4.0
+    for xs, ys in ((x, y), (x2, y2), (x3, y3)):
+        got = _lib.debug_pow(xs, ys)
+        m = 200_000  # math.pow is the C library's pow, one call per element
+        ref = np.array([math.pow(a, b) for a, b in zip(xs[:m], ys[:m])])
+        assert np.array_equal(got[:m].view(np.uint64), ref.view(np.uint64))
+
+
+def test_search_psi_collapse_keeps_last_index():
+    """d = 40: every product of squared differences vanishes beside eps, every candidate scores the same psi, and
+    the reference's fold keeps the LAST candidate (lib.rs:85-97: ties go to the later index)."""
+    n, d, seed, lo, hi = 12, 40, 11, 5, 505
+    s_ref, i_ref = oracle.search_range(n, d, METRIC_MAXPRO, seed, lo, hi)
+    assert i_ref == hi - 1
+    s, i = engine.search_range(n, d, METRIC_MAXPRO, seed, lo, hi)
+    assert i == i_ref and s == s_ref
+
+
+def test_score_batch_psi_ties_go_to_later_index():
+    """Two designs whose raw sums differ by a few ulp but whose criteria are equal after the power: the later one
+    wins, as in lib.rs:85-97 (the fold compares psi, not S)."""
+    rng = np.random.default_rng(21)
+    n, d = 30, 24
+    base = np.stack([random_lhd(rng, n, d) for _ in range(64)])
+    ref, ref_arg = oracle.score_batch(base, METRIC_MAXPRO)
+    got, arg = engine.score_batch(base, METRIC_MAXPRO)
+    assert rel_err(got, ref) < REL
+    # identical copies at both ends: equal psi by construction, the LAST index must win
+    best = base[ref_arg]
+    dup = np.concatenate([best[None], base, best[None]])
+    _, arg2 = engine.score_batch(dup, METRIC_MAXPRO)
+    assert arg2 == len(dup) - 1 == oracle.score_batch(dup, METRIC_MAXPRO)[1]
+
+
+# ---------------------------------------------------------------- devices, scratch
+
+def test_anneal_scratch_is_per_resident_cta_not_per_chain():
+    """C4 (65,536 chains of a 1000 x 20 design): the chains' bests are folded per CTA on the device."""
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        b = _lib.anneal_scratch_bytes(1000, 20, metric, True, 65536)
+        assert b < 100 * 2 ** 20, b
+    assert _lib.anneal_scratch_bytes(50, 3, METRIC_MAXPRO, True, 1 << 20) < 100 * 2 ** 20
+
+
+def test_anneal_many_chains_match_single_chain_runs():
+    """More chains than resident CTAs: every CTA runs several chains and keeps the best; the result must be the
+    chain a one-chain-at-a-time run finds (lowest chain index on equal metrics)."""
+    x = oracle.generate_lhd(24, 3, 4)
+    for metric, minimize in ((METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)):
+        n_chains = 6000
+        got, best, chain = engine.anneal_lhd(x, 40, 1.0, 0.99, metric, minimize, 77, True, n_chains=n_chains)
+        alone, best1, _ = engine.anneal_lhd(x, 40, 1.0, 0.99, metric, minimize, 77 + chain, True, n_chains=1)
+        assert best1 == best and np.array_equal(alone, got)
+        ref, ref_best = oracle.anneal_lhd(x, 40, 1.0, 0.99, metric, minimize, 77 + chain, True)
+        assert np.array_equal(ref, got)
+        assert math.isclose(best, ref_best, rel_tol=REL) if metric == METRIC_MAXPRO else best == ref_best
+
+
+def test_multi_device_calls_match_one_device():
+    """maxpro_set_devices: index blocks over the devices, host fold -- same winner and same chain as one device."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    try:
+        for n, d, iters in ((50, 3, 300_000), (500, 10, 900)):
+            for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+                _lib.set_devices([0])
+                one = engine.build_lhd(n, d, iters, metric, 42)
+                _lib.set_devices([0, 1])
+                two = engine.build_lhd(n, d, iters, metric, 42)
+                assert one[2] == two[2] and one[1] == two[1] and np.array_equal(one[0], two[0])
+        x = oracle.generate_lhd(60, 4, 9)
+        _lib.set_devices([0])
+        a = engine.anneal_lhd(x, 100, 1.0, 0.99, METRIC_MAXPRO, True, 5, True, n_chains=500)
+        _lib.set_devices([])
+        b = engine.anneal_lhd(x, 100, 1.0, 0.99, METRIC_MAXPRO, True, 5, True, n_chains=500)
+        assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])
+    finally:
+        _lib.set_device(0)
 
 
 # ---------------------------------------------------------------- python surface end to end

@@ -1,10 +1,10 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from maxpro_b200 import METRIC_MAXPRO, engine
+from maxpro_b200 import METRIC_MAXPRO, _lib, engine
 x = engine.generate_lhd(1000, 20, 42)
 engine.anneal_lhd(x, 10, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, 148)
 for thr in (512, 384, 256, 128, 64):
-    os.environ["MAXPRO_ANNEAL_THREADS"] = str(thr)
+    _lib.debug_set("MAXPRO_ANNEAL_THREADS", str(thr))
     ts = []
     for steps in (100, 500):
         t0 = time.perf_counter(); engine.anneal_lhd(x, steps, 1.0, 0.99, METRIC_MAXPRO, True, 43, True, 148); ts.append(time.perf_counter() - t0)

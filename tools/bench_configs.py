@@ -78,10 +78,10 @@ if "c4" in which:
     (out, bestm, ch), t_m = timed(engine.anneal_lhd, x, 1000, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
     for _ in range(2):  # a 50 ms call: the best of three keeps host-side noise (allocation, copies) out
         t_m = min(t_m, timed(engine.anneal_lhd, x, 1000, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)[1])
-    os.environ["MAXPRO_NO_ANNEAL_MAXIMIN_INC"] = "1"
+    _lib.debug_set("MAXPRO_NO_ANNEAL_MAXIMIN_INC", "1")
     engine.anneal_lhd(x, 2, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
     (_, bestf, _), t_f = timed(engine.anneal_lhd, x, 20, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
-    del os.environ["MAXPRO_NO_ANNEAL_MAXIMIN_INC"]
+    _lib.debug_set("MAXPRO_NO_ANNEAL_MAXIMIN_INC", None)
     (_, b20, _), _t = timed(engine.anneal_lhd, x, 20, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, chains)
     emit(config="C4-maximin-swap", n=n, d=d, chains=chains, steps=1000, gpu_s=t_m, gpu_chain_steps_per_s=chains * 1000 / t_m,
          full_rescore_chain_steps_per_s=chains * 20 / t_f, same_best_after_20_steps=(b20 == bestf),

@@ -50,19 +50,19 @@ if mode == "screen":
 
 if mode == "sweep":
     total = 1 << 25
-    os.environ["MAXPRO_NO_CYCLIC"] = "0"
+    _lib.debug_set("MAXPRO_NO_CYCLIC", "0")
     for ring in (0, 2, 3):
-        os.environ["MAXPRO_CYCLIC_RING"] = str(ring)
+        _lib.debug_set("MAXPRO_CYCLIC_RING", str(ring))
         for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
             for (n, d) in ((50, 3), (50, 2)):
                 ms = dev_search(n, d, metric, total)
                 print(f"cyclic ring={ring} n={n} d={d} metric={metric}: {ms:.2f} ms = {total/ms/1e6:.3f} Gcand/s", flush=True)
-    os.environ["MAXPRO_NO_CYCLIC"] = "1"
+    _lib.debug_set("MAXPRO_NO_CYCLIC", "1")
     for lock in (0,):
         for G, cands in ((1, 192), (2, 192)):
-            os.environ["MAXPRO_SMALL_GROUP"] = str(G)
-            os.environ["MAXPRO_SMALL_CANDS"] = str(cands)
-            os.environ["MAXPRO_SMALL_LOCK"] = str(lock)
+            _lib.debug_set("MAXPRO_SMALL_GROUP", str(G))
+            _lib.debug_set("MAXPRO_SMALL_CANDS", str(cands))
+            _lib.debug_set("MAXPRO_SMALL_LOCK", str(lock))
             ms = dev_search(50, 3, METRIC_MAXPRO, total)
             print(f"lock={lock} G={G} cands/CTA={cands} threads={G*cands}: {ms:.2f} ms = {total/ms/1e6:.3f} Gcand/s", flush=True)
     sys.exit(0)

@@ -3,7 +3,7 @@ cluster barriers (order_cluster.cu).  usage: order_stress.py [seconds]"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine
+from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, _lib, engine
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 45.0
 rng = np.random.default_rng(7)
@@ -15,16 +15,16 @@ while time.time() < t_end:
     if rng.random() < 0.3:  # a grid: exact ties everywhere
         x = np.round(x * 8) / 8
     metric, mini = ((METRIC_MAXPRO, True), (METRIC_MAXIMIN, False), (METRIC_MAXIMIN, True), (METRIC_MAXPRO, False))[int(rng.integers(0, 4))]
-    os.environ["MAXPRO_ORDER_CLUSTER_SYNC"] = "1"
+    _lib.debug_set("MAXPRO_ORDER_CLUSTER_SYNC", "1")
     _, ref = engine.order_design(x, metric, mini)
-    del os.environ["MAXPRO_ORDER_CLUSTER_SYNC"]
+    _lib.debug_set("MAXPRO_ORDER_CLUSTER_SYNC", None)
     for ctas in ("8", "16"):
-        os.environ["MAXPRO_ORDER_CLUSTER_CTAS"] = ctas
+        _lib.debug_set("MAXPRO_ORDER_CLUSTER_CTAS", ctas)
         for _ in range(3):
             _, p = engine.order_design(x, metric, mini)
             runs += 1
             if p.tolist() != ref.tolist():
                 bad += 1
                 print(f"MISMATCH n={n} d={d} metric={metric} minimize={mini} ctas={ctas}", flush=True)
-    del os.environ["MAXPRO_ORDER_CLUSTER_CTAS"]
+    _lib.debug_set("MAXPRO_ORDER_CLUSTER_CTAS", None)
 print(f"order stress: {runs} runs, {bad} mismatches")
