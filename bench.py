@@ -106,9 +106,10 @@ def host_info():
     return {"nproc": os.cpu_count(), "cpu_model": model}
 
 
-def cpu_rate(seconds_target: float, lo0: int):
+def cpu_rate(seconds_target: float, lo0: int, stream_version: int = 2):
     """Oracle port of build_lhd's map+reduce on the host cores; bounded sample."""
     import oracle
+    oracle.set_stream_version(stream_version)
     oracle.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     probe = 100_000
@@ -126,6 +127,7 @@ def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     import oracle
+    oracle.set_stream_version(args.stream_version)
     oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     cores = oracle.num_threads()
     probe = 200_000
@@ -165,6 +167,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--candidates", type=int, default=CANDIDATES_PER_GPU, help="candidates per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stream-version", type=int, default=2, choices=[1, 2],
+                    help="design stream: 2 = LHD-mix v2 (default), 1 = LHD-Philox v1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +201,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: maxpro_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     _lib.set_device(local_rank)
+    _lib.set_stream_version(args.stream_version)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -363,7 +368,7 @@ def main():
         "fp32_screen": fp32_screen,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sample, dt, cores = cpu_rate(15.0, 1 << 40)
+        rate, sample, dt, cores = cpu_rate(15.0, 1 << 40, args.stream_version)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{sample} candidates (n=50, d=3, MaxPro) in {dt:.1f} s, OpenMP over candidates, "
                                           f"{host_info()['cpu_model']}"}

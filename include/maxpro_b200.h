@@ -60,6 +60,13 @@ typedef enum {
 /* ---- housekeeping ------------------------------------------------------ */
 MAXPRO_API const char *maxpro_last_error(void);
 MAXPRO_API const char *maxpro_version(void);
+/* The design stream generate_lhd / build_lhd draw from (the reference's rand 0.9.2 StdRng stream is not pinned
+ * by any reference test, so the engine defines its own): 2 = LHD-mix v2, the default --
+ * one Philox4x32-10 call per column for the key, a 32-bit multiply-xorshift mixer per element; 1 = LHD-Philox
+ * v1, the stream of the first release (one Philox call per two elements).  Process-wide.  Every kernel, the
+ * winner regeneration and the CPU oracle implement both; a seed names different designs under the two. */
+MAXPRO_API int maxpro_set_stream_version(int version);
+MAXPRO_API int maxpro_get_stream_version(int *version);
 MAXPRO_API int maxpro_device_count(int *count);
 MAXPRO_API int maxpro_set_device(int device);
 MAXPRO_API int maxpro_get_device(int *device);
@@ -94,7 +101,7 @@ MAXPRO_API int maxpro_anneal_scratch_bytes(uint64_t n, uint64_t d, int metric, i
 
 /* lhd::generate_lhd(n_samples, n_dim, &mut StdRng::seed_from_u64(seed))  -- src/lhd.rs:97-132
  * (py: generate_lhd, src/lhd.rs:189-213).  n == 0 writes nothing and returns OK
- * (lhd.rs:98-101); d == 0 is MAXPRO_ERR_INVALID (lhd.rs:106).  Stream = LHD-Philox v1
+ * (lhd.rs:98-101); d == 0 is MAXPRO_ERR_INVALID (lhd.rs:106).  Stream = maxpro_set_stream_version,
  * keyed by `seed`; every column is a permutation of the n strata. */
 MAXPRO_API int maxpro_generate_lhd(uint64_t n, uint64_t d, uint64_t seed, double *out);
 

@@ -28,7 +28,8 @@ EXPORTS = [
     "maxpro_search_workspace_bytes", "maxpro_search_range_device",
     "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe",
     "maxpro_release_device_cache", "maxpro_set_device_cache_limit", "maxpro_set_devices", "maxpro_get_devices",
-    "maxpro_anneal_scratch_bytes", "maxpro_debug_set", "maxpro_debug_pow",
+    "maxpro_anneal_scratch_bytes", "maxpro_debug_set", "maxpro_debug_pow", "maxpro_set_stream_version",
+    "maxpro_get_stream_version",
 ]
 
 
@@ -66,6 +67,8 @@ def lib() -> C.CDLL:
         "maxpro_set_devices": (i32, [C.POINTER(i32), i32]),
         "maxpro_get_devices": (i32, [C.POINTER(i32), i32, C.POINTER(i32)]),
         "maxpro_anneal_scratch_bytes": (i32, [u64, u64, i32, i32, u64, szp]),
+        "maxpro_set_stream_version": (i32, [i32]),
+        "maxpro_get_stream_version": (i32, [C.POINTER(i32)]),
         "maxpro_debug_set": (i32, [C.c_char_p, C.c_char_p]),
         "maxpro_debug_pow": (i32, [dp, dp, u64, dp]),
         "maxpro_generate_lhd": (i32, [u64, u64, u64, dp]),
@@ -129,6 +132,17 @@ def get_devices() -> list:
     arr = (C.c_int * 64)()
     check(lib().maxpro_get_devices(arr, 64, C.byref(n)))
     return [arr[i] for i in range(min(n.value, 64))]
+
+
+def set_stream_version(version: int) -> None:
+    """Design stream: 2 = LHD-mix v2 (default), 1 = LHD-Philox v1."""
+    check(lib().maxpro_set_stream_version(version))
+
+
+def get_stream_version() -> int:
+    v = C.c_int(0)
+    check(lib().maxpro_get_stream_version(C.byref(v)))
+    return v.value
 
 
 def debug_set(name: str, value) -> None:

@@ -228,7 +228,7 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");
     if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
     if (hi < lo) return fail(MAXPRO_ERR_INVALID, "search range is inverted");
-    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the LHD-Philox v1 stratum-exactness bound");
+    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the stratum-exactness bound of the design streams");
     SearchWs w = carve_search_ws(d_ws, n, d);
     if (ws_bytes < w.total) return fail(MAXPRO_ERR_INVALID, "workspace smaller than maxpro_search_workspace_bytes");
     BestRec* result = static_cast<BestRec*>(d_result);
@@ -584,7 +584,19 @@ int criterion_host(const double* design, uint64_t n, uint64_t d, int metric, dou
 extern "C" {
 
 const char* maxpro_last_error(void) { return g_err.c_str(); }
-const char* maxpro_version(void) { return "maxpro_b200 0.1.0 (sm_100a; LHD-Philox v1)"; }
+const char* maxpro_version(void) { return "maxpro_b200 0.2.0 (sm_100a; design streams: LHD-mix v2 (default), LHD-Philox v1)"; }
+
+int maxpro_set_stream_version(int version) {
+    if (version != 1 && version != 2) return fail(MAXPRO_ERR_INVALID, "stream version must be 1 (LHD-Philox v1) or 2 (LHD-mix v2)");
+    mp::set_stream_version(version);
+    return MAXPRO_OK;
+}
+
+int maxpro_get_stream_version(int* version) {
+    if (!version) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    *version = mp::stream_version();
+    return MAXPRO_OK;
+}
 uint64_t maxpro_kernel_launch_count(void) { return mp::g_launches.load(std::memory_order_relaxed); }
 
 int maxpro_release_device_cache(uint64_t* bytes) {
@@ -661,7 +673,7 @@ int maxpro_generate_lhd(uint64_t n, uint64_t d, uint64_t seed, double* out) {
     if (n == 0) return MAXPRO_OK;  // lhd.rs:98-101
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be a positive, nonzero integer");  // lhd.rs:106
     if (!out) return fail(MAXPRO_ERR_INVALID, "null pointer");
-    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the LHD-Philox v1 stratum-exactness bound");
+    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the stratum-exactness bound of the design streams");
     if (int rc = ensure_device()) return rc;
     DevBuf buf;
     CUDA_TRY(buf.alloc(n * d * sizeof(double)));
@@ -677,7 +689,7 @@ int maxpro_generate_batch(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, ui
     if (n == 0 || count == 0) return MAXPRO_OK;
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be a positive, nonzero integer");
     if (!out) return fail(MAXPRO_ERR_INVALID, "null pointer");
-    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the LHD-Philox v1 stratum-exactness bound");
+    if (n > (1ull << 18)) return fail(MAXPRO_ERR_UNSUPPORTED, "n_samples above 262144 is outside the stratum-exactness bound of the design streams");
     if (int rc = ensure_device()) return rc;
     DevBuf buf;
     size_t bytes = count * n * d * sizeof(double);

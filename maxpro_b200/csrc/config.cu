@@ -5,6 +5,7 @@
 // variants.  They are set through the test-only entry point maxpro_debug_set(); MAXPRO_* environment variables
 // are read ONCE, when the library first looks at a switch, never per call -- an environment that changes
 // later cannot change which kernel serves a call or how large its workspace is.
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -40,6 +41,10 @@ const char* cfg(const char* name) {
     auto it = g_cfg.find(name);
     return it == g_cfg.end() ? nullptr : it->second.c_str();
 }
+
+static std::atomic<int> g_stream_version{2};
+int stream_version() { return g_stream_version.load(std::memory_order_relaxed); }
+void set_stream_version(int v) { g_stream_version.store(v, std::memory_order_relaxed); }
 
 void cfg_set(const char* name, const char* value) {
     std::lock_guard<std::mutex> lock(g_cfg_mutex);

@@ -69,6 +69,83 @@ __device__ __forceinline__ double stratum_value(uint32_t i, uint32_t jit, double
     return fma(__ull2double_rn(m), c1, c0);
 }
 
+// ---- LHD-mix v2: the design stream with the generator off the FP64 issue path ---------------------------
+// v1 spends one Philox4x32-10 call (20 wide multiplies, 20 three-input logic ops) on every TWO elements, and in
+// the fused search kernels those instructions do not hide behind the FP64 stream: they were 15 % of the headline
+// kernel's time (profiles/README.md, r1g).  v2 keeps Philox where it buys independence between streams -- ONE call
+// per column, keyed by (stream id, column) -- and draws the elements of a column from a counter-based 32-bit
+// mixer under that key:
+//     {A, B} = Philox4x32-10(ctr = {k, "LHD2", s_lo, s_hi}, key = {kKeyLhd0, kKeyLhd1}).{x, y | 1}
+//     w_i    = mix32(A + i * B)            mix32: x ^= x>>16; x *= 0x21f0aaad; x ^= x>>15; x *= 0x735a2d97; x ^= x>>15
+//     P      = w_i * (i + 1)               (64 bits)
+//     j_i    = P >> 32                     the Fisher-Yates index in [0, i], bias (i+1) 2^-32
+//     jit_i  = P mod 2^32                  the fractional part of w_i (i+1) 2^-32: uniform and independent of j_i
+//     v_i    = (i + (jit_i + 1/2) 2^-32) / n,  evaluated as  fma(2^52 + (i 2^32 + jit_i), c1, c0'),
+//              c1 = 2^-32 / n,  c0' = c1/2 - 2^52 c1:  the integer is written into the mantissa of 2^52 (one
+//              integer op instead of a 64-bit int -> double conversion); floor(v_i n) == i for every draw, n <= 2^18.
+// mix32 is the two-round multiply-xorshift finaliser with the constants of C. Wellons' hash-prospector search
+// (avalanche bias 0.10); A + i B is a Weyl sequence with a per-column odd step.  Per element: 2 multiplies, one
+// wide multiply and 6 shift/logic ops instead of 10 wide multiplies and 10 logic ops.  tests/test_oracle.py holds
+// the statistics (uniformity of every j_i, of adjacent pairs, of whole permutations for small n, KS of the jitter).
+constexpr uint32_t kLhd2Tag = 0x4C484432u;  // "LHD2"
+
+__host__ __device__ __forceinline__ uint32_t lhd2_mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x21f0aaadu;
+    x ^= x >> 15;
+    x *= 0x735a2d97u;
+    x ^= x >> 15;
+    return x;
+}
+
+// one column's key: a = start, b = odd step of the Weyl sequence fed to the mixer
+__host__ __device__ __forceinline__ void lhd2_column_key(uint32_t k, uint32_t s_lo, uint32_t s_hi, uint32_t& a, uint32_t& b) {
+    const Philox4 w = philox4x32_10(k, kLhd2Tag, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+    a = w.x;
+    b = w.y | 1u;
+}
+
+// element i of the column: Fisher-Yates index j in [0, i] and jitter word
+__host__ __device__ __forceinline__ void lhd2_element(uint32_t a, uint32_t b, uint32_t i, uint32_t& j, uint32_t& jit) {
+    mulhilo32(lhd2_mix32(a + i * b), i + 1u, j, jit);
+}
+
+// host: the additive constant of the v2 value formula (see above); c1 = ldexp(1.0 / n, -32)
+__host__ __device__ __forceinline__ double lhd2_c0(double c1) { return 0.5 * c1 - 0x1p52 * c1; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double lhd2_value(uint32_t i, uint32_t jit, double c1, double c0p) {
+    return fma(__hiloint2double((int)(0x43300000u | i), (int)jit), c1, c0p);
+}
+
+// ---- version-independent front end used by every generator in the engine ---------------------------------------
+// gen = 1: LHD-Philox v1, gen = 2: LHD-mix v2.  A draw block is the element pair (2b, 2b+1) of column k.
+struct LhdBlock { uint32_t j0, jit0, j1, jit1; };
+struct LhdKeyCache { uint32_t k, a, b; };  // v2: the key of the column a thread drew from last (k = ~0: none yet)
+
+__device__ __forceinline__ LhdBlock lhd_draw_block(int gen, uint32_t b, uint32_t k, uint32_t s_lo, uint32_t s_hi, LhdKeyCache& kc) {
+    LhdBlock r;
+    if (gen == 1) {
+        const Philox4 w = philox4x32_10(b, k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+        r.jit0 = w.x; r.j0 = __umulhi(w.y, 2u * b + 1u);
+        r.jit1 = w.z; r.j1 = __umulhi(w.w, 2u * b + 2u);
+    } else {
+        if (kc.k != k) { kc.k = k; lhd2_column_key(k, s_lo, s_hi, kc.a, kc.b); }
+        lhd2_element(kc.a, kc.b, 2u * b, r.j0, r.jit0);
+        lhd2_element(kc.a, kc.b, 2u * b + 1u, r.j1, r.jit1);
+    }
+    return r;
+}
+#endif
+
+#ifdef __CUDACC__
+// v_i of either stream; c0 is the version's additive constant (host: lhd_c0)
+__device__ __forceinline__ double lhd_value(int gen, uint32_t i, uint32_t jit, double c1, double c0) {
+    return gen == 1 ? stratum_value(i, jit, c1, c0) : lhd2_value(i, jit, c1, c0);
+}
+#endif
+inline double lhd_c0(int gen, double c1) { return gen == 1 ? 0.5 * c1 : lhd2_c0(c1); }
+
 // The sequential half of the inside-out Fisher-Yates shuffle for one column whose draws were staged
 // beforehand: a[i] holds the stratum value v_i and js[i] the index drawn for step i, and step i does
 //   t = a[j_i];  a[i] = t;  a[j_i] = v_i.

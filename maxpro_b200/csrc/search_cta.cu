@@ -29,6 +29,7 @@ namespace mp {
 
 constexpr int kCtaThreads = 128;
 struct CtaParams {
+    int gen;       // design stream version (philox.cuh)
     int n, d, ns;  // ns = row stride of the [k][i] layout (cta_row_stride)
     unsigned long long seed, lo, hi;
     double c1, c0, n_pairs, inv_d;
@@ -44,20 +45,21 @@ __host__ __device__ __forceinline__ unsigned long long cta_row_stride(unsigned l
 
 // Generation phase 1 for one candidate: every thread runs Philox for its share of the (column,
 // element-pair) blocks and stages v_i at a[i] and the Fisher-Yates index j_i in the side array.
-__device__ __forceinline__ void cta_stage_candidate(double* xs, unsigned short* jst, int n, int d, int ns, uint32_t s_lo, uint32_t s_hi,
+__device__ __forceinline__ void cta_stage_candidate(int gen, double* xs, unsigned short* jst, int n, int d, int ns, uint32_t s_lo, uint32_t s_hi,
                                                     double c1, double c0, int tid, int nthreads) {
     const int nb = (n + 1) / 2;
+    LhdKeyCache kc{0xFFFFFFFFu, 0u, 0u};
     // block q <-> (column k, element pair b), walked without a division
     int k = 0, b = tid;
     while (b >= nb && k < d) { b -= nb; ++k; }
     while (k < d) {
-        Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+        const LhdBlock w = lhd_draw_block(gen, (uint32_t)b, (uint32_t)k, s_lo, s_hi, kc);
         const int i = 2 * b;
-        xs[k * ns + i] = stratum_value((uint32_t)i, w.x, c1, c0);
-        jst[k * ns + i] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
+        xs[k * ns + i] = lhd_value(gen, (uint32_t)i, w.jit0, c1, c0);
+        jst[k * ns + i] = (unsigned short)w.j0;
         if (i + 1 < n) {
-            xs[k * ns + i + 1] = stratum_value((uint32_t)i + 1u, w.z, c1, c0);
-            jst[k * ns + i + 1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
+            xs[k * ns + i + 1] = lhd_value(gen, (uint32_t)i + 1u, w.jit1, c1, c0);
+            jst[k * ns + i + 1] = (unsigned short)w.j1;
         }
         b += nthreads;
         while (b >= nb && k < d) { b -= nb; ++k; }
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         __syncthreads();  // previous candidate fully consumed
-        cta_stage_candidate(xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, kCtaThreads);
+        cta_stage_candidate(p.gen, xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, kCtaThreads);
         __syncthreads();
         cta_walk_columns(xs, jst, n, d, ns, tid, kCtaThreads);
         __syncthreads();
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
     unsigned long long idx = p.lo + blockIdx.x;
     if (idx < p.hi) {  // prologue: the first candidate, nothing to overlap it with
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
-        cta_stage_candidate(xbase, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
+        cta_stage_candidate(p.gen, xbase, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
         __syncthreads();
         cta_walk_columns(xbase, jst, n, d, ns, tid, kPipeThreads);
     }
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
         // the side array is free (the previous walk ended before the last barrier) and so is the other buffer
         if (has_next) {
             const unsigned long long stream = p.seed + nidx;
-            cta_stage_candidate(xbase + (cur ^ 1) * xstride, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
+            cta_stage_candidate(p.gen, xbase + (cur ^ 1) * xstride, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
         }
         if (tid == 0) next_item = 0;
         __syncthreads();  // staged values visible to the walker; buffer `cur` complete; counter armed
@@ -239,8 +241,9 @@ cudaError_t launch_search_cta(const SearchLaunch& L) {
     CtaParams p;
     p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)cta_row_stride(L.n);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
+    p.gen = stream_version();
     p.c1 = ldexp(1.0 / (double)L.n, -32);
-    p.c0 = 0.5 * p.c1;
+    p.c0 = lhd_c0(p.gen, p.c1);
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;

@@ -26,6 +26,7 @@
 namespace mp {
 
 struct CyclicParams {
+    int gen;   // design stream version (philox.cuh)
     int ring;  // warps per sub-partition that take turns on the FP64 pipe (0 = no turn-taking)
     unsigned long long seed, lo, hi;
     // list mode (stage 2 of the fp32-screened search): score list[0..list_count) instead of lo..hi
@@ -76,28 +77,45 @@ __device__ __forceinline__ void load_row_at(double (&dst)[D], const unsigned cha
         dst[k] = *reinterpret_cast<const double*>(cand + row_off + k * Layout<N, D, C>::kDimBytes);
 }
 
-// One Fisher-Yates step of the inside-out shuffle: element i gets jitter word `jit`, index word `idx`.
+// One Fisher-Yates step of the inside-out shuffle: a[i] = a[j]; a[j] = v.
 template <int N, int D, int C>
-__device__ __forceinline__ void cyc_fy_step(unsigned char* col, int i, uint32_t jit, uint32_t idx, double c1, double c0) {
+__device__ __forceinline__ void cyc_fy_step(unsigned char* col, int i, uint32_t j, double v) {
     constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
-    const uint32_t j = __umulhi(idx, (uint32_t)i + 1u);
-    const double v = stratum_value((uint32_t)i, jit, c1, c0);
     *reinterpret_cast<double*>(col + i * RB) = *reinterpret_cast<double*>(col + j * RB);
     *reinterpret_cast<double*>(col + j * RB) = v;
 }
 
-// Philox blocks [b0, b0 + count) of one column: two Fisher-Yates steps per block.  `col`, `k`
+// Draw blocks [b0, b0 + count) of one column: two Fisher-Yates steps per block.  `col`, `k`
 // and `b0` may differ between the two lanes of a candidate; `count` is uniform.
-template <int N, int D, int C>
+// GEN = 1: LHD-Philox v1, one Philox call per block.  GEN = 2: LHD-mix v2 (philox.cuh), one Philox call per
+// column segment for the key, then a multiply-xorshift mix of a Weyl sequence per element.
+template <int N, int D, int C, int GEN>
 __device__ __forceinline__ void cyc_generate_blocks(unsigned char* col, uint32_t k, int b0, int count, uint32_t s_lo,
                                                     uint32_t s_hi, double c1, double c0) {
+    if (GEN == 1) {
 #pragma unroll 2
-    for (int t = 0; t < count; ++t) {
-        const int b = b0 + t;
-        const Philox4 w = philox4x32_10((uint32_t)b, k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
-        const int i = 2 * b;
-        if (i < N) cyc_fy_step<N, D, C>(col, i, w.x, w.y, c1, c0);
-        if (i + 1 < N) cyc_fy_step<N, D, C>(col, i + 1, w.z, w.w, c1, c0);
+        for (int t = 0; t < count; ++t) {
+            const int b = b0 + t;
+            const Philox4 w = philox4x32_10((uint32_t)b, k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+            const int i = 2 * b;
+            if (i < N) cyc_fy_step<N, D, C>(col, i, __umulhi(w.y, (uint32_t)i + 1u), stratum_value((uint32_t)i, w.x, c1, c0));
+            if (i + 1 < N) cyc_fy_step<N, D, C>(col, i + 1, __umulhi(w.w, (uint32_t)i + 2u), stratum_value((uint32_t)i + 1u, w.z, c1, c0));
+        }
+    } else {
+        uint32_t ka, kb;
+        lhd2_column_key(k, s_lo, s_hi, ka, kb);
+        uint32_t x = ka + (uint32_t)(2 * b0) * kb;  // Weyl sequence A + i B, stepped instead of multiplied
+#pragma unroll 2
+        for (int t = 0; t < count; ++t) {
+            const int i = 2 * (b0 + t);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                uint32_t j, jit;
+                mulhilo32(lhd2_mix32(x), (uint32_t)(i + e) + 1u, j, jit);
+                x += kb;
+                if (i + e < N) cyc_fy_step<N, D, C>(col, i + e, j, lhd2_value((uint32_t)(i + e), jit, c1, c0));
+            }
+        }
     }
 }
 
@@ -106,7 +124,7 @@ __device__ __forceinline__ void cyc_generate_blocks(unsigned char* col, uint32_t
 // 0..h-1) and then does column 0; lane 1 does column 1 and then finishes the third column
 // (blocks h..) -- by then lane 0 has long left it (a __syncwarp orders the hand-over).
 // 38 block iterations per lane instead of 50.
-template <int N, int C>
+template <int N, int C, int GEN>
 __device__ __forceinline__ void cyc_generate_three(unsigned char* cand, uint32_t s_lo, uint32_t s_hi, double c1, double c0,
                                                    int g, unsigned int group_mask) {
     constexpr int D = 3;
@@ -114,12 +132,12 @@ __device__ __forceinline__ void cyc_generate_three(unsigned char* cand, uint32_t
     constexpr unsigned DB = Layout<N, D, C>::kDimBytes;
     static_assert(NB - H <= NB && H <= NB, "hand-over happens after lane 0 is done with column 2");
     // stage 1 (H iterations): lane 0 -> column 2 blocks [0,H); lane 1 -> column 1 blocks [0,H)
-    cyc_generate_blocks<N, D, C>(cand + (g ? 1u : 2u) * DB, g ? 1u : 2u, 0, H, s_lo, s_hi, c1, c0);
+    cyc_generate_blocks<N, D, C, GEN>(cand + (g ? 1u : 2u) * DB, g ? 1u : 2u, 0, H, s_lo, s_hi, c1, c0);
     // stage 2 (NB-H iterations): lane 0 -> column 0 blocks [0,NB-H); lane 1 -> column 1 blocks [H,NB)
-    cyc_generate_blocks<N, D, C>(cand + (g ? 1u : 0u) * DB, g ? 1u : 0u, g ? H : 0, NB - H, s_lo, s_hi, c1, c0);
+    cyc_generate_blocks<N, D, C, GEN>(cand + (g ? 1u : 0u) * DB, g ? 1u : 0u, g ? H : 0, NB - H, s_lo, s_hi, c1, c0);
     __syncwarp(group_mask);  // column 2's first half is in place before lane 1 continues it
     // stage 3 (H iterations): lane 0 -> column 0 blocks [NB-H,NB); lane 1 -> column 2 blocks [H,NB) (+ one idle)
-    cyc_generate_blocks<N, D, C>(cand + (g ? 2u : 0u) * DB, g ? 2u : 0u, g ? H : NB - H, H, s_lo, s_hi, c1, c0);
+    cyc_generate_blocks<N, D, C, GEN>(cand + (g ? 2u : 0u) * DB, g ? 2u : 0u, g ? H : NB - H, H, s_lo, s_hi, c1, c0);
 }
 
 // One tile of the cyclic schedule: R rows against the lane's KP shifts.  The R + KP - 1 partner rows
@@ -276,7 +294,7 @@ __device__ __forceinline__ void cyc_token_pass(int id) { asm volatile("bar.arriv
 // from 2.07 to 3.56 cycles per instruction), so the two phases cost their sum however they are
 // arranged, and a lone scoring warp reaches only ~62% of the pipe.  Kept as an experiment switch
 // (MAXPRO_CYCLIC_RING), off by default.
-template <int N, int D, int C, bool MAXPRO, bool SUPPLIED = false>
+template <int N, int D, int C, bool MAXPRO, bool SUPPLIED = false, int GEN = 2>
 __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int G = 2, kPerWarp = 16;
@@ -316,11 +334,11 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
             in_cube = cyc_load_design<N, D, C>(cand, p.designs + idx * (unsigned long long)(N * D), g);
         } else if (active) {
             if (D == 3) {
-                cyc_generate_three<N, C>(cand, s_lo, s_hi, p.c1, p.c0, g, group_mask);
+                cyc_generate_three<N, C, GEN>(cand, s_lo, s_hi, p.c1, p.c0, g, group_mask);
             } else {
 #pragma unroll 1
                 for (int k = g; k < D; k += G)
-                    cyc_generate_blocks<N, D, C>(cand + (size_t)k * Layout<N, D, C>::kDimBytes, (uint32_t)k, 0, (N + 1) / 2, s_lo, s_hi, p.c1, p.c0);
+                    cyc_generate_blocks<N, D, C, GEN>(cand + (size_t)k * Layout<N, D, C>::kDimBytes, (uint32_t)k, 0, (N + 1) / 2, s_lo, s_hi, p.c1, p.c0);
             }
         }
         __syncwarp(group_mask);
@@ -364,7 +382,8 @@ static cudaError_t launch_cyclic_nd(const SearchLaunch& L, const CyclicParams& p
         return cudaGetLastError();
     };
     if (p.designs) return L.metric == 0 ? go(search_cyclic_kernel<N, D, C, true, true>) : go(search_cyclic_kernel<N, D, C, false, true>);
-    return L.metric == 0 ? go(search_cyclic_kernel<N, D, C, true, false>) : go(search_cyclic_kernel<N, D, C, false, false>);
+    if (p.gen == 1) return L.metric == 0 ? go(search_cyclic_kernel<N, D, C, true, false, 1>) : go(search_cyclic_kernel<N, D, C, false, false, 1>);
+    return L.metric == 0 ? go(search_cyclic_kernel<N, D, C, true, false, 2>) : go(search_cyclic_kernel<N, D, C, false, false, 2>);
 }
 
 // Shapes with a specialised instantiation; *cands = candidates per CTA.
@@ -385,8 +404,9 @@ cudaError_t launch_search_cyclic(const SearchLaunch& L) {
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.list = L.list; p.list_count = L.list_count;
     p.designs = L.designs; p.scores = L.scores;
+    p.gen = stream_version();
     p.c1 = ldexp(1.0 / (double)L.n, -32);
-    p.c0 = 0.5 * p.c1;
+    p.c0 = lhd_c0(p.gen, p.c1);
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;

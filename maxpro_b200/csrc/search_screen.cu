@@ -28,6 +28,7 @@
 namespace mp {
 
 struct ScreenParams {
+    int gen;                         // design stream version (philox.cuh)
     unsigned long long seed, lo, hi;
     float inv_n;                     // 1/n
     unsigned long long* survivors;   // [gridDim.x * warps per CTA] candidate indices (kNoIndex = none)
@@ -81,15 +82,16 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
         for (int k = 0; k < D; ++k) {
             unsigned char* col = cand + k * DB;
             const float scale = (MAXPRO && k == 0) ? p.inv_n * kScale : p.inv_n;
+            LhdKeyCache kc{0xFFFFFFFFu, 0u, 0u};
 #pragma unroll 2
             for (int b = 0; b < (N + 1) / 2; ++b) {
-                const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
-                const uint32_t jit[2] = {w.x, w.z}, ix[2] = {w.y, w.w};
+                const LhdBlock w = lhd_draw_block(p.gen, (uint32_t)b, (uint32_t)k, s_lo, s_hi, kc);
+                const uint32_t jit[2] = {w.jit0, w.jit1}, jx[2] = {w.j0, w.j1};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int i = 2 * b + e;
                     if (i < N) {
-                        const uint32_t j = __umulhi(ix[e], (uint32_t)i + 1u);
+                        const uint32_t j = jx[e];
                         const float v = (fmaf((float)jit[e], 0x1p-32f, 0x1p-33f) + (float)i) * scale;
                         *reinterpret_cast<float*>(col + i * RB) = *reinterpret_cast<float*>(col + j * RB);
                         *reinterpret_cast<float*>(col + j * RB) = v;
@@ -197,6 +199,7 @@ bool search_screen_supported(unsigned long long n, unsigned long long d, int* ca
 // survivors: [L.grid * (cands/32)] indices
 cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* survivors) {
     ScreenParams p;
+    p.gen = stream_version();
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.inv_n = 1.0f / (float)L.n;
     p.survivors = survivors;

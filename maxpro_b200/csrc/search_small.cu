@@ -34,6 +34,7 @@ namespace mp {
 
 struct SearchParams {
     int n;
+    int gen;              // design stream version (philox.cuh)
     unsigned long long seed, lo, hi;
     double c1, c0;        // 2^-32/n and 2^-33/n : v = (i + (jit+0.5)*2^-32)/n
     double n_pairs, inv_d;
@@ -66,23 +67,20 @@ __device__ __forceinline__ double sqdist_term(const double (&a)[D], const double
 
 // One column of generate_lhd: inside-out Fisher-Yates over the strata, the
 // in-stratum jitter attached to the value being placed.
-__device__ __forceinline__ void generate_column(double* col, int stride, int n, uint32_t k,
+__device__ __forceinline__ void generate_column(int gen, double* col, int stride, int n, uint32_t k,
                                                 uint32_t s_lo, uint32_t s_hi, double c1, double c0) {
+    LhdKeyCache kc{0xFFFFFFFFu, 0u, 0u};
     for (int i = 0; i < n; i += 2) {
-        Philox4 w = philox4x32_10((uint32_t)(i >> 1), k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+        const LhdBlock w = lhd_draw_block(gen, (uint32_t)(i >> 1), k, s_lo, s_hi, kc);
         {
-            uint32_t j = mulhi_bound(w.y, (uint32_t)i + 1u);
-            unsigned long long m = ((unsigned long long)(uint32_t)i << 32) | w.x;
-            double v = fma((double)m, c1, c0);
-            col[i * stride] = col[j * stride];
-            col[j * stride] = v;
+            const double v = lhd_value(gen, (uint32_t)i, w.jit0, c1, c0);
+            col[i * stride] = col[w.j0 * stride];
+            col[w.j0 * stride] = v;
         }
         if (i + 1 < n) {
-            uint32_t j = mulhi_bound(w.w, (uint32_t)i + 2u);
-            unsigned long long m = ((unsigned long long)(uint32_t)(i + 1) << 32) | w.z;
-            double v = fma((double)m, c1, c0);
-            col[(i + 1) * stride] = col[j * stride];
-            col[j * stride] = v;
+            const double v = lhd_value(gen, (uint32_t)i + 1u, w.jit1, c1, c0);
+            col[(i + 1) * stride] = col[w.j1 * stride];
+            col[w.j1 * stride] = v;
         }
     }
 }
@@ -259,7 +257,7 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
         if (active) {
 #pragma unroll 1
             for (int k = g; k < D; k += G)
-                generate_column(xs + (size_t)k * n * C, C, n, (uint32_t)k, s_lo, s_hi, p.c1, p.c0);
+                generate_column(p.gen, xs + (size_t)k * n * C, C, n, (uint32_t)k, s_lo, s_hi, p.c1, p.c0);
         }
         if (G > 1) __syncwarp(group_mask);
         if (LOCK) token_wait(tok_in);
@@ -370,8 +368,9 @@ cudaError_t launch_search_small(const SearchLaunch& L) {
     SearchParams p;
     p.n = (int)L.n;
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
+    p.gen = stream_version();
     p.c1 = ldexp(1.0 / (double)L.n, -32);
-    p.c0 = 0.5 * p.c1;
+    p.c0 = lhd_c0(p.gen, p.c1);
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;

@@ -35,6 +35,7 @@ constexpr int kWarpCtaThreads = 128;  // 4 candidates per CTA, up to 4 CTAs per 
 constexpr int kWarpSB = 8;            // shifts per work item
 
 struct WarpParams {
+    int gen;       // design stream version (philox.cuh)
     int n, d, ns;  // ns = row stride of the [k][i] layout: n + copied rows, even (16-byte loads), 2 or 10 mod 16 (the column walkers hit different banks)
     unsigned int cand_bytes;  // shared memory of one candidate slot
     unsigned long long seed, lo, hi;
@@ -73,16 +74,17 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
         {
             int k = 0, b = lane;
             while (b >= nb) { b -= nb; ++k; }
+            LhdKeyCache kc{0xFFFFFFFFu, 0u, 0u};
             while (k < d) {
-                Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+                const LhdBlock w = lhd_draw_block(p.gen, (uint32_t)b, (uint32_t)k, s_lo, s_hi, kc);
                 const int i = 2 * b;
                 double* col = xs + k * ns + i;
                 unsigned short* jc = jst + k * n + i;
-                col[0] = stratum_value((uint32_t)i, w.x, p.c1, p.c0);
-                jc[0] = (unsigned short)mulhi_bound(w.y, (uint32_t)i + 1u);
+                col[0] = lhd_value(p.gen, (uint32_t)i, w.jit0, p.c1, p.c0);
+                jc[0] = (unsigned short)w.j0;
                 if (i + 1 < n) {
-                    col[1] = stratum_value((uint32_t)(i + 1), w.z, p.c1, p.c0);
-                    jc[1] = (unsigned short)mulhi_bound(w.w, (uint32_t)i + 2u);
+                    col[1] = lhd_value(p.gen, (uint32_t)(i + 1), w.jit1, p.c1, p.c0);
+                    jc[1] = (unsigned short)w.j1;
                 }
                 b += 32;
                 while (b >= nb) { b -= nb; ++k; }
@@ -236,8 +238,9 @@ cudaError_t launch_search_warp(const SearchLaunch& L) {
     p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)warp_row_stride(L.n);
     p.cand_bytes = warp_cand_bytes(L.n, L.d);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
+    p.gen = stream_version();
     p.c1 = ldexp(1.0 / (double)L.n, -32);
-    p.c0 = 0.5 * p.c1;
+    p.c0 = lhd_c0(p.gen, p.c1);
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
     p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;

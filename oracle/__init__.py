@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         L.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.oracle_generate_lhd.restype = i32
         L.oracle_generate_lhd.argtypes = [u64, u64, u64, dp]
+        L.oracle_generate_batch.restype = i32
+        L.oracle_generate_batch.argtypes = [u64, u64, u64, u64, u64, dp]
         L.oracle_search_range.restype = i32
         L.oracle_search_range.argtypes = [u64, u64, i32, u64, u64, u64, dp, u64p]
         L.oracle_build_lhd.restype = i32
@@ -66,11 +68,23 @@ def lib() -> C.CDLL:
         L.oracle_order_design.argtypes = [dp, u64, u64, i32, i32, dp, u64p]
         L.oracle_order_design_incremental.restype = i32
         L.oracle_order_design_incremental.argtypes = [dp, u64, u64, i32, i32, dp, u64p]
+        L.oracle_set_stream_version.restype = None
+        L.oracle_set_stream_version.argtypes = [i32]
+        L.oracle_get_stream_version.restype = i32
         L.oracle_num_threads.restype = i32
         L.oracle_set_num_threads.restype = None
         L.oracle_set_num_threads.argtypes = [i32]
         _lib = L
     return _lib
+
+
+def set_stream_version(v: int) -> None:
+    """Design stream the oracle generates: 1 = LHD-Philox v1, 2 = LHD-mix v2 (default, as in the engine)."""
+    lib().oracle_set_stream_version(int(v))
+
+
+def get_stream_version() -> int:
+    return int(lib().oracle_get_stream_version())
 
 
 def _dp(a: np.ndarray):
@@ -132,6 +146,14 @@ def generate_lhd(n: int, d: int, stream: int) -> np.ndarray:
     rc = lib().oracle_generate_lhd(n, d, stream & (2**64 - 1), _dp(out))
     if rc:
         raise ValueError(f"oracle_generate_lhd failed rc={rc}")
+    return out
+
+
+def generate_batch(n: int, d: int, seed: int, lo: int, count: int) -> np.ndarray:
+    """count consecutive candidates of the search seeded `seed`, from candidate `lo`: shape (count, n, d)."""
+    out = np.empty((count, n, d), dtype=np.float64)
+    if lib().oracle_generate_batch(n, d, seed & (2 ** 64 - 1), lo, count, _dp(out)):
+        raise ValueError("oracle_generate_batch failed")
     return out
 
 

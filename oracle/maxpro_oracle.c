@@ -16,8 +16,10 @@
  *   - RANDOM STREAM: parity unpinned.  The reference draws from rand 0.9.2
  *     StdRng (ChaCha12; crate not vendored under /root/reference, no
  *     Cargo.lock) and none of its tests pins a stream.  This file instead
- *     defines the "LHD-Philox v1" stream (Philox4x32-10, Random123 KATs) that
- *     the CUDA engine implements independently; generated designs are checked
+ *     defines the two design streams of the engine -- "LHD-Philox v1"
+ *     (Philox4x32-10, Random123 KATs) and "LHD-mix v2" (one Philox call per
+ *     column + a 32-bit mixer per element; the default) -- which the CUDA
+ *     engine implements independently; generated designs are checked
  *     bit-exactly between the two and for LHD validity, not against rand.
  *
  * Compile with -ffp-contract=off: Rust never contracts a*b+c into an FMA.
@@ -33,6 +35,18 @@
 
 #define ORACLE_METRIC_MAXPRO 0
 #define ORACLE_METRIC_MAXIMIN 1
+
+/* design stream version used by oracle_generate_lhd and everything built on it: 1 = LHD-Philox v1,
+ * 2 = LHD-mix v2 (the engine's default) */
+static int g_stream_version = 2;
+void oracle_set_stream_version(int v) { g_stream_version = v == 1 ? 1 : 2; }
+int oracle_get_stream_version(void) { return g_stream_version; }
+int oracle_generate_lhd_v1(uint64_t n, uint64_t d, uint64_t stream, double *out);
+int oracle_generate_lhd_v2(uint64_t n, uint64_t d, uint64_t stream, double *out);
+int oracle_generate_lhd(uint64_t n, uint64_t d, uint64_t stream, double *out)
+{
+    return g_stream_version == 1 ? oracle_generate_lhd_v1(n, d, stream, out) : oracle_generate_lhd_v2(n, d, stream, out);
+}
 
 /* ------------------------------------------------------------------ */
 /* Criteria                                                            */
@@ -160,7 +174,7 @@ void oracle_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], ui
  *     j = (idx * (i+1)) >> 32;  a[i] = a[j];  a[j] = v_i
  *     v_i = (i + (jit + 0.5) * 2^-32) / n   evaluated as ((i<<32|jit) + 0.5) * (2^-32 * (1/n))
  * so that floor(v*n) == i for every draw (no edge rounding into i+1). */
-int oracle_generate_lhd(uint64_t n, uint64_t d, uint64_t stream, double *out)
+int oracle_generate_lhd_v1(uint64_t n, uint64_t d, uint64_t stream, double *out)
 {
     if (n == 0) return 0;              /* :98-101 empty design */
     if (d == 0) return -1;             /* :106 panics */
@@ -186,6 +200,64 @@ int oracle_generate_lhd(uint64_t n, uint64_t d, uint64_t stream, double *out)
     }
     free(col);
     return 0;
+}
+
+/* LHD-mix v2 (the engine's default design stream; maxpro_b200/csrc/philox.cuh has the rationale).
+ * One Philox4x32-10 call per column gives the key, a counter-based 32-bit mixer gives the elements:
+ *     {A, B} = Philox(ctr = {k, "LHD2", s_lo, s_hi}, key = {KEY_LHD0, KEY_LHD1}).{x, y | 1}
+ *     w_i = mix32(A + i*B);  P = w_i * (i+1);  j_i = P >> 32;  jit_i = (uint32)P
+ *     v_i = fma(2^52 + (i*2^32 + jit_i), c1, c0'),  c1 = 2^-32/n,  c0' = c1/2 - 2^52*c1
+ * Same inside-out Fisher-Yates as v1. */
+static uint32_t lhd2_mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x21f0aaadu;
+    x ^= x >> 15; x *= 0x735a2d97u;
+    x ^= x >> 15;
+    return x;
+}
+
+int oracle_generate_lhd_v2(uint64_t n, uint64_t d, uint64_t stream, double *out)
+{
+    if (n == 0) return 0;
+    if (d == 0) return -1;
+    if (n > (1ull << 18)) return -2;
+    const double c1 = ldexp(1.0 / (double)n, -32);
+    const double c0p = 0.5 * c1 - 0x1p52 * c1;
+    const uint32_t key[2] = { KEY_LHD0, KEY_LHD1 };
+    double *col = (double *)malloc(n * sizeof(double));
+    if (!col) return -3;
+    for (uint64_t k = 0; k < d; ++k) {
+        uint32_t ctr[4] = { (uint32_t)k, 0x4C484432u, (uint32_t)stream, (uint32_t)(stream >> 32) };
+        uint32_t w[4];
+        oracle_philox4x32_10(ctr, key, w);
+        const uint32_t a = w[0], b = w[1] | 1u;
+        for (uint64_t i = 0; i < n; ++i) {
+            uint32_t wi = lhd2_mix32(a + (uint32_t)i * b);
+            uint64_t p = (uint64_t)wi * (uint64_t)(i + 1);
+            uint64_t j = p >> 32;
+            uint32_t jit = (uint32_t)p;
+            uint64_t bits = 0x4330000000000000ull | (i << 32) | jit;   /* the double 2^52 + (i*2^32 + jit) */
+            double m;
+            memcpy(&m, &bits, 8);
+            double v = fma(m, c1, c0p);
+            col[i] = col[j];
+            col[j] = v;
+        }
+        for (uint64_t i = 0; i < n; ++i) out[i * d + k] = col[i];
+    }
+    free(col);
+    return 0;
+}
+
+/* `count` consecutive designs of the search seeded `seed`, starting at candidate `lo` (design c is
+ * generate_lhd of stream seed + lo + c, src/lib.rs:70).  Used by the statistical tests of the streams. */
+int oracle_generate_batch(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, uint64_t count, double *out)
+{
+    int status = 0;
+#pragma omp parallel for schedule(static)
+    for (uint64_t c = 0; c < count; ++c)
+        if (oracle_generate_lhd(n, d, seed + lo + c, out + c * n * d) != 0) status = -1;
+    return status;
 }
 
 /* ------------------------------------------------------------------ */
