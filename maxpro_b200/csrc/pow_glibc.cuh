@@ -12,9 +12,9 @@
 // with FMA, transcribed from its instruction sequence.  tests/test_pow_glibc.py builds this header for
 // the host and compares it with libm bit for bit (4e8 arguments checked when it was written: 0 differences).
 //
-// Exact-path domain: x positive and finite, 2^-65 <= |y| < 2^63, 2^-54 <= |y log x| < 512 (or smaller:
-// 1 + y log x, as glibc).  That covers every call the engine makes (x = S / n_pairs > 0, y = 1/d).  Anything
-// else goes to the toolkit's pow (device) / std::pow (host).
+// Exact-path domain: x positive and finite, 2^-65 <= |y| < 2^63, |y log x| < 1024 with a normal (or infinite)
+// result.  That covers every call the engine makes (x = S / n_pairs > 0, y = 1/d) with a margin of hundreds of
+// binades.  Anything else (x <= 0, NaN, subnormal results, huge y) goes to the toolkit's pow (device) / std::pow (host).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -137,7 +137,7 @@ MP_HD double pow_glibc(double x, double y) {
         const double elo = fma_(y, tail, fma_(hi, y, -ehi));
         // ---- exp_inline
         const unsigned int abstop = (unsigned int)(as_bits(ehi) >> 52) & 0x7ffu;
-        if (abstop - 0x3c9u <= 0x3eu) {
+        if (abstop - 0x3c9u <= 0x3fu) {  // 2^-54 <= |y log x| < 1024
             double kd2 = fma_(ehi, 0x1.71547652b82fep+7, 0x1.8p52);
             const unsigned long long ki = as_bits(kd2);
             kd2 = sub(kd2, 0x1.8p52);
@@ -154,12 +154,27 @@ MP_HD double pow_glibc(double x, double y) {
             double t = fma_(p23, r2, s0);
             const double r4 = mul(r2, r2);
             t = fma_(p45, r4, t);
-            const double scale = as_double(sbits);
-            return fma_(t, scale, scale);
+            if (abstop != 0x408u) return fma_(t, as_double(sbits), as_double(sbits));
+            // 512 <= |y log x| < 1024 (glibc's specialcase): the exponent of `scale` may have left the range, so the
+            // result is formed with a rescaled scale and brought back by an exact power of two
+            if ((ki & 0x80000000ull) == 0) {  // k > 0: overflows to +inf exactly where glibc's does
+                const double sc = as_double(sbits - (1009ull << 52));
+                return mul(0x1p1009, fma_(t, sc, sc));
+            }
+            const double sc = as_double(sbits + (1022ull << 52));
+            const double yv = add(sc, mul(sc, t));  // not fused in glibc's build: the product is shared with the subnormal branch
+            if (yv >= 1.0) return mul(0x1p-1022, yv);  // normal result; below that glibc rounds in the subnormal range
+        } else if (abstop < 0x3c9u) {
+            return add(1.0, ehi);  // |y log x| < 2^-54
+        } else if (abstop < 0x7ffu) {
+            return (as_bits(ehi) >> 63) ? 0.0 : as_double(0x7ff0000000000000ull);  // |y log x| >= 1024: underflow / overflow
         }
-        if (abstop < 0x3c9u) return add(1.0, ehi);  // |y log x| < 2^-54
     }
+#ifdef MP_POW_NO_FALLBACK
+    return -1.0;  // host test build: shows which arguments leave the exact path
+#else
     return pow(x, y);
+#endif
 }
 
 }  // namespace mp

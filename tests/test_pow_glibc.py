@@ -21,14 +21,21 @@ def host_check(tmp_path_factory):
     flags = open("/proc/cpuinfo").read()
     if " fma " not in flags:
         pytest.skip("host CPU has no FMA: glibc selects a different pow variant there")
-    exe = str(tmp_path_factory.mktemp("pow") / "pow_glibc_host")
-    subprocess.run([gxx, "-O2", "-ffp-contract=off", "-mfma", "-o", exe, os.path.join(ROOT, "tests", "pow_glibc_host.cpp")], check=True)
-    return exe
+    d = tmp_path_factory.mktemp("pow")
+    exes = {}
+    for name, extra in (("plain", []), ("no_fallback", ["-DMP_POW_NO_FALLBACK"])):
+        exes[name] = str(d / f"pow_glibc_host_{name}")
+        subprocess.run([gxx, "-O2", "-ffp-contract=off", "-mfma", *extra, "-o", exes[name], os.path.join(ROOT, "tests", "pow_glibc_host.cpp")], check=True)
+    return exes
 
 
 @pytest.mark.parametrize("seed", [1, 0x9E3779B97F4A7C15])
-def test_pow_glibc_bit_exact_against_libm(host_check, seed):
-    out = subprocess.run([host_check, "10000000", str(seed)], check=True, capture_output=True, text=True).stdout.split()
+@pytest.mark.parametrize("build", ["plain", "no_fallback"])
+def test_pow_glibc_bit_exact_against_libm(host_check, seed, build):
+    """`no_fallback`: the build whose escape to std::pow is cut off -- every positive finite x with a normal (or
+    infinite) result must be served by the transcribed arithmetic itself, including glibc's special case for
+    512 <= |y log x| < 1024 and the overflow / underflow returns."""
+    out = subprocess.run([host_check[build], "10000000", str(seed)], check=True, capture_output=True, text=True).stdout.split()
     count, mismatches = int(out[0]), int(out[1])
     assert count == 10_000_000 and mismatches == 0, out
 
