@@ -55,7 +55,10 @@ typedef enum {
 
 /* flags for maxpro_search_range_device / maxpro_build_lhd_ex */
 #define MAXPRO_FLAG_DEFAULT 0u
-#define MAXPRO_FLAG_FP32_SCREEN 1u /* fp32 products / fp64 accumulate screening pass (not 1e-9 parity; reported separately) */
+/* Two-stage search (MaxPro at n = 50, d = 2 or 3; ignored elsewhere): an fp32 screening pass with a proven error
+ * bound keeps every candidate that can still be the winner, the exact fp64 kernel re-scores those.  Same winner,
+ * same score and same tie rule as the default search (csrc/search_screen.cu derives the bound), about twice the rate. */
+#define MAXPRO_FLAG_FP32_SCREEN 1u
 
 /* ---- housekeeping ------------------------------------------------------ */
 MAXPRO_API const char *maxpro_last_error(void);
@@ -148,6 +151,10 @@ MAXPRO_API int maxpro_search_range(uint64_t n, uint64_t d, int metric, uint64_t 
                                    uint64_t lo, uint64_t hi, double *best_score,
                                    uint64_t *best_index);
 
+MAXPRO_API int maxpro_search_range_ex(uint64_t n, uint64_t d, int metric, uint64_t seed,
+                                      uint64_t lo, uint64_t hi, uint32_t flags, double *best_score,
+                                      uint64_t *best_index);
+
 /* The fold of src/lib.rs:76-98 over per-shard winners (min-loc / max-loc with the
  * later-index tie rule).  Host arithmetic over `count` 16-byte records. */
 MAXPRO_API int maxpro_reduce_best(int metric, const double *scores, const uint64_t *indices,
@@ -206,6 +213,14 @@ MAXPRO_API int maxpro_fp64_peak_probe(int repeats, double *tflops, double *kerne
  * another one normally takes.  MAXPRO_* environment variables are read once, at the first look-up of the process,
  * as initial values; nothing on the call path reads the environment. */
 MAXPRO_API int maxpro_debug_set(const char *name, const char *value);
+
+/* Stage 1 of the two-stage search alone, over candidates lo..hi-1: the survivor indices (up to `capacity`; *count
+ * is the number stage 1 produced), and, if fp32_sums is given (hi - lo doubles), every candidate's fp32 MaxPro sum
+ * in the reference's units.  maxpro_debug_screen_threshold: the survivor threshold (same units) that a candidate
+ * with fp32 sum s implies.  The tests check the error bound of search_screen.cu against the oracle with these. */
+MAXPRO_API int maxpro_debug_screen(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, uint64_t hi,
+                                   uint64_t *survivors, uint64_t capacity, uint64_t *count, double *fp32_sums);
+MAXPRO_API int maxpro_debug_screen_threshold(uint64_t n, uint64_t d, double s, double *threshold);
 
 /* out[i] = the device's pow(x[i], y[i]) as the kernels evaluate (S / pairs)^(1/d): the arithmetic of glibc's pow
  * (maxpro_b200/csrc/pow_glibc.cuh), so that criteria tie exactly where the reference's do. */

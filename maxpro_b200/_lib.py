@@ -29,7 +29,7 @@ EXPORTS = [
     "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe",
     "maxpro_release_device_cache", "maxpro_set_device_cache_limit", "maxpro_set_devices", "maxpro_get_devices",
     "maxpro_anneal_scratch_bytes", "maxpro_debug_set", "maxpro_debug_pow", "maxpro_set_stream_version",
-    "maxpro_get_stream_version",
+    "maxpro_get_stream_version", "maxpro_search_range_ex", "maxpro_debug_screen", "maxpro_debug_screen_threshold",
 ]
 
 
@@ -69,6 +69,9 @@ def lib() -> C.CDLL:
         "maxpro_anneal_scratch_bytes": (i32, [u64, u64, i32, i32, u64, szp]),
         "maxpro_set_stream_version": (i32, [i32]),
         "maxpro_get_stream_version": (i32, [C.POINTER(i32)]),
+        "maxpro_search_range_ex": (i32, [u64, u64, i32, u64, u64, u64, u32, dp, u64p]),
+        "maxpro_debug_screen": (i32, [u64, u64, u64, u64, u64, u64p, u64, u64p, dp]),
+        "maxpro_debug_screen_threshold": (i32, [u64, u64, dbl, dp]),
         "maxpro_debug_set": (i32, [C.c_char_p, C.c_char_p]),
         "maxpro_debug_pow": (i32, [dp, dp, u64, dp]),
         "maxpro_generate_lhd": (i32, [u64, u64, u64, dp]),
@@ -148,6 +151,22 @@ def get_stream_version() -> int:
 def debug_set(name: str, value) -> None:
     """Test / tooling switch; value None clears it."""
     check(lib().maxpro_debug_set(name.encode(), None if value is None else str(value).encode()))
+
+
+def debug_screen(n: int, d: int, seed: int, lo: int, hi: int, want_sums: bool = False, capacity: int = 1 << 20):
+    """Stage 1 of the two-stage search alone: (survivor indices, count stage 1 produced, fp32 sums or None)."""
+    surv = np.zeros(capacity, dtype=np.uint64)
+    cnt = C.c_uint64(0)
+    sums = np.zeros(hi - lo, dtype=np.float64) if want_sums else None
+    check(lib().maxpro_debug_screen(n, d, seed & (2 ** 64 - 1), lo, hi, u64ptr(surv), capacity, C.byref(cnt),
+                                    dptr(sums) if want_sums else None))
+    return surv[:min(cnt.value, capacity)], int(cnt.value), sums
+
+
+def debug_screen_threshold(n: int, d: int, s: float) -> float:
+    t = C.c_double(0)
+    check(lib().maxpro_debug_screen_threshold(n, d, s, C.byref(t)))
+    return t.value
 
 
 def debug_pow(x, y) -> np.ndarray:

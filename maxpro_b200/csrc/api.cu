@@ -4,6 +4,7 @@
 // usable sm_100 device every compute entry point fails with MAXPRO_ERR_NO_DEVICE.
 #include "../../include/maxpro_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -161,7 +162,7 @@ __global__ void fold_result_kernel(BestRec* total, const BestRec* chunk, unsigne
     if (take) { total->score = s; total->index = i; }
 }
 
-__global__ void init_counter_kernel(unsigned int* c) { *c = 0u; }
+__global__ void init_counter_kernel(unsigned int* c) { c[0] = 0u; c[1] = 0u; }  // done counter, survivor count
 
 // maxpro_debug_pow: the device build of pow_glibc.cuh, element-wise (tests compare it with libm bit for bit)
 __global__ void debug_pow_kernel(const double* x, const double* y, unsigned long long count, double* out) {
@@ -172,6 +173,7 @@ __global__ void debug_pow_kernel(const double* x, const double* y, unsigned long
 // ---- search dispatch -----------------------------------------------------------
 
 constexpr size_t kMaxBlockRecs = 4096;
+constexpr unsigned int kSurvivorCap = 1u << 20;  // 8 MB; a 2^28-candidate range leaves a few tens of thousands
 constexpr size_t kGenericChunkBytes = 128ull << 20;
 
 unsigned long long generic_chunk(unsigned long long n, unsigned long long d) {
@@ -194,7 +196,7 @@ struct SearchWs {
     unsigned int* counter;
     BestRec* block_best;
     BestRec* chunk_result;
-    unsigned long long* survivors;  // fp32 screening: one index per warp
+    unsigned long long* survivors;  // two-stage search: candidates that passed the fp32 screen (kSurvivorCap entries)
     double* designs;
     double* partial;
     double* scores;
@@ -209,7 +211,7 @@ SearchWs carve_search_ws(void* base, unsigned long long n, unsigned long long d)
     w.counter = reinterpret_cast<unsigned int*>(take(256));
     w.block_best = reinterpret_cast<BestRec*>(take(kMaxBlockRecs * sizeof(BestRec)));
     w.chunk_result = reinterpret_cast<BestRec*>(take(256));
-    w.survivors = reinterpret_cast<unsigned long long*>(take(kMaxBlockRecs * 16 * sizeof(unsigned long long)));
+    w.survivors = reinterpret_cast<unsigned long long*>(take((size_t)kSurvivorCap * sizeof(unsigned long long)));
     if (!mp::search_small_supported(n, d) && !use_cta_kernel(n, d) && !use_warp_kernel(n, d)) {
         unsigned long long bc = generic_chunk(n, d);
         w.designs = reinterpret_cast<double*>(take(bc * n * d * sizeof(double)));
@@ -251,9 +253,9 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
     mp::count_launch();
     int cyc_cands = 0, scr_cands = 0;
-    if ((flags & MAXPRO_FLAG_FP32_SCREEN) && mp::search_screen_supported(n, d, &scr_cands) &&
+    if ((flags & MAXPRO_FLAG_FP32_SCREEN) && mp::search_screen_supported(n, d, metric, &scr_cands) &&
         mp::search_cyclic_supported(n, d, &cyc_cands)) {
-        // stage 1: fp32 screening, one survivor per warp
+        // stage 1: fp32 screening with a proven bound; every candidate that can still win goes to the survivor list
         mp::SearchLaunch L{};
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
         L.threads = scr_cands; L.group = 1;
@@ -261,15 +263,17 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
         unsigned long long want = (total + scr_cands - 1) / scr_cands;
         L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
         L.stream = stream;
-        CUDA_TRY(mp::launch_search_screen(L, w.survivors));
+        unsigned int cap = kSurvivorCap;
+        if (const char* v = mp::cfg("MAXPRO_SCREEN_CAP")) { const long c = atol(v); if (c >= 1 && c < (long)kSurvivorCap) cap = (unsigned int)c; }  // tests: force the overflow path
+        CUDA_TRY(mp::launch_search_screen(L, w.survivors, w.counter + 1, cap));
         mp::count_launch();
-        // stage 2: exact fp64 re-score of the survivors, usual fold
+        // stage 2: the exact fp64 kernel over the survivors (over lo..hi if the list overflowed), usual fold
         mp::SearchLaunch E{};
-        E.n = n; E.d = d; E.metric = metric; E.seed = seed; E.lo = 0; E.hi = 0; E.flags = flags;
+        E.n = n; E.d = d; E.metric = metric; E.seed = seed; E.lo = lo; E.hi = hi; E.flags = flags;
         E.block_best = w.block_best; E.done_counter = w.counter; E.result = result;
         E.group = 2; E.threads = 2 * cyc_cands;
-        E.list = w.survivors; E.list_count = (unsigned long long)L.grid * (unsigned long long)(scr_cands / 32);
-        unsigned long long want2 = (E.list_count + cyc_cands - 1) / cyc_cands;
+        E.list = w.survivors; E.list_count = 0; E.list_count_dev = w.counter + 1; E.list_cap = cap;
+        unsigned long long want2 = (total + cyc_cands - 1) / cyc_cands;
         E.grid = (int)(want2 < (unsigned long long)sms ? want2 : (unsigned long long)sms);
         E.stream = stream;
         CUDA_TRY(mp::launch_search_cyclic(E));
@@ -751,13 +755,18 @@ int maxpro_score_batch(const double* designs, uint64_t b, uint64_t n, uint64_t d
 
 int maxpro_search_range(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi,
                         double* best_score, uint64_t* best_index) {
+    return maxpro_search_range_ex(n, d, metric, seed, lo, hi, MAXPRO_FLAG_DEFAULT, best_score, best_index);
+}
+
+int maxpro_search_range_ex(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t flags,
+                           double* best_score, uint64_t* best_index) {
     if (n == 0) return fail(MAXPRO_ERR_INVALID, "n_samples must be positive and nonzero");
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");
     if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
     if (hi < lo) return fail(MAXPRO_ERR_INVALID, "search range is inverted");
     double s = 0.0;
     uint64_t i = 0;
-    if (int rc = search_range_sharded(n, d, metric, seed, lo, hi, MAXPRO_FLAG_DEFAULT, &s, &i)) return rc;
+    if (int rc = search_range_sharded(n, d, metric, seed, lo, hi, flags, &s, &i)) return rc;
     if (best_score) *best_score = s;
     if (best_index) *best_index = i;
     return MAXPRO_OK;
@@ -967,6 +976,55 @@ int maxpro_anneal_scratch_bytes(uint64_t n, uint64_t d, int metric, int swap, ui
     AnnealScratch sc{};
     if (int rc = anneal_scratch(n, d, metric, swap, n_chains, sms, &grid, &sc)) return rc;
     *bytes = sc.total();
+    return MAXPRO_OK;
+}
+
+int maxpro_debug_screen(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, uint64_t hi, uint64_t* survivors,
+                        uint64_t capacity, uint64_t* count, double* fp32_sums) {
+    if (!count) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    if (hi < lo) return fail(MAXPRO_ERR_INVALID, "search range is inverted");
+    int sms = 0, cands = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    if (!mp::search_screen_supported(n, d, MAXPRO_METRIC_MAXPRO, &cands))
+        return fail(MAXPRO_ERR_UNSUPPORTED, "the fp32 screening pass covers MaxPro at n = 50, d = 2 or 3");
+    const uint64_t total = hi - lo;
+    DevBuf dl, dc, ds;
+    CUDA_TRY(dl.alloc((size_t)kSurvivorCap * sizeof(unsigned long long)));
+    CUDA_TRY(dc.alloc(2 * sizeof(unsigned int)));
+    if (fp32_sums) CUDA_TRY(ds.alloc(total * sizeof(double)));
+    cudaStream_t st = cudaStreamPerThread;
+    init_counter_kernel<<<1, 1, 0, st>>>(dc.as<unsigned int>());
+    mp::count_launch();
+    mp::SearchLaunch L{};
+    L.n = n; L.d = d; L.metric = MAXPRO_METRIC_MAXPRO; L.seed = seed; L.lo = lo; L.hi = hi;
+    L.threads = cands; L.group = 1; L.stream = st;
+    const uint64_t want = (total + cands - 1) / cands;
+    L.grid = (int)(want < (uint64_t)sms ? (want ? want : 1) : (uint64_t)sms);
+    CUDA_TRY(mp::launch_search_screen(L, dl.as<unsigned long long>(), dc.as<unsigned int>() + 1, kSurvivorCap,
+                                      fp32_sums ? ds.as<double>() : nullptr));
+    mp::count_launch();
+    unsigned int got = 0;
+    CUDA_TRY(cudaMemcpyAsync(&got, dc.as<unsigned int>() + 1, sizeof(got), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *count = got;
+    const uint64_t copy = std::min<uint64_t>(std::min<uint64_t>(got, kSurvivorCap), capacity);
+    if (survivors && copy) CUDA_TRY(cudaMemcpyAsync(survivors, dl.p, copy * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (fp32_sums && total) {
+        CUDA_TRY(cudaMemcpyAsync(fp32_sums, ds.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        double g2 = 1.0;
+        mp::screen_debug_constants(n, d, &g2, nullptr, 1.0);
+        for (uint64_t t = 0; t < total; ++t) fp32_sums[t] *= g2;  // scaled units -> the reference's S
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MAXPRO_OK;
+}
+
+int maxpro_debug_screen_threshold(uint64_t n, uint64_t d, double s, double* threshold) {
+    if (!threshold) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    double ratio = 0.0;
+    mp::screen_debug_constants(n, d, nullptr, &ratio, s);
+    *threshold = s * ratio;
     return MAXPRO_OK;
 }
 

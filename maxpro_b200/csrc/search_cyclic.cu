@@ -32,6 +32,8 @@ struct CyclicParams {
     // list mode (stage 2 of the fp32-screened search): score list[0..list_count) instead of lo..hi
     const unsigned long long* list;
     unsigned long long list_count;
+    const unsigned int* list_count_dev;  // list length written by stage 1; above list_cap = overflow: score lo..hi instead
+    unsigned int list_cap;
     // supplied mode (score_batch): candidate idx is the design designs[idx*N*D ...], row-major
     // [i][k] in HBM; scores[idx] receives its criterion.  lo..hi index the batch.
     const double* designs;
@@ -307,7 +309,13 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
 
     const unsigned long long gcid = (unsigned long long)blockIdx.x * C + c;
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
-    const unsigned long long total = p.list ? p.list_count : p.hi - p.lo;
+    const unsigned long long* list = p.list;
+    unsigned long long list_count = p.list_count;
+    if (list && p.list_count_dev) {
+        list_count = *p.list_count_dev;
+        if (list_count > p.list_cap) list = nullptr;  // stage 1 overflowed its list: the exact search over the whole range
+    }
+    const unsigned long long total = list ? list_count : p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
 
     LaneBest<MAXPRO> lb;  // fold of src/lib.rs:85-97 on the criterion (reduce.cuh)
@@ -323,8 +331,8 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
         const unsigned long long off = gcid + rnd * gstep;
         bool active = off < total;
         unsigned long long idx = p.lo + off;
-        if (p.list) {
-            idx = active ? p.list[off] : kNoIndex;
+        if (list) {
+            idx = active ? list[off] : kNoIndex;
             active = idx != kNoIndex;
         }
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
@@ -402,7 +410,7 @@ cudaError_t launch_search_cyclic(const SearchLaunch& L) {
     if (const char* e = cfg("MAXPRO_CYCLIC_RING")) { int v = atoi(e); if (v == 0 || v == 2 || v == 3) p.ring = v; }
     if (p.ring > (L.threads / 32) / 4) p.ring = 0;
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
-    p.list = L.list; p.list_count = L.list_count;
+    p.list = L.list; p.list_count = L.list_count; p.list_count_dev = L.list_count_dev; p.list_cap = L.list_cap;
     p.designs = L.designs; p.scores = L.scores;
     p.gen = stream_version();
     p.c1 = ldexp(1.0 / (double)L.n, -32);

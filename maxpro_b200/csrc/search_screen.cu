@@ -1,211 +1,314 @@
-// K1+K2 fused, FP32 SCREENING variant (MAXPRO_FLAG_FP32_SCREEN) for the headline shapes.
+// K1+K2 fused, TWO-STAGE search for the headline shapes (MAXPRO_FLAG_FP32_SCREEN, MaxPro only): an fp32 screening
+// pass with a PROVEN error bound, then the exact fp64 kernel on the survivors.  The result is the result of the
+// exact search -- same winner under the reference's fold (src/lib.rs:85-97, criterion after powf, later index on
+// ties), same score -- at about twice its rate.
 //
-// north_star: "fp32-product / fp64-accumulate variant benchmarked separately".  This is not a
-// parity path: products and reciprocals are fp32 (relative error ~1e-6 on a score), so it is
-// used as stage 1 of a two-stage search:
-//   stage 1  every candidate of the range is generated and scored in fp32; each WARP keeps the
-//            index of its best candidate (one 8-byte survivor per warp, 1776 per GPU);
-//   stage 2  the survivors are regenerated and re-scored by the fp64 kernel of
-//            search_cyclic.cu in list mode, and the usual fold picks the winner.
-// The reported score is therefore the exact fp64 criterion of the returned design; what is
-// approximate is only WHICH candidate wins when two of the best lie within ~1e-6 of each other.
-// It replaces the same reference code as the fp64 kernels (src/lib.rs:65-98, src/lhd.rs:97-132,
-// src/maxpro_utils.rs:28-83) and draws the same LHD-Philox v1 stream (values rounded to fp32).
+// north_star: "fp32-product / fp64-accumulate variant benchmarked separately"; SURVEY.md 8f.1: a two-stage search
+// that "keeps 1e-9 parity on the reported winner".  It replaces the same reference code as the fp64 kernels
+// (src/lib.rs:65-98, src/lhd.rs:97-132, src/maxpro_utils.rs:28-83) and draws the same design stream.
 //
-// Why it is faster: an fp32 instruction occupies its pipe for one cycle per warp where an FP64
-// instruction occupies the FP64 pipe for two, a design is 600 B instead of 1200 B so ONE lane per
-// candidate still gives 12 warps per SM (no duplicated tile loads, no idle generator lane).
+//   stage 1  (this file) every candidate of the range is generated and scored in fp32.  A candidate SURVIVES if
+//            its fp32 score is not above a threshold derived from the best true upper bound seen so far by its
+//            CTA; the threshold is wide enough that the true winner -- and every candidate whose criterion can
+//            tie with it -- is certain to be below it (the bound is derived below).  Survivors are appended to a
+//            list in HBM (8 bytes each; a few hundred per CTA for 2^28 candidates).
+//   stage 2  search_cyclic.cu in list mode regenerates the survivors, scores them in fp64 and folds them exactly
+//            as the full fp64 search would.  If the list overflows, stage 2 scores the whole range instead.
 //
-// fp32 range: terms p = q^2 + eps span [1e-12, 1] = [2^-40, 1]; a reciprocal chain of 6 terms
-// would underflow.  Column 0 is stored pre-multiplied by 2^10, which scales every q by 2^10
-// and every p by 2^20 into [2^-20, 2^20]: six terms stay inside [2^-120, 2^120], and the sum
-// is rescaled once at the end.
+// ---- fp32 arithmetic with exact differences ----------------------------------------------------------------
+// A coordinate of the design stream is x = (i + (jit + 1/2) 2^-32) / n.  Stage 1 keeps y = i 2^18 + (jit >> 14), an
+// INTEGER below 2^24 (n <= 64), as a float: exactly representable, and so is every difference y_a - y_b.  The
+// only departure from the true design is the truncated jitter: |x_a - x_b - (y_a - y_b) / (n 2^18)| < eta =
+// 2^-18 / n.  Column 0 carries an exact power-of-two factor so that the scaled terms
+//     p_s = q_s^2 + eps_s,   q_s = G prod_k (x_ak - x_bk),   eps_s = G^2 eps        (G: exact scale, G^2 eps ~ 2^-20)
+// lie in [2^-20, 2^20]: six of them can be chained ((num, den) <- (num p + den, den p)) inside the fp32 range, and
+// S = G^2 sum 1/p_s.  Rounding happens in two products, one fma, the chain and the sums: below 2^-18 relative in
+// total (`arith`).
+//
+// ---- the bound -----------------------------------------------------------------------------------------------
+// With |delta'_k - delta_k| < eta and |delta_k| <= 1: |q' - q| <= dq = d eta (1 + eta)^(d-1).  For one term
+// f = 1 / (q^2 + eps) the computed f' = 1 / (q'^2 + eps) satisfies
+//     f'/f >= (q^2 + eps) / ((|q| + dq)^2 + eps) >= gmin                      for every q  (gmin ~ 0.75: host, numerically)
+//     |f'/f - 1| <= rho(F) = (2 Q dq + dq^2) / (1/F - 2 Q dq),  Q = sqrt(1/F - eps)   whenever f <= F < 1/(2 eps)
+// (the ratio is worst at the smallest admissible |q|, which is Q).  Every term of a design is at most its sum S, so
+//   (i)  S <= S'/gmin =: F0, hence every term is <= F0 and S <= U := S' / (1 - rho(F0)) (1 + arith):
+//        U is a TRUE upper bound of that candidate's S, and so of the minimum over the range;
+//   (ii) a candidate with S <= U (1 + tau) has S' <= W := U (1 + tau) (1 + rho(U (1 + tau))) (1 + arith),
+//        where tau = (4d + 4) 2^-52 is the band inside which two sums can share a criterion (reduce.cuh).
+// The winner and everything that can tie with it have S <= U (1 + tau) for the U of ANY candidate, so keeping every
+// candidate with S' <= W, for the smallest W known when it is scored, loses none of them.  W / S' is about 1.07
+// at n = 50, d = 3: the survivors are the candidates within a few percent of the running best.
 #include "common.cuh"
 #include "philox.cuh"
 #include "reduce.cuh"
 #include "kernels.h"
 
+#include <cmath>
+
 namespace mp {
+
+struct ScreenBound {
+    double g2;      // S_true = g2 * S_scaled
+    double eps;     // the reference's eps as stage 1 sees it: eps_s / g2 (eps_s is a rounded float)
+    double dq;      // bound of |q' - q|
+    double gmin;    // lower bound of f'/f over all q
+    double arith;   // relative bound of all fp32 rounding in one score
+    double tau;     // criterion tie band
+};
 
 struct ScreenParams {
     int gen;                         // design stream version (philox.cuh)
     unsigned long long seed, lo, hi;
-    float inv_n;                     // 1/n
-    unsigned long long* survivors;   // [gridDim.x * warps per CTA] candidate indices (kNoIndex = none)
+    float col0_scale;                // exact power of two carried by column 0
+    float eps_s;                     // eps in scaled units
+    ScreenBound bound;
+    unsigned long long* list;        // survivors (candidate indices)
+    unsigned int* count;             // appended so far (may exceed cap: overflow)
+    unsigned int cap;
+    double* debug_scores;            // tests: scaled fp32 score of candidate lo + t at [t] (null otherwise)
 };
 
-struct ChainF {
-    float num, den;
-    __device__ __forceinline__ void reset() { num = 0.0f; den = 1.0f; }
-    __device__ __forceinline__ void push(float p) { num = fmaf(num, p, den); den *= p; }
-    __device__ __forceinline__ float flush() {
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-        float v = num * r;
-        reset();
-        return v;
+// rho(F) of the header comment; returns a negative value where the bound does not apply
+__host__ __device__ inline double screen_rho(double F, const ScreenBound& b) {
+    const double inv = 1.0 / F;
+    if (!(inv > 2.0 * b.eps)) return -1.0;
+    const double Q = sqrt(inv - b.eps);
+    const double den = inv - 2.0 * Q * b.dq;
+    if (!(den > 0.0)) return -1.0;
+    return (2.0 * Q * b.dq + b.dq * b.dq) / den;
+}
+
+// W of the header comment for a candidate whose scaled fp32 score is s; +inf where no bound applies
+__host__ __device__ inline double screen_threshold(double s, const ScreenBound& b) {
+    const double inf = 1.0 / 0.0;
+    const double s_true = s * b.g2;
+    const double r0 = screen_rho(s_true / b.gmin, b);
+    if (r0 < 0.0 || r0 >= 0.5) return inf;
+    const double U = s_true / (1.0 - r0) * (1.0 + b.arith) * (1.0 + b.tau);
+    const double r1 = screen_rho(U, b);
+    if (r1 < 0.0) return inf;
+    return U * (1.0 + r1) * (1.0 + b.arith) / b.g2;
+}
+
+namespace {
+
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 do two lanes' worth per issue slot) -----------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ f2 lds2(unsigned int addr) { f2 r; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr)); return r; }
+
+// sum of reciprocals of up to six packed terms without a divide per term (see header): first term starts the chain
+struct Chain2 {
+    f2 num, den;
+    __device__ __forceinline__ void start(f2 p) { num = pk(1.0f, 1.0f); den = p; }
+    __device__ __forceinline__ void push(f2 p) { num = fma2(num, p, den); den = mul2(den, p); }
+    __device__ __forceinline__ f2 value() const {
+        float d0, d1;
+        unpk(den, d0, d1);
+        return mul2(num, pk(rcp_approx(d0), rcp_approx(d1)));
     }
 };
 
-template <int D>
-__device__ __forceinline__ float screen_term(const float (&a)[D], const float (&b)[D], float eps_scaled) {
-    float q = a[0] - b[0];
-#pragma unroll
-    for (int k = 1; k < D; ++k) q *= (a[k] - b[k]);
-    return fmaf(q, q, eps_scaled);
-}
-
-template <int N, int D, int C, bool MAXPRO>
+// Shared-memory layout: rows in blocks of two, block m of dimension k of candidate c (= lane) at
+// ((k * NB + m) * C + c) * 8, the even row in the low half.  A block is one LDS.64, conflict-free across the warp.
+template <int N, int D, int C, int GEN>
 __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr unsigned RB = C * 4u;       // row stride in bytes: element (k,i) at (k*N + i)*RB
-    constexpr unsigned DB = N * RB;       // dimension stride
-    constexpr int R = 5, S = 6;
-    constexpr int kHalf = (N - 1) / 2;
-    static_assert(N % R == 0 && kHalf % S == 0 && (N % 2 != 0 || (N / 2) % R == 0), "shape not tileable");
-    constexpr float kScale = 1024.0f;                       // column 0 carries 2^10
-    constexpr float kEpsScaled = 1e-12f * 1048576.0f;       // eps * 2^20
-    unsigned char* cand = smem_raw + threadIdx.x * 4u;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ unsigned long long cta_thr;  // smallest survivor threshold W implied by a candidate of this CTA (bits of a positive double)
+    static_assert(N % 2 == 0 && (N / 2) % 2 == 1 && N <= 64, "row blocks: an odd number of them, strata below 2^6");
+    constexpr int NB = N / 2, SH = (NB - 1) / 2;  // row blocks; block shifts 1..SH cover every pair of blocks once
+    static_assert((2 * SH) % 4 == 0 && (2 * SH) / 4 <= 6, "four chains of at most six terms per row block");
+    constexpr unsigned BS = C * 8u, DS = NB * BS;
+    const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + threadIdx.x * 8u;
 
     const unsigned long long gtid = (unsigned long long)blockIdx.x * C + threadIdx.x;
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
+    const unsigned long long total = p.hi - p.lo;
+    const unsigned long long rounds = (total + gstep - 1) / gstep;
+    if (threadIdx.x == 0) cta_thr = 0x7FF0000000000000ull;
+    __syncthreads();
+    const f2 eps2 = pk(p.eps_s, p.eps_s);
 
-    double best = MAXPRO ? CUDART_INF : -CUDART_INF;
-    unsigned long long best_idx = kNoIndex;
-
-    for (unsigned long long idx = p.lo + gtid; idx < p.hi; idx += gstep) {
-        const unsigned long long stream = p.seed + idx;
-        const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
-        // ---- generation: same stream and shuffle as the fp64 kernels, values rounded to fp32
+    for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
+        const unsigned long long off = gtid + rnd * gstep;
+        const bool active = off < total;
+        const unsigned long long idx = p.lo + off;
+        double s = 0.0;
+        if (active) {
+            const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
+            const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
+            // ---- generation: the design stream's draws and shuffle (philox.cuh); values as exact integers (see header)
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) {
-            unsigned char* col = cand + k * DB;
-            const float scale = (MAXPRO && k == 0) ? p.inv_n * kScale : p.inv_n;
-            LhdKeyCache kc{0xFFFFFFFFu, 0u, 0u};
+            for (int k = 0; k < D; ++k) {
+                const unsigned int col = base + k * DS;
+                const float scale = k == 0 ? p.col0_scale : 1.0f;
+                uint32_t ka = 0u, kb = 0u, x = 0u;
+                if (GEN == 2) { lhd2_column_key((uint32_t)k, s_lo, s_hi, ka, kb); x = ka; }
 #pragma unroll 2
-            for (int b = 0; b < (N + 1) / 2; ++b) {
-                const LhdBlock w = lhd_draw_block(p.gen, (uint32_t)b, (uint32_t)k, s_lo, s_hi, kc);
-                const uint32_t jit[2] = {w.jit0, w.jit1}, jx[2] = {w.j0, w.j1};
+                for (int b = 0; b < NB; ++b) {
+                    uint32_t jx[2], jit[2];
+                    if (GEN == 1) {
+                        const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+                        jit[0] = w.x; jx[0] = __umulhi(w.y, 2u * b + 1u);
+                        jit[1] = w.z; jx[1] = __umulhi(w.w, 2u * b + 2u);
+                    } else {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int i = 2 * b + e;
-                    if (i < N) {
-                        const uint32_t j = jx[e];
-                        const float v = (fmaf((float)jit[e], 0x1p-32f, 0x1p-33f) + (float)i) * scale;
-                        *reinterpret_cast<float*>(col + i * RB) = *reinterpret_cast<float*>(col + j * RB);
-                        *reinterpret_cast<float*>(col + j * RB) = v;
-                    }
-                }
-            }
-        }
-        // ---- scoring: cyclic pairs {i, (i+s) mod N}, s = 1..kHalf, plus the N/2 diameters
-        double acc = 0.0;
-        float mn = CUDART_INF_F;
-        ChainF ch[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) ch[r].reset();
-#pragma unroll 1
-        for (int t = 0; t < N / R; ++t) {
-            const unsigned i0_off = (unsigned)t * R * RB;
-            float xi[R][D];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int k = 0; k < D; ++k) xi[r][k] = *reinterpret_cast<const float*>(cand + i0_off + r * RB + k * DB);
-            float tile_sum = 0.0f;
-#pragma unroll
-            for (int b = 0; b < kHalf / S; ++b) {
-                const unsigned base = i0_off + (1u + (unsigned)b * S) * RB;
-                float xj[R + S - 1][D];
-#pragma unroll
-                for (int u = 0; u < R + S - 1; ++u) {
-                    unsigned off = base + u * RB;
-                    off = min(off, off - N * RB);  // wrap modulo N rows
-#pragma unroll
-                    for (int k = 0; k < D; ++k) xj[u][k] = *reinterpret_cast<const float*>(cand + off + k * DB);
-                }
-#pragma unroll
-                for (int c = 0; c < S; ++c)
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if (MAXPRO) ch[r].push(screen_term<D>(xi[r], xj[r + c], kEpsScaled));
-                        else {
-                            float sq = 0.0f;
-#pragma unroll
-                            for (int k = 0; k < D; ++k) { float df = xi[r][k] - xj[r + c][k]; sq = fmaf(df, df, sq); }
-                            mn = fminf(mn, sq);
+                        for (int e = 0; e < 2; ++e) {
+                            mulhilo32(lhd2_mix32(x), 2u * b + e + 1u, jx[e], jit[e]);
+                            x += kb;  // Weyl sequence A + i B
                         }
                     }
-                if (MAXPRO) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) tile_sum += ch[r].flush();  // 6 terms per chain
-                }
-            }
-            if (N % 2 == 0 && t < N / (2 * R)) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float xd[D];
-#pragma unroll
-                    for (int k = 0; k < D; ++k) xd[k] = *reinterpret_cast<const float*>(cand + i0_off + (N / 2 + r) * RB + k * DB);
-                    if (MAXPRO) ch[r].push(screen_term<D>(xi[r], xd, kEpsScaled));
-                    else {
-                        float sq = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) { float df = xi[r][k] - xd[k]; sq = fmaf(df, df, sq); }
-                        mn = fminf(mn, sq);
+                    for (int e = 0; e < 2; ++e) {
+                        const uint32_t i = 2u * b + e, j = jx[e];
+                        const float v = (float)((i << 18) | (jit[e] >> 14)) * scale;
+                        const unsigned int aj = col + (j >> 1) * BS + (j & 1u) * 4u;
+                        float t;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(aj) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(col + (unsigned int)b * BS + e * 4u), "f"(t) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj), "f"(v) : "memory");
                     }
                 }
-                if (MAXPRO) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) tile_sum += ch[r].flush();
-                }
             }
-            acc += (double)tile_sum;  // fp64 accumulation across tiles
+            // ---- scoring: block m against blocks m+1 .. m+SH (cyclically), plus the pair inside block m
+            double acc = 0.0;
+#pragma unroll 1
+            for (int m = 0; m < NB; ++m) {
+                f2 ax[D], ay[D];
+                float q_in = 1.0f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    float a0, a1;
+                    unpk(lds2(base + k * DS + m * BS), a0, a1);
+                    ax[k] = pk(a0, a0);
+                    ay[k] = pk(a1, a1);
+                    q_in = k == 0 ? a0 - a1 : q_in * (a0 - a1);
+                }
+                const float inner = rcp_approx(fmaf(q_in, q_in, p.eps_s));  // rows 2m, 2m+1
+                Chain2 ch[4];
+#pragma unroll
+                for (int sft = 1; sft <= SH; ++sft) {
+                    unsigned int o = (unsigned int)(m + sft) * BS;
+                    o = min(o, o - DS);  // block index modulo NB
+                    f2 qa, qb;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const f2 bk = lds2(base + k * DS + o);
+                        const f2 da = sub2(ax[k], bk), db = sub2(ay[k], bk);
+                        qa = k == 0 ? da : mul2(qa, da);
+                        qb = k == 0 ? db : mul2(qb, db);
+                    }
+                    const f2 pa = fma2(qa, qa, eps2), pb = fma2(qb, qb, eps2);
+                    const int t0 = 2 * (sft - 1);  // term counter of this row block: chain t % 4, started by its first term
+                    if (t0 < 4) ch[t0 % 4].start(pa); else ch[t0 % 4].push(pa);
+                    if (t0 + 1 < 4) ch[(t0 + 1) % 4].start(pb); else ch[(t0 + 1) % 4].push(pb);
+                }
+                const f2 v = add2(add2(ch[0].value(), ch[1].value()), add2(ch[2].value(), ch[3].value()));
+                float v0, v1;
+                unpk(v, v0, v1);
+                acc += (double)(v0 + v1 + inner);
+            }
+            s = acc;
+            if (p.debug_scores) p.debug_scores[off] = s;
         }
-        const double s = MAXPRO ? acc : (double)mn;
-        if (MAXPRO ? (s <= best) : (s >= best)) { best = s; best_idx = idx; }
+        // ---- survivors
+        if (rnd == 0) {
+            // the CTA's first round: everybody's threshold first, then the test against the smallest of them
+            if (active) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
+            __syncthreads();
+            const double thr = __longlong_as_double((long long)cta_thr);
+            if (active && s <= thr) {
+                const unsigned int pos = atomicAdd(p.count, 1u);
+                if (pos < p.cap) p.list[pos] = idx;
+            }
+        } else {
+            const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
+            if (active && s <= thr) {
+                const unsigned int pos = atomicAdd(p.count, 1u);
+                if (pos < p.cap) p.list[pos] = idx;
+                const double w = screen_threshold(s, p.bound);
+                if (w < thr) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(w));
+            }
+        }
     }
-    // one survivor per warp
-    warp_reduce_best<MAXPRO>(best, best_idx);
-    if (lane == 0) p.survivors[blockIdx.x * (C / 32) + wid] = best_idx;
 }
 
 template <int N, int D, int C>
-static cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
+cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
     constexpr size_t smem = (size_t)N * D * C * sizeof(float);
     static_assert(smem <= kSmemBudget, "candidates per CTA do not fit shared memory");
-    cudaError_t e;
-    if (L.metric == 0) {
-        e = cudaFuncSetAttribute(search_screen_kernel<N, D, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        search_screen_kernel<N, D, C, true><<<L.grid, C, smem, L.stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(search_screen_kernel<N, D, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        search_screen_kernel<N, D, C, false><<<L.grid, C, smem, L.stream>>>(p);
-    }
-    return cudaGetLastError();
+        kernel<<<L.grid, C, smem, L.stream>>>(p);
+        return cudaGetLastError();
+    };
+    return p.gen == 1 ? go(search_screen_kernel<N, D, C, 1>) : go(search_screen_kernel<N, D, C, 2>);
 }
 
-bool search_screen_supported(unsigned long long n, unsigned long long d, int* cands) {
+}  // namespace
+
+bool search_screen_supported(unsigned long long n, unsigned long long d, int metric, int* cands) {
     int c = 0;
-    if (n == 50 && d == 3) c = 384;
-    else if (n == 50 && d == 2) c = 512;
+    if (metric == 0 && n == 50 && d == 3) c = 384;
+    else if (metric == 0 && n == 50 && d == 2) c = 512;
     if (cands) *cands = c;
     return c != 0;
 }
 
-// survivors: [L.grid * (cands/32)] indices
-cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* survivors) {
+// Host: the constants of the bound for a shape (see the header comment).
+static ScreenBound screen_bound(unsigned long long n, unsigned long long d, float* col0_scale, float* eps_s) {
+    const double unit = (double)n * 262144.0;  // y = x * n * 2^18
+    // exact power of two on column 0 that puts G^2 eps next to 2^-20
+    const double log2_g2eps = log2(kEps) + 2.0 * (double)d * log2(unit);
+    const int a = (int)llround(0.5 * (log2_g2eps + 20.0));
+    const double G = pow(unit, (double)d) * ldexp(1.0, -a);
+    *col0_scale = (float)ldexp(1.0, -a);
+    *eps_s = (float)(kEps * G * G);
+    ScreenBound b;
+    b.g2 = G * G;
+    b.eps = (double)*eps_s / b.g2;
+    const double eta = ldexp(1.0, -18) / (double)n;
+    b.dq = (double)d * eta * pow(1.0 + eta, (double)d - 1.0);
+    // gmin = min over q >= 0 of (q^2 + eps) / ((q + dq)^2 + eps), scanned on a log grid around sqrt(eps), 2 % margin
+    double g = 1.0;
+    for (int t = -4000; t <= 4000; ++t) {
+        const double q = sqrt(b.eps) * exp2((double)t / 200.0);
+        const double r = (q * q + b.eps) / ((q + b.dq) * (q + b.dq) + b.eps);
+        if (r < g) g = r;
+    }
+    b.gmin = g * 0.98;
+    b.arith = ldexp(1.0, -18);
+    b.tau = (4.0 * (double)d + 4.0) * ldexp(1.0, -52);
+    return b;
+}
+
+// list: survivor indices (cap entries), count: number appended (zeroed by the caller's init kernel)
+cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list, unsigned int* count, unsigned int cap,
+                                 double* debug_scores) {
     ScreenParams p;
     p.gen = stream_version();
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
-    p.inv_n = 1.0f / (float)L.n;
-    p.survivors = survivors;
+    p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s);
+    p.list = list; p.count = count; p.cap = cap;
+    p.debug_scores = debug_scores;
     if (L.n == 50 && L.d == 3) return launch_screen_nd<50, 3, 384>(L, p);
     if (L.n == 50 && L.d == 2) return launch_screen_nd<50, 2, 512>(L, p);
     return cudaErrorInvalidValue;
+}
+
+// tests: S_true of a scaled score, and the survivor threshold a scaled score implies, in true units
+void screen_debug_constants(unsigned long long n, unsigned long long d, double* g2, double* threshold_ratio_at, double s_true) {
+    float c0, es;
+    const ScreenBound b = screen_bound(n, d, &c0, &es);
+    if (g2) *g2 = b.g2;
+    if (threshold_ratio_at) *threshold_ratio_at = screen_threshold(s_true / b.g2, b) * b.g2 / s_true;
 }
 
 }  // namespace mp

@@ -79,10 +79,10 @@ def build_lhd(n: int, d: int, n_iterations: int, metric: int, seed: int, flags: 
     return out, score.value, int(idx.value)
 
 
-def search_range(n: int, d: int, metric: int, seed: int, lo: int, hi: int):
+def search_range(n: int, d: int, metric: int, seed: int, lo: int, hi: int, flags: int = 0):
     score = C.c_double(0)
     idx = C.c_uint64(0)
-    check(lib().maxpro_search_range(n, d, metric, seed & U64, lo, hi, C.byref(score), C.byref(idx)))
+    check(lib().maxpro_search_range_ex(n, d, metric, seed & U64, lo, hi, flags, C.byref(score), C.byref(idx)))
     return score.value, int(idx.value)
 
 

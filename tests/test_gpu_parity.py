@@ -259,9 +259,8 @@ def test_search_generic_path(n, d, switches):
 @pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 def test_search_fp32_screen_two_stage(n, d, metric):
-    """MAXPRO_FLAG_FP32_SCREEN: fp32 screening + exact fp64 re-score of one survivor per warp.
-    The returned score is always the exact criterion of the returned design; the winner equals
-    the exact search's unless two of the best lie within fp32 noise (not the case for these seeds)."""
+    """MAXPRO_FLAG_FP32_SCREEN through build_lhd: fp32 screening with a proven bound + exact fp64 re-score of the
+    survivors (MaxPro; the flag is ignored for maximin).  Same design, score and index as the exact search."""
     for iters, seed in ((20_000, 42), (1 << 21, 7)):
         design, s, i = engine.build_lhd(n, d, iters, metric, seed, flags=1)
         _, s_exact, i_exact = engine.build_lhd(n, d, iters, metric, seed)
@@ -654,6 +653,64 @@ def test_score_batch_psi_ties_go_to_later_index():
     dup = np.concatenate([best[None], base, best[None]])
     _, arg2 = engine.score_batch(dup, METRIC_MAXPRO)
     assert arg2 == len(dup) - 1 == oracle.score_batch(dup, METRIC_MAXPRO)[1]
+
+
+# ---------------------------------------------------------------- two-stage search (fp32 screen + exact re-score)
+
+@pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
+def test_screen_bound_and_survivors_against_oracle(n, d):
+    """Stage 1 alone (maxpro_debug_screen): its fp32 sums against the oracle's S for every candidate of a range, and
+    its survivor list against what the proven bound promises -- every candidate that can be the winner or tie with
+    it is on the list; the list is a small fraction of the range."""
+    seed, lo, hi = 42, 1000, 1000 + 40_000
+    surv, count, sums = _lib.debug_screen(n, d, seed, lo, hi, want_sums=True)
+    assert count == len(surv) < (hi - lo) // 10
+    designs = oracle.generate_batch(n, d, seed, lo, hi - lo)
+    S = np.array([oracle.maxpro_sum(x) for x in designs])
+    rel = np.abs(sums - S) / S
+    best = int(np.argmin(S))
+    good = S <= 4.0 * S[best]
+    assert rel[good].max() < 0.05, rel[good].max()      # the analytic bound is ~3-4 % at these sums
+    assert np.median(rel) < 1e-4                         # and the typical error is far below it
+    # the promise: whoever is within the tie band of the true minimum survived ...
+    must = {lo + int(i) for i in np.nonzero(S <= S[best] * (1 + 1e-9))[0]}
+    assert must <= set(int(v) for v in surv)
+    # ... and so did everyone whose fp32 sum is under the smallest threshold any candidate implies
+    w_min = min(_lib.debug_screen_threshold(n, d, float(v)) for v in np.sort(sums)[:200])
+    for i in np.nonzero(sums <= w_min)[0]:
+        assert lo + int(i) in must or (lo + int(i)) in set(int(v) for v in surv)
+    # the threshold of a candidate is a true upper bound on every fp32 sum of candidates at or below its true S
+    for i in np.argsort(S)[:50]:
+        w = _lib.debug_screen_threshold(n, d, float(sums[i]))
+        assert np.all(sums[S <= S[i]] <= w)
+
+
+@pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
+def test_two_stage_search_returns_the_exact_winner(n, d, switches):
+    """MAXPRO_FLAG_FP32_SCREEN must return what the exact search returns: index, score bits, tie rule."""
+    s_ref, i_ref = oracle.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000)
+    assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000)
+    assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1)[1] == i_ref
+    for seed in range(8):
+        lo = seed * (1 << 33)
+        exact = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24))
+        fast = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24), flags=1)
+        assert fast == exact, (seed, fast, exact)
+    # ragged and tiny ranges, and a survivor list that overflows (stage 2 then scores the whole range)
+    for lo, hi in ((5, 6), (5, 5 + 383), (5, 5 + 385), (0, 148 * 384 + 17)):
+        assert engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi)
+    switches.set("MAXPRO_SCREEN_CAP", "3")
+    assert engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22)
+    switches.clear("MAXPRO_SCREEN_CAP")
+    # the flag is ignored where stage 1 does not apply
+    assert engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000, flags=1) == engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000)
+    assert engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000, flags=1) == engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000)
+    # both design streams
+    _lib.set_stream_version(1)
+    try:
+        assert engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22)
+    finally:
+        _lib.set_stream_version(2)
 
 
 # ---------------------------------------------------------------- devices, scratch
