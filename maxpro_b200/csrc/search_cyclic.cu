@@ -142,6 +142,85 @@ __device__ __forceinline__ void cyc_generate_three(unsigned char* cand, uint32_t
     cyc_generate_blocks<N, D, C, GEN>(cand + (g ? 2u : 0u) * DB, g ? 2u : 0u, g ? H : NB - H, H, s_lo, s_hi, c1, c0);
 }
 
+// ---- LHD-mix v2 generation for the two-lane layout: short dependent chains ---------------------------------------
+// A Fisher-Yates step reads a position an EARLIER step of the same column may have written, so a column is a chain
+// of dependent shared-memory round trips (~35 cycles each): with Philox gone that latency, not the instruction
+// count, is what generation costs.  Two things shorten the chain:
+//   * the two elements of a draw block are loaded TOGETHER, before either is stored; what the second one would
+//     have read after the first one's stores is patched in from registers (it can only alias a[2b] or a[j0]);
+//   * two columns are walked side by side by each lane (lane g: column g all the way, and half of the third
+//     column -- lane 0 its first half while t < H, lane 1 the rest afterwards), predicated, not branched.
+// 25 block steps per candidate instead of 76 element steps.
+__device__ __forceinline__ double cyc_lds(unsigned int addr, bool on, double keep) {
+    double t = keep;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.shared.f64 %0, [%1]; }" : "+d"(t) : "r"(addr), "r"((unsigned int)on) : "memory");
+    return t;
+}
+__device__ __forceinline__ void cyc_sts(unsigned int addr, double v, bool on) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(addr), "d"(v), "r"((unsigned int)on) : "memory");
+}
+
+struct CycBlockDraw { uint32_t j0, j1; double v0, v1; };
+
+__device__ __forceinline__ CycBlockDraw cyc_draw_block_v2(uint32_t& x, uint32_t kb, uint32_t b, double c1, double c0, bool advance) {
+    CycBlockDraw r;
+    uint32_t jit0, jit1;
+    mulhilo32(lhd2_mix32(x), 2u * b + 1u, r.j0, jit0);
+    mulhilo32(lhd2_mix32(x + kb), 2u * b + 2u, r.j1, jit1);
+    if (advance) x += 2u * kb;  // Weyl sequence A + i B
+    r.v0 = lhd2_value(2u * b, jit0, c1, c0);
+    r.v1 = lhd2_value(2u * b + 1u, jit1, c1, c0);
+    return r;
+}
+
+template <int N, int D, int C>
+__device__ __forceinline__ void cyc_generate_v2(unsigned int cand, uint32_t s_lo, uint32_t s_hi, double c1, double c0, int g,
+                                                unsigned int group_mask) {
+    static_assert(N % 2 == 0 && (D == 2 || D == 3), "row blocks of two; two lanes own two or three columns");
+    constexpr int NB = N / 2, H = (NB + 1) / 2;
+    constexpr unsigned RB = Layout<N, D, C>::kRowBytes, DB = Layout<N, D, C>::kDimBytes;
+    uint32_t xp, pb, xs = 0u, sb = 0u;
+    lhd2_column_key((uint32_t)g, s_lo, s_hi, xp, pb);
+    if (D == 3) {
+        lhd2_column_key(2u, s_lo, s_hi, xs, sb);
+        if (g) xs += (uint32_t)(2 * H) * sb;  // lane 1 takes the third column over at block H
+    }
+    const unsigned int colp = cand + (unsigned int)g * DB, cols = cand + 2u * DB;
+    auto phase = [&](int t_begin, int t_end, bool sec) {
+#pragma unroll 2
+        for (int t = t_begin; t < t_end; ++t) {
+            const CycBlockDraw P = cyc_draw_block_v2(xp, pb, (uint32_t)t, c1, c0, true);
+            CycBlockDraw S{};
+            if (D == 3) S = cyc_draw_block_v2(xs, sb, (uint32_t)t, c1, c0, sec);
+            const unsigned int a0 = (unsigned int)(2 * t) * RB;
+            // both elements of both blocks: loads first
+            double p0 = cyc_lds(colp + P.j0 * RB, true, 0.0), p1 = cyc_lds(colp + P.j1 * RB, true, 0.0);
+            double q0 = 0.0, q1 = 0.0;
+            if (D == 3) { q0 = cyc_lds(cols + S.j0 * RB, sec, 0.0); q1 = cyc_lds(cols + S.j1 * RB, sec, 0.0); }
+            // what element 2t+1 reads AFTER the stores of element 2t
+            if (P.j1 == P.j0) p1 = P.v0; else if (P.j1 == 2u * t) p1 = p0;
+            if (D == 3) { if (S.j1 == S.j0) q1 = S.v0; else if (S.j1 == 2u * t) q1 = q0; }
+            cyc_sts(colp + a0, p0, true);
+            cyc_sts(colp + P.j0 * RB, P.v0, true);
+            cyc_sts(colp + a0 + RB, p1, true);
+            cyc_sts(colp + P.j1 * RB, P.v1, true);
+            if (D == 3) {
+                cyc_sts(cols + a0, q0, sec);
+                cyc_sts(cols + S.j0 * RB, S.v0, sec);
+                cyc_sts(cols + a0 + RB, q1, sec);
+                cyc_sts(cols + S.j1 * RB, S.v1, sec);
+            }
+        }
+    };
+    if (D == 3) {
+        phase(0, H, g == 0);
+        __syncwarp(group_mask);  // the third column's first half is in place before lane 1 continues it
+        phase(H, NB, g == 1);
+    } else {
+        phase(0, NB, false);
+    }
+}
+
 // One tile of the cyclic schedule: R rows against the lane's KP shifts.  The R + KP - 1 partner rows
 // are read once for all shifts (16 row loads per 60 pairs at R = 5, KP = 12).  Tiles whose partner
 // rows stay below N for both lanes (WRAP = false) address them as base + immediate; only the
@@ -341,7 +420,9 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
         if (active && SUPPLIED) {
             in_cube = cyc_load_design<N, D, C>(cand, p.designs + idx * (unsigned long long)(N * D), g);
         } else if (active) {
-            if (D == 3) {
+            if (GEN == 2 && N % 2 == 0) {
+                cyc_generate_v2<N, D, C>((unsigned int)__cvta_generic_to_shared(cand), s_lo, s_hi, p.c1, p.c0, g, group_mask);
+            } else if (D == 3) {
                 cyc_generate_three<N, C, GEN>(cand, s_lo, s_hi, p.c1, p.c0, g, group_mask);
             } else {
 #pragma unroll 1

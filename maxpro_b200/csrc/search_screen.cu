@@ -144,36 +144,53 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
             const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
             // ---- generation: the design stream's draws and shuffle (philox.cuh); values as exact integers (see header)
-#pragma unroll 1
-            for (int k = 0; k < D; ++k) {
-                const unsigned int col = base + k * DS;
-                const float scale = k == 0 ? p.col0_scale : 1.0f;
-                uint32_t ka = 0u, kb = 0u, x = 0u;
-                if (GEN == 2) { lhd2_column_key((uint32_t)k, s_lo, s_hi, ka, kb); x = ka; }
+            // The D columns are independent Fisher-Yates chains (each step reads what an earlier step of the SAME
+            // column wrote), so they are walked side by side: D loads in flight per step instead of one.
+            uint32_t kb[D], x[D];
+            if (GEN == 2) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)k, s_lo, s_hi, x[k], kb[k]);
+            }
 #pragma unroll 2
-                for (int b = 0; b < NB; ++b) {
-                    uint32_t jx[2], jit[2];
+            for (int b = 0; b < NB; ++b) {
+                uint32_t jx[D][2], jit[D][2];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
                     if (GEN == 1) {
                         const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
-                        jit[0] = w.x; jx[0] = __umulhi(w.y, 2u * b + 1u);
-                        jit[1] = w.z; jx[1] = __umulhi(w.w, 2u * b + 2u);
+                        jit[k][0] = w.x; jx[k][0] = __umulhi(w.y, 2u * b + 1u);
+                        jit[k][1] = w.z; jx[k][1] = __umulhi(w.w, 2u * b + 2u);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            mulhilo32(lhd2_mix32(x), 2u * b + e + 1u, jx[e], jit[e]);
-                            x += kb;  // Weyl sequence A + i B
+                            mulhilo32(lhd2_mix32(x[k]), 2u * b + e + 1u, jx[k][e], jit[k][e]);
+                            x[k] += kb[k];  // Weyl sequence A + i B
                         }
                     }
+                }
+                // both elements of the block in all D columns: loads first, then the stores in shuffle order.  What
+                // element 2b+1 would have read after the stores of element 2b is patched in from registers (it can
+                // only alias a[2b] or a[j0]).
+                float t0[D], t1[D], v0[D], v1[D];
+                unsigned int aj0[D], aj1[D];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const uint32_t i = 2u * b + e, j = jx[e];
-                        const float v = (float)((i << 18) | (jit[e] >> 14)) * scale;
-                        const unsigned int aj = col + (j >> 1) * BS + (j & 1u) * 4u;
-                        float t;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(aj) : "memory");
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(col + (unsigned int)b * BS + e * 4u), "f"(t) : "memory");
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj), "f"(v) : "memory");
-                    }
+                for (int k = 0; k < D; ++k) {
+                    v0[k] = (float)(((2u * b) << 18) | (jit[k][0] >> 14));
+                    v1[k] = (float)(((2u * b + 1u) << 18) | (jit[k][1] >> 14));
+                    if (k == 0) { v0[k] *= p.col0_scale; v1[k] *= p.col0_scale; }
+                    aj0[k] = base + k * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
+                    aj1[k] = base + k * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
+                }
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    if (jx[k][1] == jx[k][0]) t1[k] = v0[k]; else if (jx[k][1] == 2u * b) t1[k] = t0[k];
+                    const unsigned int a0 = base + k * DS + (unsigned int)b * BS;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj0[k]), "f"(v0[k]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u), "f"(t1[k]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj1[k]), "f"(v1[k]) : "memory");
                 }
             }
             // ---- scoring: block m against blocks m+1 .. m+SH (cyclically), plus the pair inside block m
