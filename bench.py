@@ -159,6 +159,171 @@ def run_reference(args, rank, world, emit):
     emit(line)
 
 
+
+def newest_profile_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the newest
+    profiles/*_search_cyclic_metrics.csv (one launch under `ncu --set full`); None if no capture."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_search_cyclic_metrics.csv")), key=os.path.basename)  # r1k < r2a < ...: round, then pass
+    for path in reversed(files):
+        got = {}
+        try:
+            for row in csv.reader(open(path)):
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    if key in row:
+                        i = row.index(key)
+                        unit, val = row[i + 1].lower(), float(row[i + 2].replace(",", ""))
+                        got[key] = val * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+        except (OSError, ValueError, IndexError):
+            continue
+        if len(got) == 2:
+            return int(got["dram__bytes_read.sum"] + got["dram__bytes_write.sum"]), os.path.basename(path)
+    return None, None
+
+
+# ---------------------------------------------------------------- BASELINE.json configs C1-C5
+# Short in-run measurements of the five configs BASELINE.json names, each with its own parity check and its own
+# roofline (algorithmic flops of SURVEY.md 8d over the measured time, against the FP64 peak probed in this run).
+CONFIG_NAMES = ("C1", "C2", "C3", "C4", "C5")
+
+
+def _best_of(fn, reps=3):
+    best, out = None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return out, best
+
+
+def run_configs(which, rank, world, dev, peak_tflops, max_over_ranks, barrier):
+    """Returns {name: record}.  Sequential paths (C1 CLI, C5 ordering) and the millisecond-sized C2 run on rank 0
+    (replicas only); C3 shards candidate-index blocks and C4 chains across the ranks."""
+    import numpy as np
+
+    import oracle
+    from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine, shard
+
+    out = {}
+
+    def roof(rate, flops_per_unit, note=None):
+        a = rate * flops_per_unit / 1e12
+        r = {"bound": "fp64", "achieved": a, "peak": peak_tflops * world, "unit": "TFLOP/s",
+             "frac": a / (peak_tflops * world), "flops_per_unit": flops_per_unit, "traffic": None}
+        if note:
+            r["note"] = note
+        return r
+
+    if "C1" in which and rank == 0:
+        # cargo run --release -- --iterations 100000 --samples 50 --ndims 2 --metric max-pro  (src/main.rs)
+        n, d = 50, 2
+        cli = os.path.join(ROOT, "maxpro_b200", "bin", "maxpro")
+        argv = [cli, "--iterations", "100000", "--samples", "50", "--ndims", "2", "--metric", "max-pro", "--seed", "42"]
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev.index))
+        r, wall = _best_of(lambda: subprocess.run(argv, capture_output=True, text=True, env=env), 2)
+        lines = r.stdout.strip().splitlines()
+        metrics = {}
+        for ln in lines:
+            for key in ("Original metric", "Swapped metric", "Annealed metric"):
+                if ln.startswith(key + ":"):
+                    metrics[key] = float(ln.split(":", 1)[1])
+        N = 1 << 26
+        (_, s, i), t = _best_of(lambda: engine.build_lhd(n, d, N, METRIC_MAXPRO, 42), 2)
+        flops = (3 * d + 3) * n * (n - 1) // 2 + 2
+        ok = (r.returncode == 0 and len(metrics) == 3 and
+              metrics["Annealed metric"] <= metrics["Swapped metric"] <= metrics["Original metric"])
+        out["C1"] = {"workload": "CLI --iterations 100000 --samples 50 --ndims 2 --metric max-pro --seed 42 "
+                                 "(search + 20,000 swap + 80,000 jitter annealing steps, process start included)",
+                     "value": wall, "unit": "s (CLI wall, best of 2)", "cli_rc": r.returncode, "cli_metrics": metrics,
+                     "check": {"annealed <= swapped <= original": ok},
+                     "search_rate": {"value": N / t, "unit": "candidates/s", "candidates": N},
+                     "roofline": roof(N / t, flops, "n=50, d=2 MaxPro search at 2^26 candidates through build_lhd")}
+
+    if "C2" in which and rank == 0:
+        n, d, N = 50, 3, 1_000_000
+        (s, i), t = _best_of(lambda: engine.search_range(n, d, METRIC_MAXIMIN, 42, 0, N))
+        oracle.set_num_threads(os.cpu_count() or 1)
+        s_ref, i_ref = oracle.search_range(n, d, oracle.MAXIMIN, 42, 0, N)
+        Nb = 1 << 27
+        _, tb = _best_of(lambda: engine.search_range(n, d, METRIC_MAXIMIN, 42, N, N + Nb), 2)
+        flops = (3 * d + 2) * n * (n - 1) // 2
+        out["C2"] = {"workload": "maximin random search --iterations 1000000 --samples 50 --ndims 3 --seed 42",
+                     "value": t * 1e3, "unit": "ms (host call, best of 3)", "winner": {"score": s, "index": i},
+                     "check": {"winner == CPU oracle (bit-exact score, same index)": (s, i) == (s_ref, i_ref)},
+                     "steady_rate": {"value": Nb / tb, "unit": "candidates/s", "candidates": Nb},
+                     "roofline": roof(Nb / tb, flops, "steady rate at 2^27 candidates")}
+
+    if "C3" in which:
+        n, d, N = 500, 10, 10_000_000
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        engine.search_range(n, d, METRIC_MAXPRO, 42, 0, 2000)  # module load, workspace
+        barrier()
+        t0 = time.perf_counter()
+        s, i = engine.search_range(n, d, METRIC_MAXPRO, 42, lo, hi)
+        if world > 1:
+            s, i = shard.allgather_minloc(s, i, METRIC_MAXPRO, device=dev)  # 16 B per rank over NCCL
+        barrier()
+        t = max_over_ranks(time.perf_counter() - t0)
+        flops = (3 * d + 3) * n * (n - 1) // 2 + 2
+        if rank == 0:
+            Nc = 3000
+            oracle.set_num_threads(os.cpu_count() or 1)
+            s_ref, i_ref = oracle.search_range(n, d, oracle.MAXPRO, 42, 0, Nc)
+            s_gpu, i_gpu = engine.search_range(n, d, METRIC_MAXPRO, 42, 0, Nc)
+            out["C3"] = {"workload": f"MaxPro random search n=500 d=10, 1e7 candidates in index blocks over {world} GPU(s), "
+                                     "16-byte min-loc all-gather",
+                         "value": N / t, "unit": "candidates/s", "seconds": t, "winner": {"score": s, "index": i},
+                         "check": {f"first {Nc} candidates: winner index == CPU oracle, score within 1e-9":
+                                   bool(i_gpu == i_ref and abs(s_gpu - s_ref) <= 1e-9 * s_ref)},
+                         "roofline": roof(N / t, flops)}
+
+    if "C4" in which:
+        n, d, chains, steps = 1000, 20, 65536, 1000
+        x = engine.generate_lhd(n, d, 42)
+        rec = {"workload": f"anneal_lhd swap moves n=1000 d=20, {chains} chains per GPU x {steps} steps, T0=1, cooling 0.99, "
+                           f"start = generate_lhd(1000, 20, 42), chain c of rank r draws from stream 43 + r*{chains} + c",
+               "unit": "chain-steps/s"}
+        for name, metric, minimize, per_pair in (("maximin", METRIC_MAXIMIN, False, 3 * d + 2), ("maxpro", METRIC_MAXPRO, True, 3 * d + 3)):
+            engine.anneal_lhd(x, 10, 1.0, 0.99, metric, minimize, 43, True, 148)
+            barrier()
+            t0 = time.perf_counter()
+            best_design, best, chain = engine.anneal_lhd(x, steps, 1.0, 0.99, metric, minimize, 43 + rank * chains, True, chains)
+            barrier()
+            t = max_over_ranks(time.perf_counter() - t0)
+            if rank == 0:
+                start = oracle.maximin_criterion(x) if metric == METRIC_MAXIMIN else oracle.maxpro_criterion(x)
+                rescored = oracle.maximin_criterion(best_design) if metric == METRIC_MAXIMIN else oracle.maxpro_criterion(best_design)
+                never_worse = best >= start if not minimize else best <= start
+                rate = chains * world * steps / t
+                rec[name] = {"value": rate, "seconds": t, "start_metric": start, "best_metric": best, "best_chain": chain,
+                             "check": {"never worse than the input (anneal.rs:92-94,142)": bool(never_worse),
+                                       "returned design re-scored by the CPU oracle": bool(abs(rescored - best) <= 1e-9 * abs(best))},
+                             "roofline": roof(rate, 4 * (n - 2) * per_pair,
+                                              "incremental step: the 2(n-2) pairs of the two swapped rows, old and new")}
+        if rank == 0:
+            rec["value"] = rec["maximin"]["value"]
+            rec["note"] = ("headline of this config = maximin (trajectory bit-exact against the oracle in the tests). "
+                           "MaxPro at d=20 is numerically degenerate in the reference itself: every product of 20 squared "
+                           "differences is far below eps=1e-12, so psi = 3.981 for every design and accept/reject is rounding "
+                           "noise; its rate is reported as throughput only")
+            out["C4"] = rec
+
+    if "C5" in which and rank == 0:
+        n, d = 5000, 8
+        x = engine.generate_lhd(n, d, 42)
+        (ordered, perm), t = _best_of(lambda: engine.order_design(x, METRIC_MAXPRO, True))
+        _, perm_ref = oracle.order_design(x, oracle.MAXPRO, True, True)
+        flops = (3 * d + 3) * n * (n - 1) // 2
+        out["C5"] = {"workload": "order_design(generate_lhd(5000, 8, seed 42), maxpro): greedy ordering, 4,999 dependent argmin steps",
+                     "value": t * 1e3, "unit": "ms (host call, best of 3)",
+                     "check": {"permutation == incremental CPU oracle (src/order.rs:34-105 tie rules)": perm.tolist() == perm_ref.tolist()},
+                     "roofline": roof(1.0 / t, flops, "latency-bound: one cluster of CTAs, n-1 sequential steps; "
+                                                      "the reference's own O(n^4 d) formulation would be 7e14 flops")}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +332,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--candidates", type=int, default=CANDIDATES_PER_GPU, help="candidates per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="headline", choices=["headline", "all"] + list(CONFIG_NAMES),
+                    help="headline (default): the BASELINE.json metric plus a short `configs` block with C1-C5; "
+                         "C1..C5: that config alone; all: C1-C5 without the headline")
+    ap.add_argument("--no-configs", action="store_true", help="headline without the C1-C5 block")
     ap.add_argument("--stream-version", type=int, default=2, choices=[1, 2],
                     help="design stream: 2 = LHD-mix v2 (default), 1 = LHD-Philox v1")
     args = ap.parse_args()
@@ -218,6 +387,25 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.config != "headline":
+        # one BASELINE.json config (or all five) instead of the headline metric
+        which = set(CONFIG_NAMES) if args.config == "all" else {args.config}
+        probed, _ = engine.fp64_peak_probe(10)
+        peak = probed if probed >= 0.95 * NOMINAL_FP64_TFLOPS else NOMINAL_FP64_TFLOPS
+        t0 = time.perf_counter()
+        recs = run_configs(which, rank, world, dev, peak, max_over_ranks, barrier)
+        wall = time.perf_counter() - t0
+        if rank == 0:
+            first = recs[sorted(recs)[0]]
+            emit({"metric": "maxpro_baseline_config_" + args.config, "value": first["value"], "unit": first["unit"],
+                  "n_gpus": world, "steps": 1, "warmup": 0, "ms_per_step": wall * 1e3,
+                  "higher_is_better": not first["unit"].startswith(("s ", "ms ")), "scaling": "weak", "vs_baseline": None,
+                  "dtype": "f64", "data": "synthetic", "config": {"workload": first["workload"]},
+                  "roofline": first["roofline"], "configs": recs, "gpu_launches": int(_lib.kernel_launch_count())})
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     L = _lib.lib()
     per_gpu = args.candidates
@@ -299,8 +487,11 @@ def main():
     screen_ms = max_over_ranks(s0.elapsed_time(s1))
     fp32_screen = {"value": per_gpu * world * args.steps / (screen_ms * 1e-3), "unit": UNIT,
                    "same_winner_as_fp64_search": screen_winner == exact_winner,
-                   "note": "MAXPRO_FLAG_FP32_SCREEN: fp32 products/reciprocals, one survivor per warp re-scored in fp64; "
-                           "the returned score is exact, which near-tied candidate wins is not guaranteed"}
+                   "exact_winner_guaranteed": True,
+                   "note": "MAXPRO_FLAG_FP32_SCREEN: every candidate scored in fp32 (exact differences of integer-valued "
+                           "coordinates) with a proven error bound; every candidate that can still be the winner or tie "
+                           "with it goes to a survivor list that the fp64 kernel re-scores with the reference's fold "
+                           "(csrc/search_screen.cu) -- same winner, same score as the fp64 search"}
 
     # ---------------- e2e: the host-facing call, winner design back in host memory
     base = args.warmup + args.steps
@@ -333,6 +524,7 @@ def main():
         sampler.stop()
         clocks = sampler.summary(timed_lines)  # clocks seen during the device-timed region
 
+    traffic, traffic_src = newest_profile_traffic()
     line = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -345,11 +537,10 @@ def main():
                    "last_winner": {"score": last_score, "index": last_index}},
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / peak_tflops if peak_tflops else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full`
-                     # (profiles/r1g_search_cyclic_metrics.csv: 236,544 B read, 0 B written for 16.8M candidates;
-                     # it is instruction/constant fetch and does not grow with the candidate count).
-                     # Algorithmic HBM bytes per candidate: 0.
-                     "traffic": 236544,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full`, read from the
+                     # newest profiles/*_search_cyclic_metrics.csv (instruction/constant fetch; it does not grow
+                     # with the candidate count).  Algorithmic HBM bytes per candidate: 0.
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": ("DFMA probe measured in this run" if peak_tflops == probed_tflops else
                                      "nominal (the in-run DFMA probe came out lower and was discarded)")
                                     + "; MEASURED_PEAKS.json has no FP64 figure; "
@@ -372,6 +563,9 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{sample} candidates (n=50, d=3, MaxPro) in {dt:.1f} s, OpenMP over candidates, "
                                           f"{host_info()['cpu_model']}"}
+    if not args.no_configs:
+        recs = run_configs(set(CONFIG_NAMES), rank, world, dev, peak_tflops, max_over_ranks, barrier)
+        line["configs"] = recs
     if rank == 0:
         emit(line)
     if world > 1:
