@@ -8,14 +8,21 @@ A "step" is one pass of the fused generate-and-score search (src/lib.rs:65-98) o
 CANDIDATES_PER_GPU fresh candidates per GPU (weak scaling: every rank scores its own
 contiguous block of GLOBAL candidate indices; no data-path collective).
 
-  value  device-resident throughput: maxpro_search_range_device on the launching stream, timed
-         with CUDA events, max over ranks.  The search has no HBM inputs at all -- candidates
-         are generated in shared memory and only 16 bytes per CTA leave the chip.
+  value  device-resident throughput of the engine's DEFAULT search path: maxpro_search_range_device
+         on the launching stream, timed with CUDA events, max over ranks.  For this shape the
+         default is the exact two-stage search -- every candidate generated and scored in fp32 with a
+         proven error bound, every candidate that can still win re-scored in fp64 -- which returns
+         the winner, score and tie-break of the fp64-only search (tests/test_gpu_parity.py).  The
+         fp64-only kernel (MAXPRO_FLAG_FP64_ONLY) is timed the same way and reported as `fp64_only`
+         with its own FP64 roofline.  The search has no HBM inputs at all -- candidates are
+         generated in shared memory and only 16 bytes per CTA (plus 8 per survivor) leave the chip.
   e2e    the same metric through the reference-facing host call (maxpro_search_range /
          maxpro_build_lhd: scalars in, winner design out to host memory), including the
          16-byte-per-rank min-loc all-gather over NCCL when N > 1.
-  roofline      algorithmic FP64 flops ((3d+3)*n(n-1)/2 + 2 per candidate) over the
-                kernel time, against the FP64 FMA peak measured in this run by a DFMA probe.
+  roofline      algorithmic flops ((3d+3)*n(n-1)/2 + 2 per candidate) over the step
+                time, against the non-tensor FMA peak of the pipe the dominant kernel runs on,
+                measured in this run by an independent-FMA probe (FP32 for the screening kernel,
+                FP64 for `fp64_only`).
   cpu_baseline  the C/OpenMP oracle port of the reference algorithm on this box's host cores,
                 bounded sample (rank 0, N == 1 only).
 
@@ -40,6 +47,8 @@ N_POINTS, N_DIMS, SEED = 50, 3, 42
 CANDIDATES_PER_GPU = 1 << 28
 FLOPS_PER_CANDIDATE = (3 * N_DIMS + 3) * N_POINTS * (N_POINTS - 1) // 2 + 2  # 14,702
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12                          # 37.2, datasheet-level
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12                         # 74.4
+FLAG_DEFAULT, FLAG_FP32_SCREEN, FLAG_FP64_ONLY = 0, 1, 2                     # include/maxpro_b200.h
 METRIC_NAME = "maxpro_candidate_lhds_scored_per_sec_n50_d3"
 UNIT = "candidates/s"
 
@@ -160,12 +169,12 @@ def run_reference(args, rank, world, emit):
 
 
 
-def newest_profile_traffic():
+def newest_profile_traffic(kernel="search_screen"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the newest
-    profiles/*_search_cyclic_metrics.csv (one launch under `ncu --set full`); None if no capture."""
+    profiles/*_<kernel>_metrics.csv (one launch under `ncu --set full`); None if no capture."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_search_cyclic_metrics.csv")), key=os.path.basename)  # r1k < r2a < ...: round, then pass
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_{kernel}_metrics.csv")), key=os.path.basename)  # r1k < r2a < ...: round, then pass
     for path in reversed(files):
         got = {}
         try:
@@ -460,38 +469,41 @@ def main():
     rec = result.cpu().numpy()
     last_score, last_index = float(rec[:1].view(np.float64)[0]), int(rec[1:].view(np.uint64)[0])
 
-    # FP64 pipe peak of this GPU (roofline denominator), probed right after the timed region so
-    # the clocks are the ones the search ran at.  A probe that lands below the datasheet-level
-    # figure by more than 5% (clock ramp, a neighbour's power draw) is not used: the nominal
-    # figure is the more conservative denominator then.
+    # Pipe peaks of this GPU (roofline denominators), probed right after the timed region so the clocks are the
+    # ones the search ran at.  A probe that lands below the datasheet-level figure by more than 5% (clock ramp,
+    # a neighbour's power draw) is not used: the nominal figure is the more conservative denominator then.
     probed_tflops, _ = engine.fp64_peak_probe(10)
     peak_tflops = probed_tflops if probed_tflops >= 0.95 * NOMINAL_FP64_TFLOPS else NOMINAL_FP64_TFLOPS
+    probed32_tflops, _ = engine.fp32_peak_probe(10)
+    peak32_tflops = probed32_tflops if probed32_tflops >= 0.95 * NOMINAL_FP32_TFLOPS else NOMINAL_FP32_TFLOPS
 
-    # ---------------- reported separately: fp32-product screening + fp64 re-score (not a parity path)
+    # ---------------- fp64_only: every candidate scored in fp64 (the kernel the FP64 roofline describes)
     def read_result():
         r = result.cpu().numpy()
         return float(r[:1].view(np.float64)[0]), int(r[1:].view(np.uint64)[0])
-    device_step(0, flags=1)
+    device_step(0, flags=FLAG_DEFAULT)
     torch.cuda.synchronize()
-    screen_winner = read_result()
-    device_step(0, flags=0)
+    default_winner = read_result()
+    device_step(0, flags=FLAG_FP64_ONLY)
     torch.cuda.synchronize()
     exact_winner = read_result()
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record(stream)
     for s in range(args.steps):
-        device_step(args.warmup + s, flags=1)
+        device_step(args.warmup + s, flags=FLAG_FP64_ONLY)
     s1.record(stream)
     barrier()
-    screen_ms = max_over_ranks(s0.elapsed_time(s1))
-    fp32_screen = {"value": per_gpu * world * args.steps / (screen_ms * 1e-3), "unit": UNIT,
-                   "same_winner_as_fp64_search": screen_winner == exact_winner,
-                   "exact_winner_guaranteed": True,
-                   "note": "MAXPRO_FLAG_FP32_SCREEN: every candidate scored in fp32 (exact differences of integer-valued "
-                           "coordinates) with a proven error bound; every candidate that can still be the winner or tie "
-                           "with it goes to a survivor list that the fp64 kernel re-scores with the reference's fold "
-                           "(csrc/search_screen.cu) -- same winner, same score as the fp64 search"}
+    fp64_ms = max_over_ranks(s0.elapsed_time(s1))
+    fp64_rate = per_gpu * args.steps / (fp64_ms * 1e-3)
+    fp64_only = {"value": fp64_rate * world, "unit": UNIT, "ms_per_step": fp64_ms / args.steps,
+                 "same_winner_as_default_path": default_winner == exact_winner,
+                 "roofline": {"bound": "fp64", "achieved": fp64_rate * FLOPS_PER_CANDIDATE / 1e12, "peak": peak_tflops,
+                              "unit": "TFLOP/s", "frac": fp64_rate * FLOPS_PER_CANDIDATE / 1e12 / peak_tflops,
+                              "kernel": "search_cyclic_kernel<50,3,192,true,false,2>", "peak_probed": probed_tflops,
+                              "traffic": newest_profile_traffic("search_cyclic")[0],
+                              "note": "MAXPRO_FLAG_FP64_ONLY; the kernel issues ~8.3 FP64-pipe instructions per pair for 12 "
+                                      "algorithmic flops, see profiles/ for pipe utilisation"}}
 
     # ---------------- e2e: the host-facing call, winner design back in host memory
     base = args.warmup + args.steps
@@ -528,35 +540,39 @@ def main():
     line = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "maxpro_search_n50_d3 (fused Philox LHD generation + MaxPro criterion + on-chip argmin)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 screen + f64 re-score (fp64_only: f64)", "data": "synthetic",
+        "config": {"workload": "maxpro_search_n50_d3 (fused LHD generation + MaxPro criterion + on-chip argmin)",
                    "n": N_POINTS, "d": N_DIMS, "candidates_per_gpu_per_step": per_gpu, "seed": SEED,
                    "sharding": f"candidate-index blocks x{world}, min-loc all-gather (16 B/rank)",
                    "l2": "n/a: the search reads no HBM inputs (candidates are generated in shared memory); "
                          "each step scores fresh candidate indices, nothing is cached between steps",
                    "last_winner": {"score": last_score, "index": last_index}},
-        "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak_tflops if peak_tflops else None,
+        "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak32_tflops, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / peak32_tflops if peak32_tflops else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full`, read from the
-                     # newest profiles/*_search_cyclic_metrics.csv (instruction/constant fetch; it does not grow
-                     # with the candidate count).  Algorithmic HBM bytes per candidate: 0.
+                     # newest profiles/*_search_screen_metrics.csv (instruction/constant fetch plus the survivor
+                     # list; it does not grow with the candidate count).  Algorithmic HBM bytes per candidate: 0.
                      "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": ("DFMA probe measured in this run" if peak_tflops == probed_tflops else
-                                     "nominal (the in-run DFMA probe came out lower and was discarded)")
-                                    + "; MEASURED_PEAKS.json has no FP64 figure; "
-                                    f"nominal 148 SM x 64 lanes x 2 x 1.965 GHz = {NOMINAL_FP64_TFLOPS:.1f}",
-                     "peak_probed": probed_tflops,
-                     "flops_per_candidate": FLOPS_PER_CANDIDATE, "kernel": "search_cyclic_kernel<50,3,192,true>",
+                     "peak_source": ("FFMA probe measured in this run" if peak32_tflops == probed32_tflops else
+                                     "nominal (the in-run FFMA probe came out lower and was discarded)")
+                                    + "; MEASURED_PEAKS.json has no non-tensor FP32/FP64 figure; "
+                                    f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = {NOMINAL_FP32_TFLOPS:.1f}",
+                     "peak_probed": probed32_tflops,
+                     "flops_per_candidate": FLOPS_PER_CANDIDATE, "kernel": "search_screen_kernel<50,3,384,2>",
                      "kernel_ms_per_launch": kernel_ms, "candidates_per_launch": per_gpu,
-                     "note": "algorithmic flops; the kernel issues ~8.3 FP64-pipe instructions per pair for 12 "
-                             "algorithmic flops, see profiles/ for pipe utilisation"},
+                     "note": "algorithmic flops of the criterion (12 per pair) over the whole step -- the screening kernel "
+                             "plus the fp64 re-score of its survivors and a 1-thread counter reset, so the kernel's own "
+                             "fraction is slightly higher; the screening kernel issues 8 fp32 lane-operations per pair. "
+                             "`fp64_only.roofline` is the FP64-pipe figure BASELINE.json's metric asks for"},
+        "path": "two-stage exact search (engine default for this shape): fp32 screening with a proven bound + fp64 re-score "
+                "of every candidate that can still win; winner, score and tie-break identical to the fp64-only search",
+        "fp64_only": fp64_only,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 16 + N_POINTS * N_DIMS * 8,
                 "note": "reference API takes scalars (n, d, iterations, metric, seed): no input buffers exist; "
                         "the winner record and the regenerated design are copied to host every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "fp32_screen": fp32_screen,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, sample, dt, cores = cpu_rate(15.0, 1 << 40, args.stream_version)

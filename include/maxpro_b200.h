@@ -53,12 +53,18 @@ typedef enum {
     MAXPRO_METRIC_MAXIMIN = 1   /* enums::Metrics::MaxiMin (src/enums.rs:6) */
 } maxpro_metric;
 
-/* flags for maxpro_search_range_device / maxpro_build_lhd_ex */
+/* flags for maxpro_search_range_device / maxpro_search_range_ex / maxpro_build_lhd_ex.
+ * Two-stage search (MaxPro at n = 50, d = 2 or 3): an fp32 screening pass with a proven error bound keeps every
+ * candidate that can still be the winner or tie with it, the exact fp64 kernel re-scores those.  Same winner,
+ * same score and same tie rule as the fp64-only search (csrc/search_screen.cu derives the bound; the parity tests
+ * compare the two paths), at about twice the rate.
+ *   MAXPRO_FLAG_DEFAULT      the engine chooses: two-stage for the shapes above when the range holds at least
+ *                            32,768 candidates, fp64-only otherwise
+ *   MAXPRO_FLAG_FP32_SCREEN  two-stage wherever the shape has a screening kernel, whatever the range size
+ *   MAXPRO_FLAG_FP64_ONLY    every candidate scored in fp64 (the kernel the FP64 roofline figures describe) */
 #define MAXPRO_FLAG_DEFAULT 0u
-/* Two-stage search (MaxPro at n = 50, d = 2 or 3; ignored elsewhere): an fp32 screening pass with a proven error
- * bound keeps every candidate that can still be the winner, the exact fp64 kernel re-scores those.  Same winner,
- * same score and same tie rule as the default search (csrc/search_screen.cu derives the bound), about twice the rate. */
 #define MAXPRO_FLAG_FP32_SCREEN 1u
+#define MAXPRO_FLAG_FP64_ONLY 2u
 
 /* ---- housekeeping ------------------------------------------------------ */
 MAXPRO_API const char *maxpro_last_error(void);
@@ -205,6 +211,8 @@ MAXPRO_API int maxpro_score_batch_device(const double *d_designs, uint64_t b, ui
  * kernel (the roofline denominator; MEASURED_PEAKS.json has no FP64 figure).
  * tflops = 2 * DFMA/s / 1e12 (best of `repeats`). */
 MAXPRO_API int maxpro_fp64_peak_probe(int repeats, double *tflops, double *kernel_ms);
+/* The same for the FP32 FMA pipe (independent FFMA chains): the denominator for the fp32 screening stage. */
+MAXPRO_API int maxpro_fp32_peak_probe(int repeats, double *tflops, double *kernel_ms);
 
 /* ---- test and tooling entry points (not part of the reference's surface) ---- */
 

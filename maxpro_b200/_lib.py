@@ -26,7 +26,7 @@ EXPORTS = [
     "maxpro_l2_distance", "maxpro_score_batch", "maxpro_build_lhd", "maxpro_build_lhd_ex",
     "maxpro_search_range", "maxpro_reduce_best", "maxpro_anneal_lhd", "maxpro_order_design",
     "maxpro_search_workspace_bytes", "maxpro_search_range_device",
-    "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe",
+    "maxpro_score_workspace_bytes", "maxpro_score_batch_device", "maxpro_fp64_peak_probe", "maxpro_fp32_peak_probe",
     "maxpro_release_device_cache", "maxpro_set_device_cache_limit", "maxpro_set_devices", "maxpro_get_devices",
     "maxpro_anneal_scratch_bytes", "maxpro_debug_set", "maxpro_debug_pow", "maxpro_set_stream_version",
     "maxpro_get_stream_version", "maxpro_search_range_ex", "maxpro_debug_screen", "maxpro_debug_screen_threshold",
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         "maxpro_score_workspace_bytes": (i32, [u64, u64, u64, szp]),
         "maxpro_score_batch_device": (i32, [vp, u64, u64, u64, i32, vp, vp, vp, C.c_size_t, vp]),
         "maxpro_fp64_peak_probe": (i32, [i32, dp, dp]),
+        "maxpro_fp32_peak_probe": (i32, [i32, dp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

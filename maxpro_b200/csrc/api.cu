@@ -173,6 +173,7 @@ __global__ void debug_pow_kernel(const double* x, const double* y, unsigned long
 // ---- search dispatch -----------------------------------------------------------
 
 constexpr size_t kMaxBlockRecs = 4096;
+constexpr unsigned long long kScreenMinRange = 1ull << 15;  // MAXPRO_FLAG_DEFAULT: ranges below this go straight to the fp64 kernel
 constexpr unsigned int kSurvivorCap = 1u << 20;  // 8 MB; a 2^28-candidate range leaves a few tens of thousands
 constexpr size_t kGenericChunkBytes = 128ull << 20;
 
@@ -225,7 +226,6 @@ SearchWs carve_search_ws(void* base, unsigned long long n, unsigned long long d)
 int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, uint64_t lo, uint64_t hi,
                              uint32_t flags, void* d_result, void* d_ws, size_t ws_bytes, cudaStream_t stream,
                              int sms) {
-    (void)flags;
     if (n == 0) return fail(MAXPRO_ERR_INVALID, "n_samples must be positive and nonzero");
     if (d == 0) return fail(MAXPRO_ERR_INVALID, "n_dim must be positive and nonzero");
     if (!metric_ok(metric)) return fail(MAXPRO_ERR_INVALID, "Metric must be 'maxpro' or 'maximin'.");
@@ -253,8 +253,8 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
     mp::count_launch();
     int cyc_cands = 0, scr_cands = 0;
-    if ((flags & MAXPRO_FLAG_FP32_SCREEN) && mp::search_screen_supported(n, d, metric, &scr_cands) &&
-        mp::search_cyclic_supported(n, d, &cyc_cands)) {
+    const bool want_screen = !(flags & MAXPRO_FLAG_FP64_ONLY) && ((flags & MAXPRO_FLAG_FP32_SCREEN) || hi - lo >= kScreenMinRange);
+    if (want_screen && mp::search_screen_supported(n, d, metric, &scr_cands) && mp::search_cyclic_supported(n, d, &cyc_cands)) {
         // stage 1: fp32 screening with a proven bound; every candidate that can still win goes to the survivor list
         mp::SearchLaunch L{};
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
@@ -954,6 +954,41 @@ int maxpro_fp64_peak_probe(int repeats, double* tflops, double* kernel_ms) {
         cudaEventRecord(e1, st);
         if (e == cudaSuccess) e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(e, "dfma probe"); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)grid;
+    *tflops = flops / (best_ms * 1e-3) / 1e12;
+    if (kernel_ms) *kernel_ms = best_ms;
+    return MAXPRO_OK;
+}
+
+int maxpro_fp32_peak_probe(int repeats, double* tflops, double* kernel_ms) {
+    if (!tflops) return fail(MAXPRO_ERR_INVALID, "null pointer");
+    int sms = 0;
+    if (int rc = ensure_device(&sms)) return rc;
+    if (repeats < 1) repeats = 1;
+    DevBuf sink;
+    CUDA_TRY(sink.alloc(17 * sizeof(float)));
+    cudaStream_t st = cudaStreamPerThread;
+    float vals[17];
+    vals[0] = 0.f;
+    for (int i = 0; i < 16; ++i) vals[i + 1] = 0.9999f + 1e-5f * (float)i;
+    CUDA_TRY(cudaMemcpyAsync(sink.p, vals, sizeof(vals), cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int threads = 256, grid = sms * 8, iters = 1 << 16;
+    double best_ms = 1e30;
+    for (int r = 0; r < repeats + 1; ++r) {  // first launch is warm-up
+        cudaEventRecord(e0, st);
+        cudaError_t e = mp::launch_ffma_probe(sink.as<float>(), grid, threads, iters, st);
+        cudaEventRecord(e1, st);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(e, "ffma probe"); }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         if (r > 0 && ms < best_ms) best_ms = ms;

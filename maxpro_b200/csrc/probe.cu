@@ -59,6 +59,29 @@ cudaError_t launch_dfma_probe(double* d_sink, int grid, int threads, int iters, 
     return cudaGetLastError();
 }
 
+// FP32 FMA-pipe peak probe (roofline denominator of the fp32 screening kernel): eight independent three-register
+// FFMA chains per thread, no memory traffic in the loop.
+__global__ void sp_chain_kernel(float* sink, int iters, const float* vals) {
+    float x[8], y[8], z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x * 1e-6f + i; y[i] = vals[i]; z[i] = vals[i + 8]; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], y[i], z[i]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 12345.678f) sink[0] = s;
+}
+
+cudaError_t launch_ffma_probe(float* d_sink, int grid, int threads, int iters, cudaStream_t stream) {
+    // d_sink: 17 floats -- [0] sink, [1..16] operand values (set by the caller)
+    sp_chain_kernel<<<grid, threads, 0, stream>>>(d_sink, iters, d_sink + 1);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int ILP>
 static void launch_ilp(int op, int grid, int threads, double* sink, int iters, const double* vals) {
     switch (op) {

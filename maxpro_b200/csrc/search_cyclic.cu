@@ -166,11 +166,28 @@ struct CycBlockDraw { uint32_t j0, j1; double v0, v1; };
 __device__ __forceinline__ CycBlockDraw cyc_draw_block_v2(uint32_t& x, uint32_t kb, uint32_t b, double c1, double c0, bool advance) {
     CycBlockDraw r;
     uint32_t jit0, jit1;
-    mulhilo32(lhd2_mix32(x), 2u * b + 1u, r.j0, jit0);
-    mulhilo32(lhd2_mix32(x + kb), 2u * b + 2u, r.j1, jit1);
+#ifndef CYC_KNOCK
+#define CYC_KNOCK 0
+#endif
+#if CYC_KNOCK & 1   // no mixer
+    const uint32_t w0 = x, w1 = x + kb;
+#else
+    const uint32_t w0 = lhd2_mix32(x), w1 = lhd2_mix32(x + kb);
+#endif
+#if CYC_KNOCK & 2   // no wide multiply
+    r.j0 = (w0 >> 28) & (2u * b); jit0 = w0; r.j1 = (w1 >> 28) & (2u * b + 1u); jit1 = w1;
+#else
+    mulhilo32(w0, 2u * b + 1u, r.j0, jit0);
+    mulhilo32(w1, 2u * b + 2u, r.j1, jit1);
+#endif
     if (advance) x += 2u * kb;  // Weyl sequence A + i B
+#if CYC_KNOCK & 4   // no DFMA in the value
+    r.v0 = __hiloint2double((int)(0x3fe00000u | (2u * b)), (int)jit0);
+    r.v1 = __hiloint2double((int)(0x3fe00000u | (2u * b + 1u)), (int)jit1);
+#else
     r.v0 = lhd2_value(2u * b, jit0, c1, c0);
     r.v1 = lhd2_value(2u * b + 1u, jit1, c1, c0);
+#endif
     return r;
 }
 
@@ -195,6 +212,11 @@ __device__ __forceinline__ void cyc_generate_v2(unsigned int cand, uint32_t s_lo
             if (D == 3) S = cyc_draw_block_v2(xs, sb, (uint32_t)t, c1, c0, sec);
             const unsigned int a0 = (unsigned int)(2 * t) * RB;
             // both elements of both blocks: loads first
+#if CYC_KNOCK & 8   // no shared-memory traffic: one store per block so that the draws stay live
+            cyc_sts(colp + a0, P.v0 + P.v1 + (double)(P.j0 + P.j1), true);
+            if (D == 3) cyc_sts(cols + a0, S.v0 + S.v1 + (double)(S.j0 + S.j1), sec);
+            continue;
+#endif
             double p0 = cyc_lds(colp + P.j0 * RB, true, 0.0), p1 = cyc_lds(colp + P.j1 * RB, true, 0.0);
             double q0 = 0.0, q1 = 0.0;
             if (D == 3) { q0 = cyc_lds(cols + S.j0 * RB, sec, 0.0); q1 = cyc_lds(cols + S.j1 * RB, sec, 0.0); }
@@ -515,7 +537,7 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
         } else if (active && (CYC_EXP == 1 || CYC_EXP == 2) && rnd > 0) {
             // experiment: no stand-alone generation after the first round
         } else if (active) {
-            if (GEN == 2 && N % 2 == 0) {
+            if (GEN == 2 && N % 2 == 0 && CYC_EXP != 9) {
                 cyc_generate_v2<N, D, C>((unsigned int)__cvta_generic_to_shared(cand), s_lo, s_hi, p.c1, p.c0, g, group_mask);
             } else if (D == 3) {
                 cyc_generate_three<N, C, GEN>(cand, s_lo, s_hi, p.c1, p.c0, g, group_mask);

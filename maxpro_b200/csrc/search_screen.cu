@@ -45,6 +45,13 @@
 
 #include <cmath>
 
+#ifndef SCR_EXP
+#define SCR_EXP 0
+#endif
+#ifndef SCR_MUFU
+#define SCR_MUFU 0
+#endif
+
 namespace mp {
 
 struct ScreenBound {
@@ -147,6 +154,7 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
             // The D columns are independent Fisher-Yates chains (each step reads what an earlier step of the SAME
             // column wrote), so they are walked side by side: D loads in flight per step instead of one.
             uint32_t kb[D], x[D];
+            if (SCR_EXP == 1 && rnd > 0) goto gen_done;  // experiment: scoring only
             if (GEN == 2) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)k, s_lo, s_hi, x[k], kb[k]);
@@ -193,10 +201,11 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj1[k]), "f"(v1[k]) : "memory");
                 }
             }
+        gen_done:
             // ---- scoring: block m against blocks m+1 .. m+SH (cyclically), plus the pair inside block m
             double acc = 0.0;
 #pragma unroll 1
-            for (int m = 0; m < NB; ++m) {
+            for (int m = 0; m < (SCR_EXP == 3 ? 1 : NB); ++m) {
                 f2 ax[D], ay[D];
                 float q_in = 1.0f;
 #pragma unroll
@@ -222,11 +231,20 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                         qb = k == 0 ? db : mul2(qb, db);
                     }
                     const f2 pa = fma2(qa, qa, eps2), pb = fma2(qb, qb, eps2);
+#if SCR_MUFU
+                    float pa0, pa1, pb0, pb1;
+                    unpk(pa, pa0, pa1); unpk(pb, pb0, pb1);
+                    const f2 ra = pk(rcp_approx(pa0), rcp_approx(pa1)), rb = pk(rcp_approx(pb0), rcp_approx(pb1));
+                    if (sft == 1) { ch[0].num = ra; ch[1].num = rb; } else { ch[0].num = add2(ch[0].num, ra); ch[1].num = add2(ch[1].num, rb); }
+                }
+                const f2 v = add2(ch[0].num, ch[1].num);
+#else
                     const int t0 = 2 * (sft - 1);  // term counter of this row block: chain t % 4, started by its first term
                     if (t0 < 4) ch[t0 % 4].start(pa); else ch[t0 % 4].push(pa);
                     if (t0 + 1 < 4) ch[(t0 + 1) % 4].start(pb); else ch[(t0 + 1) % 4].push(pb);
                 }
                 const f2 v = add2(add2(ch[0].value(), ch[1].value()), add2(ch[2].value(), ch[3].value()));
+#endif
                 float v0, v1;
                 unpk(v, v0, v1);
                 acc += (double)(v0 + v1 + inner);
@@ -240,13 +258,13 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
             if (active) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
             __syncthreads();
             const double thr = __longlong_as_double((long long)cta_thr);
-            if (active && s <= thr) {
+            if (active && s <= thr && (SCR_EXP == 0 || (idx & 0xFFFFF) == 0)) {
                 const unsigned int pos = atomicAdd(p.count, 1u);
                 if (pos < p.cap) p.list[pos] = idx;
             }
         } else {
             const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
-            if (active && s <= thr) {
+            if (active && s <= thr && (SCR_EXP == 0 || (idx & 0xFFFFF) == 0)) {
                 const unsigned int pos = atomicAdd(p.count, 1u);
                 if (pos < p.cap) p.list[pos] = idx;
                 const double w = screen_threshold(s, p.bound);

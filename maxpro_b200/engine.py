@@ -122,3 +122,10 @@ def fp64_peak_probe(repeats: int = 5):
     ms = C.c_double(0)
     check(lib().maxpro_fp64_peak_probe(repeats, C.byref(t), C.byref(ms)))
     return t.value, ms.value
+
+
+def fp32_peak_probe(repeats: int = 5):
+    t = C.c_double(0)
+    ms = C.c_double(0)
+    check(lib().maxpro_fp32_peak_probe(repeats, C.byref(t), C.byref(ms)))
+    return t.value, ms.value

@@ -263,13 +263,14 @@ def test_search_fp32_screen_two_stage(n, d, metric):
     survivors (MaxPro; the flag is ignored for maximin).  Same design, score and index as the exact search."""
     for iters, seed in ((20_000, 42), (1 << 21, 7)):
         design, s, i = engine.build_lhd(n, d, iters, metric, seed, flags=1)
-        _, s_exact, i_exact = engine.build_lhd(n, d, iters, metric, seed)
+        _, s_exact, i_exact = engine.build_lhd(n, d, iters, metric, seed, flags=2)
+        assert (s_exact, i_exact) == engine.build_lhd(n, d, iters, metric, seed)[1:]  # MAXPRO_FLAG_DEFAULT picks one of the two
         assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
         crit = oracle.maxpro_criterion(design) if metric == METRIC_MAXPRO else oracle.maximin_criterion(design)
         assert math.isclose(s, crit, rel_tol=REL)
         assert (i, s) == (i_exact, s_exact)
     # shapes without a screening kernel fall back to the exact path
-    assert engine.build_lhd(13, 5, 5000, metric, 3, flags=1)[1:] == engine.build_lhd(13, 5, 5000, metric, 3)[1:]
+    assert engine.build_lhd(13, 5, 5000, metric, 3, flags=1)[1:] == engine.build_lhd(13, 5, 5000, metric, 3, flags=2)[1:]
 
 
 def test_search_one_point_and_none_metric():
@@ -689,26 +690,27 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
 def test_two_stage_search_returns_the_exact_winner(n, d, switches):
     """MAXPRO_FLAG_FP32_SCREEN must return what the exact search returns: index, score bits, tie rule."""
     s_ref, i_ref = oracle.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000)
-    assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000)
+    assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=2)
     assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1)[1] == i_ref
     for seed in range(8):
         lo = seed * (1 << 33)
-        exact = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24))
+        exact = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24), flags=2)
+        assert exact == engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24))  # MAXPRO_FLAG_DEFAULT
         fast = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24), flags=1)
         assert fast == exact, (seed, fast, exact)
     # ragged and tiny ranges, and a survivor list that overflows (stage 2 then scores the whole range)
     for lo, hi in ((5, 6), (5, 5 + 383), (5, 5 + 385), (0, 148 * 384 + 17)):
-        assert engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi)
+        assert engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi, flags=2)
     switches.set("MAXPRO_SCREEN_CAP", "3")
-    assert engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22)
+    assert engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22, flags=2)
     switches.clear("MAXPRO_SCREEN_CAP")
     # the flag is ignored where stage 1 does not apply
-    assert engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000, flags=1) == engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000)
-    assert engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000, flags=1) == engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000)
+    assert engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000, flags=1) == engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000, flags=2)
+    assert engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000, flags=1) == engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000, flags=2)
     # both design streams
     _lib.set_stream_version(1)
     try:
-        assert engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22)
+        assert engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22, flags=2)
     finally:
         _lib.set_stream_version(2)
 
