@@ -48,9 +48,6 @@
 #ifndef SCR_EXP
 #define SCR_EXP 0
 #endif
-#ifndef SCR_MUFU
-#define SCR_MUFU 0
-#endif
 
 namespace mp {
 
@@ -113,7 +110,7 @@ __device__ __forceinline__ f2 lds2(unsigned int addr) { f2 r; asm volatile("ld.s
 // sum of reciprocals of up to six packed terms without a divide per term (see header): first term starts the chain
 struct Chain2 {
     f2 num, den;
-    __device__ __forceinline__ void start(f2 p) { num = pk(1.0f, 1.0f); den = p; }
+    __device__ __forceinline__ void start(f2 p) { num = pk(1.0f, 1.0f); den = p; }  // num is folded into the first push by the compiler
     __device__ __forceinline__ void push(f2 p) { num = fma2(num, p, den); den = mul2(den, p); }
     __device__ __forceinline__ f2 value() const {
         float d0, d1;
@@ -130,7 +127,8 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     __shared__ unsigned long long cta_thr;  // smallest survivor threshold W implied by a candidate of this CTA (bits of a positive double)
     static_assert(N % 2 == 0 && (N / 2) % 2 == 1 && N <= 64, "row blocks: an odd number of them, strata below 2^6");
     constexpr int NB = N / 2, SH = (NB - 1) / 2;  // row blocks; block shifts 1..SH cover every pair of blocks once
-    static_assert((2 * SH) % 4 == 0 && (2 * SH) / 4 <= 6, "four chains of at most six terms per row block");
+    constexpr int kChainTerms = 6;  // packed terms a Chain2 holds inside the fp32 range (see the header comment)
+    static_assert(SH > kChainTerms && SH <= 2 * kChainTerms, "every row meets SH terms: two chains of at most six");
     constexpr unsigned BS = C * 8u, DS = NB * BS;
     const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + threadIdx.x * 8u;
 
@@ -202,51 +200,95 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                 }
             }
         gen_done:
-            // ---- scoring: block m against blocks m+1 .. m+SH (cyclically), plus the pair inside block m
+            // ---- scoring.  Block m is paired with blocks m+1 .. m+SH (cyclically): every pair of blocks once.  The
+            // blocks are walked in TILES of two (m, m+1: four rows held as broadcast pairs), so that a partner block
+            // read from shared memory serves eight pairs: blocks m+2 .. m+SH are partners of both, block m+1 is the
+            // first partner of block m (already in registers), block m+SH+1 the last partner of block m+1.  Each row
+            // meets SH = 12 packed terms: two reciprocal chains of six.  The odd block out (NB is odd) goes last.
             double acc = 0.0;
+            auto block_off = [&](unsigned int mm) { const unsigned int o = mm * BS; return min(o, o - DS); };  // block index modulo NB
+            auto load_block = [&](f2 (&b)[D], unsigned int off) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) b[k] = lds2(base + k * DS + off);
+            };
+            auto term2 = [&](const f2 (&a)[D], const f2 (&b)[D]) {
+                f2 q = sub2(a[0], b[0]);
+#pragma unroll
+                for (int k = 1; k < D; ++k) q = mul2(q, sub2(a[k], b[k]));
+                return fma2(q, q, eps2);
+            };
 #pragma unroll 1
-            for (int m = 0; m < (SCR_EXP == 3 ? 1 : NB); ++m) {
-                f2 ax[D], ay[D];
+            for (int t = 0; t < (SCR_EXP == 3 ? 1 : NB / 2); ++t) {
+                const unsigned int m = 2u * (unsigned int)t;
+                f2 A1[D], X[4][D], qin;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    float a0, a1, c0, c1;
+                    unpk(lds2(base + k * DS + m * BS), a0, a1);
+                    A1[k] = lds2(base + k * DS + (m + 1u) * BS);
+                    unpk(A1[k], c0, c1);
+                    X[0][k] = pk(a0, a0); X[1][k] = pk(a1, a1); X[2][k] = pk(c0, c0); X[3][k] = pk(c1, c1);
+                    const f2 dd = sub2(pk(a0, c0), pk(a1, c1));  // the pair inside each of the two blocks
+                    qin = k == 0 ? dd : mul2(qin, dd);
+                }
+                float pi0, pi1;
+                unpk(fma2(qin, qin, eps2), pi0, pi1);
+                const float inner = rcp_approx(pi0) + rcp_approx(pi1);
+                Chain2 ch[4];
+                f2 E[D];
+                load_block(E, block_off(m + 1u + (unsigned int)SH));
+                ch[0].start(term2(X[0], A1)); ch[1].start(term2(X[1], A1));
+                ch[2].start(term2(X[2], E)); ch[3].start(term2(X[3], E));
+                f2 vsum;
+#pragma unroll
+                for (int sft = 2; sft <= SH; ++sft) {
+                    f2 B[D];
+                    load_block(B, block_off(m + (unsigned int)sft));
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const f2 pr = term2(X[r], B);
+                        if (sft - 1 == kChainTerms) {  // seventh term of the row: the first chain is full
+                            vsum = r == 0 ? ch[r].value() : add2(vsum, ch[r].value());
+                            ch[r].start(pr);
+                        } else {
+                            ch[r].push(pr);
+                        }
+                    }
+                }
+                vsum = add2(add2(vsum, ch[0].value()), add2(add2(ch[1].value(), ch[2].value()), ch[3].value()));
+                float v0, v1;
+                unpk(vsum, v0, v1);
+                acc += (double)(v0 + v1 + inner);
+            }
+            if (SCR_EXP != 3) {  // block NB-1 against blocks 0 .. SH-1, and the pair inside it
+                constexpr unsigned int m = NB - 1;
+                f2 X[2][D];
                 float q_in = 1.0f;
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     float a0, a1;
                     unpk(lds2(base + k * DS + m * BS), a0, a1);
-                    ax[k] = pk(a0, a0);
-                    ay[k] = pk(a1, a1);
+                    X[0][k] = pk(a0, a0); X[1][k] = pk(a1, a1);
                     q_in = k == 0 ? a0 - a1 : q_in * (a0 - a1);
                 }
-                const float inner = rcp_approx(fmaf(q_in, q_in, p.eps_s));  // rows 2m, 2m+1
-                Chain2 ch[4];
+                const float inner = rcp_approx(fmaf(q_in, q_in, p.eps_s));
+                Chain2 ch[2];
+                f2 vsum;
 #pragma unroll
                 for (int sft = 1; sft <= SH; ++sft) {
-                    unsigned int o = (unsigned int)(m + sft) * BS;
-                    o = min(o, o - DS);  // block index modulo NB
-                    f2 qa, qb;
+                    f2 B[D];
+                    load_block(B, (unsigned int)(sft - 1) * BS);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const f2 bk = lds2(base + k * DS + o);
-                        const f2 da = sub2(ax[k], bk), db = sub2(ay[k], bk);
-                        qa = k == 0 ? da : mul2(qa, da);
-                        qb = k == 0 ? db : mul2(qb, db);
+                    for (int r = 0; r < 2; ++r) {
+                        const f2 pr = term2(X[r], B);
+                        if (sft == 1) ch[r].start(pr);
+                        else if (sft - 1 == kChainTerms) { vsum = r == 0 ? ch[r].value() : add2(vsum, ch[r].value()); ch[r].start(pr); }
+                        else ch[r].push(pr);
                     }
-                    const f2 pa = fma2(qa, qa, eps2), pb = fma2(qb, qb, eps2);
-#if SCR_MUFU
-                    float pa0, pa1, pb0, pb1;
-                    unpk(pa, pa0, pa1); unpk(pb, pb0, pb1);
-                    const f2 ra = pk(rcp_approx(pa0), rcp_approx(pa1)), rb = pk(rcp_approx(pb0), rcp_approx(pb1));
-                    if (sft == 1) { ch[0].num = ra; ch[1].num = rb; } else { ch[0].num = add2(ch[0].num, ra); ch[1].num = add2(ch[1].num, rb); }
                 }
-                const f2 v = add2(ch[0].num, ch[1].num);
-#else
-                    const int t0 = 2 * (sft - 1);  // term counter of this row block: chain t % 4, started by its first term
-                    if (t0 < 4) ch[t0 % 4].start(pa); else ch[t0 % 4].push(pa);
-                    if (t0 + 1 < 4) ch[(t0 + 1) % 4].start(pb); else ch[(t0 + 1) % 4].push(pb);
-                }
-                const f2 v = add2(add2(ch[0].value(), ch[1].value()), add2(ch[2].value(), ch[3].value()));
-#endif
+                vsum = add2(vsum, add2(ch[0].value(), ch[1].value()));
                 float v0, v1;
-                unpk(v, v0, v1);
+                unpk(vsum, v0, v1);
                 acc += (double)(v0 + v1 + inner);
             }
             s = acc;

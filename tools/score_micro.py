@@ -4,7 +4,12 @@ import ctypes as C
 import numpy as np, torch
 from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, _lib, engine
 L = _lib.lib(); dev = torch.device("cuda", 0)
-for (n, d, b) in ((50, 3, 1 << 20), (50, 2, 1 << 20), (100, 5, 1 << 18), (500, 10, 1 << 13), (1000, 20, 1 << 11), (5000, 8, 64)):
+"""K2 on supplied designs (maxpro_score_batch_device, designs resident in HBM): rates per shape.
+usage: python tools/score_micro.py [n d]   (one shape: the ncu target)"""
+SHAPES = ((50, 3, 1 << 20), (50, 2, 1 << 20), (100, 5, 1 << 18), (500, 10, 1 << 13), (1000, 20, 1 << 11), (5000, 8, 64))
+if len(sys.argv) == 3:
+    SHAPES = tuple(s for s in SHAPES if s[:2] == (int(sys.argv[1]), int(sys.argv[2])))
+for (n, d, b) in SHAPES:
     x = torch.rand(b, n, d, dtype=torch.float64, device=dev)
     scores = torch.empty(b, dtype=torch.float64, device=dev)
     res = torch.zeros(2, dtype=torch.int64, device=dev)
