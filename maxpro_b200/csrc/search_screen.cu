@@ -48,6 +48,9 @@
 #ifndef SCR_EXP
 #define SCR_EXP 0
 #endif
+#ifndef SCR_TILE
+#define SCR_TILE 4  // row blocks per scoring tile (measured: profiles/README.md, round 2)
+#endif
 
 namespace mp {
 
@@ -119,6 +122,92 @@ struct Chain2 {
     }
 };
 
+// Score of T consecutive row blocks m .. m+T-1 (2T rows) against their partners, in scaled units: the sum of
+// 1 / p_s over those pairs (see the header).  Block b is paired with the SH = (NB-1)/2 blocks that follow it
+// (cyclically), which covers every pair of blocks once.  For a tile that is
+//   * the blocks after it INSIDE the tile (already in registers),
+//   * b "late" blocks m+SH+1 .. m+SH+b,
+//   * the SH-T+1 blocks m+T .. m+SH, which are partners of every block of the tile: one read of such a block
+//     from shared memory serves 4T pairs (T = 1: 4 pairs per read -- the first version of this kernel).
+// Every row meets SH packed terms; with SH = 12 that is two reciprocal chains of six per row (the chain switch
+// falls on the same common partner for all rows because every block has T-1 terms before its first common one).
+// Block layout: block m of dimension k of candidate c (= lane) at ((k * NB + m) * C + c) * 8, the even row in the
+// low half: one LDS.64, conflict-free across the warp.
+template <int NB, int D, int C, int T>
+__device__ __forceinline__ float screen_tile(unsigned int base, unsigned int m, f2 eps2) {
+    constexpr int SH = (NB - 1) / 2, kChainTerms = 6;
+    constexpr unsigned BS = C * 8u, DS = NB * BS;
+    static_assert(SH + 1 > kChainTerms && SH <= 2 * kChainTerms && T - 1 < kChainTerms && T <= SH, "two chains of at most six terms per row");
+    auto block_off = [&](unsigned int mm) { const unsigned int o = mm * BS; return min(o, o - DS); };  // block index modulo NB (mm < 2 NB)
+    auto load_block = [&](f2 (&b)[D], unsigned int off) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) b[k] = lds2(base + k * DS + off);
+    };
+    auto term2 = [&](const f2 (&a)[D], const f2 (&b)[D]) {
+        f2 q = sub2(a[0], b[0]);
+#pragma unroll
+        for (int k = 1; k < D; ++k) q = mul2(q, sub2(a[k], b[k]));
+        return fma2(q, q, eps2);
+    };
+    f2 A[T][D], X[T][2][D];
+    float inner = 0.0f;
+#pragma unroll
+    for (int b = 0; b < T; ++b) {
+        load_block(A[b], (m + (unsigned int)b) * BS);  // m + T - 1 < NB: no wrap
+        float q_in = 1.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float a0, a1;
+            unpk(A[b][k], a0, a1);
+            X[b][0][k] = pk(a0, a0); X[b][1][k] = pk(a1, a1);
+            q_in = k == 0 ? a0 - a1 : q_in * (a0 - a1);  // the pair inside the block
+        }
+        float e0, e1;
+        unpk(eps2, e0, e1);
+        inner += rcp_approx(fmaf(q_in, q_in, e0));
+    }
+    Chain2 ch[T][2];
+    int cnt[T];  // terms a row of block b has met (compile-time after unrolling)
+#pragma unroll
+    for (int b = 0; b < T; ++b) cnt[b] = 0;
+    f2 vsum = pk(0.0f, 0.0f);
+    auto feed = [&](int b, const f2 (&P)[D]) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const f2 pr = term2(X[b][r], P);
+            if (cnt[b] == kChainTerms) vsum = add2(vsum, ch[b][r].value());
+            if (cnt[b] == 0 || cnt[b] == kChainTerms) ch[b][r].start(pr); else ch[b][r].push(pr);
+        }
+        ++cnt[b];
+    };
+    // partners inside the tile
+#pragma unroll
+    for (int b = 0; b < T; ++b)
+#pragma unroll
+        for (int b2 = b + 1; b2 < T; ++b2) feed(b, A[b2]);
+    // late partners: block m+SH+e is a partner of the blocks b >= e
+#pragma unroll
+    for (int e = 1; e < T; ++e) {
+        f2 E[D];
+        load_block(E, block_off(m + (unsigned int)(SH + e)));
+#pragma unroll
+        for (int b = e; b < T; ++b) feed(b, E);
+    }
+    // common partners
+#pragma unroll
+    for (int c = 0; c <= SH - T; ++c) {
+        f2 B[D];
+        load_block(B, block_off(m + (unsigned int)(T + c)));
+#pragma unroll
+        for (int b = 0; b < T; ++b) feed(b, B);
+    }
+#pragma unroll
+    for (int b = 0; b < T; ++b) vsum = add2(vsum, add2(ch[b][0].value(), ch[b][1].value()));
+    float v0, v1;
+    unpk(vsum, v0, v1);
+    return v0 + v1 + inner;
+}
+
 // Shared-memory layout: rows in blocks of two, block m of dimension k of candidate c (= lane) at
 // ((k * NB + m) * C + c) * 8, the even row in the low half.  A block is one LDS.64, conflict-free across the warp.
 template <int N, int D, int C, int GEN>
@@ -126,9 +215,7 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long cta_thr;  // smallest survivor threshold W implied by a candidate of this CTA (bits of a positive double)
     static_assert(N % 2 == 0 && (N / 2) % 2 == 1 && N <= 64, "row blocks: an odd number of them, strata below 2^6");
-    constexpr int NB = N / 2, SH = (NB - 1) / 2;  // row blocks; block shifts 1..SH cover every pair of blocks once
-    constexpr int kChainTerms = 6;  // packed terms a Chain2 holds inside the fp32 range (see the header comment)
-    static_assert(SH > kChainTerms && SH <= 2 * kChainTerms, "every row meets SH terms: two chains of at most six");
+    constexpr int NB = N / 2;  // row blocks of two
     constexpr unsigned BS = C * 8u, DS = NB * BS;
     const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + threadIdx.x * 8u;
 
@@ -200,96 +287,16 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                 }
             }
         gen_done:
-            // ---- scoring.  Block m is paired with blocks m+1 .. m+SH (cyclically): every pair of blocks once.  The
-            // blocks are walked in TILES of two (m, m+1: four rows held as broadcast pairs), so that a partner block
-            // read from shared memory serves eight pairs: blocks m+2 .. m+SH are partners of both, block m+1 is the
-            // first partner of block m (already in registers), block m+SH+1 the last partner of block m+1.  Each row
-            // meets SH = 12 packed terms: two reciprocal chains of six.  The odd block out (NB is odd) goes last.
+            // ---- scoring: row blocks in tiles of kTile, the odd blocks out one by one (screen_tile below)
             double acc = 0.0;
-            auto block_off = [&](unsigned int mm) { const unsigned int o = mm * BS; return min(o, o - DS); };  // block index modulo NB
-            auto load_block = [&](f2 (&b)[D], unsigned int off) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) b[k] = lds2(base + k * DS + off);
-            };
-            auto term2 = [&](const f2 (&a)[D], const f2 (&b)[D]) {
-                f2 q = sub2(a[0], b[0]);
-#pragma unroll
-                for (int k = 1; k < D; ++k) q = mul2(q, sub2(a[k], b[k]));
-                return fma2(q, q, eps2);
-            };
+            constexpr int kTile = SCR_TILE;
+            constexpr int kTiles = NB / kTile;
 #pragma unroll 1
-            for (int t = 0; t < (SCR_EXP == 3 ? 1 : NB / 2); ++t) {
-                const unsigned int m = 2u * (unsigned int)t;
-                f2 A1[D], X[4][D], qin;
+            for (int t = 0; t < (SCR_EXP == 3 ? 1 : kTiles); ++t)
+                acc += (double)screen_tile<NB, D, C, kTile>(base, (unsigned int)(t * kTile), eps2);
+            if (SCR_EXP != 3) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    float a0, a1, c0, c1;
-                    unpk(lds2(base + k * DS + m * BS), a0, a1);
-                    A1[k] = lds2(base + k * DS + (m + 1u) * BS);
-                    unpk(A1[k], c0, c1);
-                    X[0][k] = pk(a0, a0); X[1][k] = pk(a1, a1); X[2][k] = pk(c0, c0); X[3][k] = pk(c1, c1);
-                    const f2 dd = sub2(pk(a0, c0), pk(a1, c1));  // the pair inside each of the two blocks
-                    qin = k == 0 ? dd : mul2(qin, dd);
-                }
-                float pi0, pi1;
-                unpk(fma2(qin, qin, eps2), pi0, pi1);
-                const float inner = rcp_approx(pi0) + rcp_approx(pi1);
-                Chain2 ch[4];
-                f2 E[D];
-                load_block(E, block_off(m + 1u + (unsigned int)SH));
-                ch[0].start(term2(X[0], A1)); ch[1].start(term2(X[1], A1));
-                ch[2].start(term2(X[2], E)); ch[3].start(term2(X[3], E));
-                f2 vsum;
-#pragma unroll
-                for (int sft = 2; sft <= SH; ++sft) {
-                    f2 B[D];
-                    load_block(B, block_off(m + (unsigned int)sft));
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const f2 pr = term2(X[r], B);
-                        if (sft - 1 == kChainTerms) {  // seventh term of the row: the first chain is full
-                            vsum = r == 0 ? ch[r].value() : add2(vsum, ch[r].value());
-                            ch[r].start(pr);
-                        } else {
-                            ch[r].push(pr);
-                        }
-                    }
-                }
-                vsum = add2(add2(vsum, ch[0].value()), add2(add2(ch[1].value(), ch[2].value()), ch[3].value()));
-                float v0, v1;
-                unpk(vsum, v0, v1);
-                acc += (double)(v0 + v1 + inner);
-            }
-            if (SCR_EXP != 3) {  // block NB-1 against blocks 0 .. SH-1, and the pair inside it
-                constexpr unsigned int m = NB - 1;
-                f2 X[2][D];
-                float q_in = 1.0f;
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    float a0, a1;
-                    unpk(lds2(base + k * DS + m * BS), a0, a1);
-                    X[0][k] = pk(a0, a0); X[1][k] = pk(a1, a1);
-                    q_in = k == 0 ? a0 - a1 : q_in * (a0 - a1);
-                }
-                const float inner = rcp_approx(fmaf(q_in, q_in, p.eps_s));
-                Chain2 ch[2];
-                f2 vsum;
-#pragma unroll
-                for (int sft = 1; sft <= SH; ++sft) {
-                    f2 B[D];
-                    load_block(B, (unsigned int)(sft - 1) * BS);
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const f2 pr = term2(X[r], B);
-                        if (sft == 1) ch[r].start(pr);
-                        else if (sft - 1 == kChainTerms) { vsum = r == 0 ? ch[r].value() : add2(vsum, ch[r].value()); ch[r].start(pr); }
-                        else ch[r].push(pr);
-                    }
-                }
-                vsum = add2(vsum, add2(ch[0].value(), ch[1].value()));
-                float v0, v1;
-                unpk(vsum, v0, v1);
-                acc += (double)(v0 + v1 + inner);
+                for (int m = kTiles * kTile; m < NB; ++m) acc += (double)screen_tile<NB, D, C, 1>(base, (unsigned int)m, eps2);
             }
             s = acc;
             if (p.debug_scores) p.debug_scores[off] = s;
