@@ -1,4 +1,4 @@
-// K1+K2 fused, TWO-STAGE search for the headline shapes (MAXPRO_FLAG_FP32_SCREEN, MaxPro only): an fp32 screening
+// K1+K2 fused, TWO-STAGE search for the headline shapes (n = 50, d = 2 or 3; both metrics): an fp32 screening
 // pass with a PROVEN error bound, then the exact fp64 kernel on the survivors.  The result is the result of the
 // exact search -- same winner under the reference's fold (src/lib.rs:85-97, criterion after powf, later index on
 // ties), same score -- at about twice its rate.
@@ -38,6 +38,16 @@
 // The winner and everything that can tie with it have S <= U (1 + tau) for the U of ANY candidate, so keeping every
 // candidate with S' <= W, for the smallest W known when it is scored, loses none of them.  W / S' is about 1.07
 // at n = 50, d = 3: the survivors are the candidates within a few percent of the running best.
+//
+// ---- maximin (same two stages) ----------------------------------------------------------------------------------
+// The criterion is the smallest pairwise distance, larger is better (src/maximin_utils.rs:54-67).  Stage 1 takes the
+// minimum m' over the pairs of s' = sum_k (y_ak - y_bk)^2 in fp32, in units of u = n 2^18 (no scaling: s' < 2^50).
+// Each true difference lies within one unit of the exact integer difference, so for every pair
+//     |s u^2 - s'| <= E(s') = 2 sqrt(d) sqrt(s') + d + arith s'        (Cauchy-Schwarz; arith: the d roundings of the sum)
+// and, E being increasing while s' - E(s') is increasing above a few units, the true minimum m satisfies
+//     lower(m') = m' - E(m') <= m u^2 <= m' + E(m') = upper(m').
+// A candidate survives if upper(m') is not below the largest lower(.) its CTA has seen: the winner and everything that
+// ties with it (sqrt can map neighbouring minima to one criterion) pass, about one candidate in 10^5 at n = 50, d = 3.
 #include "common.cuh"
 #include "philox.cuh"
 #include "reduce.cuh"
@@ -61,6 +71,7 @@ struct ScreenBound {
     double gmin;    // lower bound of f'/f over all q
     double arith;   // relative bound of all fp32 rounding in one score
     double tau;     // criterion tie band
+    double mm_c1, mm_c0, mm_arith;  // maximin: E(s') = mm_c1 sqrt(s') + mm_c0 + mm_arith s'
 };
 
 struct ScreenParams {
@@ -97,6 +108,11 @@ __host__ __device__ inline double screen_threshold(double s, const ScreenBound& 
     return U * (1.0 + r1) * (1.0 + b.arith) / b.g2;
 }
 
+// maximin: bounds of the true squared minimum (units u^2) around the fp32 minimum m
+__host__ __device__ inline double screen_mm_err(double m, const ScreenBound& b) { return b.mm_c1 * sqrt(m) + b.mm_c0 + b.mm_arith * m; }
+__host__ __device__ inline double screen_mm_lower(double m, const ScreenBound& b) { const double l = m - screen_mm_err(m, b); return l > 0.0 ? l : 0.0; }
+__host__ __device__ inline double screen_mm_upper(double m, const ScreenBound& b) { return m + screen_mm_err(m, b); }
+
 namespace {
 
 // ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 do two lanes' worth per issue slot) -----------------------
@@ -107,6 +123,7 @@ __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ f2 lds2(unsigned int addr) { f2 r; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr)); return r; }
 
@@ -208,12 +225,77 @@ __device__ __forceinline__ float screen_tile(unsigned int base, unsigned int m, 
     return v0 + v1 + inner;
 }
 
+// The same tile walk for maximin: the smallest s' = sum_k (y_ak - y_bk)^2 over the tile's pairs (units u^2).
+// Packed differences and sums as above; the running minimum takes both halves of a packed term in one FMNMX3.
+template <int NB, int D, int C, int T>
+__device__ __forceinline__ float screen_tile_min(unsigned int base, unsigned int m) {
+    constexpr int SH = (NB - 1) / 2;
+    constexpr unsigned BS = C * 8u, DS = NB * BS;
+    static_assert(T <= SH, "tile within the shift range");
+    auto block_off = [&](unsigned int mm) { const unsigned int o = mm * BS; return min(o, o - DS); };
+    auto load_block = [&](f2 (&b)[D], unsigned int off) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) b[k] = lds2(base + k * DS + off);
+    };
+    f2 A[T][D], X[T][2][D];
+    float mn[T][2];
+#pragma unroll
+    for (int b = 0; b < T; ++b) {
+        load_block(A[b], (m + (unsigned int)b) * BS);
+        float s_in = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float a0, a1;
+            unpk(A[b][k], a0, a1);
+            X[b][0][k] = pk(a0, a0); X[b][1][k] = pk(a1, a1);
+            s_in = k == 0 ? (a0 - a1) * (a0 - a1) : fmaf(a0 - a1, a0 - a1, s_in);  // the pair inside the block
+        }
+        mn[b][0] = s_in; mn[b][1] = s_in;
+    }
+    auto feed = [&](int b, const f2 (&P)[D]) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const f2 d0 = sub2(X[b][r][0], P[0]);
+            f2 q = mul2(d0, d0);
+#pragma unroll
+            for (int k = 1; k < D; ++k) { const f2 dk = sub2(X[b][r][k], P[k]); q = fma2(dk, dk, q); }
+            float lo, hi;
+            unpk(q, lo, hi);
+            mn[b][r] = min3(mn[b][r], lo, hi);
+        }
+    };
+#pragma unroll
+    for (int b = 0; b < T; ++b)
+#pragma unroll
+        for (int b2 = b + 1; b2 < T; ++b2) feed(b, A[b2]);
+#pragma unroll
+    for (int e = 1; e < T; ++e) {
+        f2 E[D];
+        load_block(E, block_off(m + (unsigned int)(SH + e)));
+#pragma unroll
+        for (int b = e; b < T; ++b) feed(b, E);
+    }
+#pragma unroll
+    for (int c = 0; c <= SH - T; ++c) {
+        f2 B[D];
+        load_block(B, block_off(m + (unsigned int)(T + c)));
+#pragma unroll
+        for (int b = 0; b < T; ++b) feed(b, B);
+    }
+    float r = fminf(mn[0][0], mn[0][1]);
+#pragma unroll
+    for (int b = 1; b < T; ++b) r = min3(r, mn[b][0], mn[b][1]);
+    return r;
+}
+
 // Shared-memory layout: rows in blocks of two, block m of dimension k of candidate c (= lane) at
 // ((k * NB + m) * C + c) * 8, the even row in the low half.  A block is one LDS.64, conflict-free across the warp.
-template <int N, int D, int C, int GEN>
+template <int N, int D, int C, int GEN, bool MAXPRO>
 __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long cta_thr;  // smallest survivor threshold W implied by a candidate of this CTA (bits of a positive double)
+    // MaxPro: smallest survivor threshold W implied by a candidate of this CTA; maximin: largest lower bound of a
+    // candidate's squared minimum (bits of non-negative doubles: the integer order is the numeric order)
+    __shared__ unsigned long long cta_thr;
     static_assert(N % 2 == 0 && (N / 2) % 2 == 1 && N <= 64, "row blocks: an odd number of them, strata below 2^6");
     constexpr int NB = N / 2;  // row blocks of two
     constexpr unsigned BS = C * 8u, DS = NB * BS;
@@ -223,7 +305,7 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
     const unsigned long long total = p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
-    if (threadIdx.x == 0) cta_thr = 0x7FF0000000000000ull;
+    if (threadIdx.x == 0) cta_thr = MAXPRO ? 0x7FF0000000000000ull : 0ull;
     __syncthreads();
     const f2 eps2 = pk(p.eps_s, p.eps_s);
 
@@ -287,37 +369,64 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                 }
             }
         gen_done:
-            // ---- scoring: row blocks in tiles of kTile, the odd blocks out one by one (screen_tile below)
-            double acc = 0.0;
+            // ---- scoring: row blocks in tiles of kTile, the odd blocks out one by one (screen_tile above)
             constexpr int kTile = SCR_TILE;
             constexpr int kTiles = NB / kTile;
+            if (MAXPRO) {
+                double acc = 0.0;
 #pragma unroll 1
-            for (int t = 0; t < (SCR_EXP == 3 ? 1 : kTiles); ++t)
-                acc += (double)screen_tile<NB, D, C, kTile>(base, (unsigned int)(t * kTile), eps2);
-            if (SCR_EXP != 3) {
+                for (int t = 0; t < (SCR_EXP == 3 ? 1 : kTiles); ++t)
+                    acc += (double)screen_tile<NB, D, C, kTile>(base, (unsigned int)(t * kTile), eps2);
+                if (SCR_EXP != 3) {
 #pragma unroll
-                for (int m = kTiles * kTile; m < NB; ++m) acc += (double)screen_tile<NB, D, C, 1>(base, (unsigned int)m, eps2);
+                    for (int m = kTiles * kTile; m < NB; ++m) acc += (double)screen_tile<NB, D, C, 1>(base, (unsigned int)m, eps2);
+                }
+                s = acc;
+            } else {
+                float mn = CUDART_INF_F;
+#pragma unroll 1
+                for (int t = 0; t < kTiles; ++t) mn = fminf(mn, screen_tile_min<NB, D, C, kTile>(base, (unsigned int)(t * kTile)));
+#pragma unroll
+                for (int m = kTiles * kTile; m < NB; ++m) mn = fminf(mn, screen_tile_min<NB, D, C, 1>(base, (unsigned int)m));
+                s = (double)mn;
             }
-            s = acc;
             if (p.debug_scores) p.debug_scores[off] = s;
         }
         // ---- survivors
-        if (rnd == 0) {
-            // the CTA's first round: everybody's threshold first, then the test against the smallest of them
-            if (active) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
-            __syncthreads();
-            const double thr = __longlong_as_double((long long)cta_thr);
-            if (active && s <= thr && (SCR_EXP == 0 || (idx & 0xFFFFF) == 0)) {
-                const unsigned int pos = atomicAdd(p.count, 1u);
-                if (pos < p.cap) p.list[pos] = idx;
+        auto append = [&]() {
+            const unsigned int pos = atomicAdd(p.count, 1u);
+            if (pos < p.cap) p.list[pos] = idx;
+        };
+        const bool listed = SCR_EXP == 0 || (idx & 0xFFFFF) == 0;
+        if (MAXPRO) {
+            if (rnd == 0) {
+                // the CTA's first round: everybody's threshold first, then the test against the smallest of them
+                if (active) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
+                __syncthreads();
+                const double thr = __longlong_as_double((long long)cta_thr);
+                if (active && s <= thr && listed) append();
+            } else {
+                const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
+                if (active && s <= thr && listed) {
+                    append();
+                    const double w = screen_threshold(s, p.bound);
+                    if (w < thr) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(w));
+                }
             }
         } else {
-            const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
-            if (active && s <= thr && (SCR_EXP == 0 || (idx & 0xFFFFF) == 0)) {
-                const unsigned int pos = atomicAdd(p.count, 1u);
-                if (pos < p.cap) p.list[pos] = idx;
-                const double w = screen_threshold(s, p.bound);
-                if (w < thr) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(w));
+            // maximin: survive unless the candidate's upper bound is below the best lower bound seen (see the header)
+            const double up = screen_mm_upper(s, p.bound), low = screen_mm_lower(s, p.bound);
+            if (rnd == 0) {
+                if (active) atomicMax(&cta_thr, (unsigned long long)__double_as_longlong(low));
+                __syncthreads();
+                const double thr = __longlong_as_double((long long)cta_thr);
+                if (active && up >= thr && listed) append();
+            } else {
+                const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
+                if (active && up >= thr && listed) {
+                    append();
+                    if (low > thr) atomicMax(&cta_thr, (unsigned long long)__double_as_longlong(low));
+                }
             }
         }
     }
@@ -333,15 +442,16 @@ cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
         kernel<<<L.grid, C, smem, L.stream>>>(p);
         return cudaGetLastError();
     };
-    return p.gen == 1 ? go(search_screen_kernel<N, D, C, 1>) : go(search_screen_kernel<N, D, C, 2>);
+    if (L.metric == 0) return p.gen == 1 ? go(search_screen_kernel<N, D, C, 1, true>) : go(search_screen_kernel<N, D, C, 2, true>);
+    return p.gen == 1 ? go(search_screen_kernel<N, D, C, 1, false>) : go(search_screen_kernel<N, D, C, 2, false>);
 }
 
 }  // namespace
 
 bool search_screen_supported(unsigned long long n, unsigned long long d, int metric, int* cands) {
     int c = 0;
-    if (metric == 0 && n == 50 && d == 3) c = 384;
-    else if (metric == 0 && n == 50 && d == 2) c = 512;
+    if ((metric == 0 || metric == 1) && n == 50 && d == 3) c = 384;
+    else if ((metric == 0 || metric == 1) && n == 50 && d == 2) c = 512;
     if (cands) *cands = c;
     return c != 0;
 }
@@ -370,6 +480,10 @@ static ScreenBound screen_bound(unsigned long long n, unsigned long long d, floa
     b.gmin = g * 0.98;
     b.arith = ldexp(1.0, -18);
     b.tau = (4.0 * (double)d + 4.0) * ldexp(1.0, -52);
+    // maximin (see the header): units of u = n 2^18, no scaling
+    b.mm_c1 = 2.0 * sqrt((double)d) * (1.0 + ldexp(1.0, -20));
+    b.mm_c0 = (double)d;
+    b.mm_arith = ((double)d + 1.0) * ldexp(1.0, -23);
     return b;
 }
 
@@ -380,6 +494,7 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
     p.gen = stream_version();
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s);
+    if (L.metric != 0) p.col0_scale = 1.0f;  // maximin works in plain units
     p.list = list; p.count = count; p.cap = cap;
     p.debug_scores = debug_scores;
     if (L.n == 50 && L.d == 3) return launch_screen_nd<50, 3, 384>(L, p);

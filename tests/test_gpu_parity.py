@@ -260,7 +260,7 @@ def test_search_generic_path(n, d, switches):
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 def test_search_fp32_screen_two_stage(n, d, metric):
     """MAXPRO_FLAG_FP32_SCREEN through build_lhd: fp32 screening with a proven bound + exact fp64 re-score of the
-    survivors (MaxPro; the flag is ignored for maximin).  Same design, score and index as the exact search."""
+    survivors.  Same design, score and index as the fp64-only search."""
     for iters, seed in ((20_000, 42), (1 << 21, 7)):
         design, s, i = engine.build_lhd(n, d, iters, metric, seed, flags=1)
         _, s_exact, i_exact = engine.build_lhd(n, d, iters, metric, seed, flags=2)
@@ -686,31 +686,34 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
         assert np.all(sums[S <= S[i]] <= w)
 
 
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 @pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
-def test_two_stage_search_returns_the_exact_winner(n, d, switches):
-    """MAXPRO_FLAG_FP32_SCREEN must return what the exact search returns: index, score bits, tie rule."""
-    s_ref, i_ref = oracle.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000)
-    assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=2)
-    assert engine.search_range(n, d, METRIC_MAXPRO, 7, 0, 60_000, flags=1)[1] == i_ref
+def test_two_stage_search_returns_the_exact_winner(n, d, metric, switches):
+    """The two-stage search (fp32 screening with a proven bound + fp64 re-score of the survivors) must return what the
+    fp64-only search returns: index, score bits, tie rule -- for MaxPro and for maximin."""
+    s_ref, i_ref = oracle.search_range(n, d, metric, 7, 0, 60_000)
+    assert engine.search_range(n, d, metric, 7, 0, 60_000, flags=1) == engine.search_range(n, d, metric, 7, 0, 60_000, flags=2)
+    assert engine.search_range(n, d, metric, 7, 0, 60_000, flags=1)[1] == i_ref
+    if metric == METRIC_MAXIMIN:
+        assert engine.search_range(n, d, metric, 7, 0, 60_000, flags=1)[0] == s_ref  # maximin: bit-exact
     for seed in range(8):
         lo = seed * (1 << 33)
-        exact = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24), flags=2)
-        assert exact == engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24))  # MAXPRO_FLAG_DEFAULT
-        fast = engine.search_range(n, d, METRIC_MAXPRO, 1000 + seed, lo, lo + (1 << 24), flags=1)
+        exact = engine.search_range(n, d, metric, 1000 + seed, lo, lo + (1 << 24), flags=2)
+        assert exact == engine.search_range(n, d, metric, 1000 + seed, lo, lo + (1 << 24))  # MAXPRO_FLAG_DEFAULT
+        fast = engine.search_range(n, d, metric, 1000 + seed, lo, lo + (1 << 24), flags=1)
         assert fast == exact, (seed, fast, exact)
     # ragged and tiny ranges, and a survivor list that overflows (stage 2 then scores the whole range)
     for lo, hi in ((5, 6), (5, 5 + 383), (5, 5 + 385), (0, 148 * 384 + 17)):
-        assert engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 3, lo, hi, flags=2)
+        assert engine.search_range(n, d, metric, 3, lo, hi, flags=1) == engine.search_range(n, d, metric, 3, lo, hi, flags=2)
     switches.set("MAXPRO_SCREEN_CAP", "3")
-    assert engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 1001, 0, 1 << 22, flags=2)
+    assert engine.search_range(n, d, metric, 1001, 0, 1 << 22, flags=1) == engine.search_range(n, d, metric, 1001, 0, 1 << 22, flags=2)
     switches.clear("MAXPRO_SCREEN_CAP")
     # the flag is ignored where stage 1 does not apply
-    assert engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000, flags=1) == engine.search_range(40, 3, METRIC_MAXPRO, 7, 0, 5000, flags=2)
-    assert engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000, flags=1) == engine.search_range(n, d, METRIC_MAXIMIN, 7, 0, 5000, flags=2)
+    assert engine.search_range(40, 3, metric, 7, 0, 5000, flags=1) == engine.search_range(40, 3, metric, 7, 0, 5000, flags=2)
     # both design streams
     _lib.set_stream_version(1)
     try:
-        assert engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22, flags=1) == engine.search_range(n, d, METRIC_MAXPRO, 9, 0, 1 << 22, flags=2)
+        assert engine.search_range(n, d, metric, 9, 0, 1 << 22, flags=1) == engine.search_range(n, d, metric, 9, 0, 1 << 22, flags=2)
     finally:
         _lib.set_stream_version(2)
 
