@@ -84,6 +84,76 @@ def test_generate_lhd_is_uniform_permutation():
     assert np.abs(counts - expected).max() < 5 * math.sqrt(expected)
 
 
+@pytest.fixture(params=[1, 2], ids=["LHD-Philox-v1", "LHD-mix-v2"])
+def stream_version(request):
+    prev = oracle.get_stream_version()
+    oracle.set_stream_version(request.param)
+    yield request.param
+    oracle.set_stream_version(prev)
+
+
+def _chi2_ok(counts, dof, sigmas=5.0):
+    expected = counts.sum() / counts.size
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    return chi2 < dof + sigmas * math.sqrt(2.0 * dof), chi2
+
+
+def test_design_stream_statistics(stream_version):
+    """The engine's own design streams (the reference pins none): 40,000 consecutive candidate streams
+    seed + i, as build_lhd draws them, must look like independent uniform Latin hypercubes."""
+    n, d, N = 50, 3, 40_000
+    x = oracle.generate_batch(n, d, 20240, 0, N)                  # [N, n, d]
+    strata = np.floor(x * n).astype(np.int64)
+    assert (np.sort(strata, axis=1) == np.arange(n)[None, :, None]).all()      # every column a permutation (lhd.rs:134-155)
+    for k in range(d):
+        # (row, stratum) table: every stratum equally likely at every row position
+        table = np.zeros((n, n))
+        np.add.at(table, (np.repeat(np.arange(n), N), strata[:, :, k].T.ravel()), 1.0)
+        ok, chi2 = _chi2_ok(table, (n - 1) * (n - 1))
+        assert ok, (k, chi2)
+        # orderings of adjacent rows: P(stratum[i] < stratum[i+1]) = 1/2 for every i
+        less = (strata[:, :-1, k] < strata[:, 1:, k]).sum(axis=0)
+        z = (less - N / 2) / math.sqrt(N / 4)
+        assert np.abs(z).max() < 5.0 and float((z ** 2).sum()) < (n - 1) + 5 * math.sqrt(2.0 * (n - 1)), (k, z)
+        # the differences of adjacent rows are those of a uniform permutation: P(|a - b| = t) = 2 (n - t) / (n (n - 1))
+        diff = np.abs(strata[:, :-1, k] - strata[:, 1:, k]).ravel()
+        obs = np.bincount(diff, minlength=n)[1:]
+        exp = diff.size * 2.0 * (n - np.arange(1, n)) / (n * (n - 1))
+        chi2 = float(((obs - exp) ** 2 / exp).sum())
+        assert chi2 < (n - 2) + 5 * math.sqrt(2.0 * (n - 2)), (k, chi2)
+    # neighbouring candidate streams (seed + i, seed + i + 1) and neighbouring columns are independent
+    for a, b in ((strata[:-1, 0, 0], strata[1:, 0, 0]), (strata[:, 0, 0], strata[:, 0, 1]), (strata[:, 7, 1], strata[:, 7, 2])):
+        table = np.zeros((n, n))
+        np.add.at(table, (a, b), 1.0)
+        ok, chi2 = _chi2_ok(table, (n - 1) * (n - 1))
+        assert ok, chi2
+    # jitter: uniform inside its stratum (Kolmogorov-Smirnov on 10^6 values) and independent of the stratum
+    u = (x * n - strata).ravel()[:1_000_000]
+    assert 0.0 < u.min() and u.max() < 1.0
+    us = np.sort(u)
+    ks = max(np.max(np.arange(1, us.size + 1) / us.size - us), np.max(us - np.arange(us.size) / us.size))
+    assert ks * math.sqrt(us.size) < 1.95, ks                                   # p ~ 1e-3
+    corr = np.corrcoef(u, strata.ravel()[:1_000_000].astype(np.float64))[0, 1]
+    assert abs(corr) < 5.0 / math.sqrt(u.size), corr
+    # consecutive jitters of one column are not correlated either (a Weyl sequence feeds the v2 mixer)
+    uu = (x[:, :, 0] * n - strata[:, :, 0])
+    c1 = np.corrcoef(uu[:, :-1].ravel(), uu[:, 1:].ravel())[0, 1]
+    assert abs(c1) < 5.0 / math.sqrt(uu[:, 1:].size), c1
+
+
+def test_design_stream_small_permutations_are_equally_likely(stream_version):
+    """n = 4: all 24 permutations of a column equally likely over 48,000 streams (chi-square, 23 degrees of freedom)."""
+    n, N = 4, 48_000
+    x = oracle.generate_batch(n, 2, 99, 0, N)
+    strata = np.floor(x * n).astype(np.int64)
+    for k in range(2):
+        code = (strata[:, :, k] * (n ** np.arange(n))[None, :]).sum(axis=1)
+        _, counts = np.unique(code, return_counts=True)
+        assert counts.size == 24
+        ok, chi2 = _chi2_ok(counts.astype(np.float64), 23)
+        assert ok, chi2
+
+
 def test_criteria_well_conditioned():  # maxpro_utils.rs:101-115, maximin_utils.rs:69-83 (fewer rounds)
     for s in range(50):
         x = oracle.generate_lhd(100, 5, 12345 + s)
