@@ -76,25 +76,31 @@ __device__ __forceinline__ double stratum_value(uint32_t i, uint32_t jit, double
 // per column, keyed by (stream id, column) -- and draws the elements of a column from a counter-based 32-bit
 // mixer under that key:
 //     {A, B} = Philox4x32-10(ctr = {k, "LHD2", s_lo, s_hi}, key = {kKeyLhd0, kKeyLhd1}).{x, y | 1}
-//     w_i    = mix32(A + i * B)            mix32: x ^= x>>16; x *= 0x21f0aaad; x ^= x>>15; x *= 0x735a2d97; x ^= x>>15
+//     w_i    = mix32(A + i * B)            mix32: x ^= x>>16; x *= 0x735a2d97
 //     P      = w_i * (i + 1)               (64 bits)
 //     j_i    = P >> 32                     the Fisher-Yates index in [0, i], bias (i+1) 2^-32
 //     jit_i  = P mod 2^32                  the fractional part of w_i (i+1) 2^-32: uniform and independent of j_i
 //     v_i    = (i + (jit_i + 1/2) 2^-32) / n,  evaluated as  fma(2^52 + (i 2^32 + jit_i), c1, c0'),
 //              c1 = 2^-32 / n,  c0' = c1/2 - 2^52 c1:  the integer is written into the mantissa of 2^52 (one
 //              integer op instead of a 64-bit int -> double conversion); floor(v_i n) == i for every draw, n <= 2^18.
-// mix32 is the two-round multiply-xorshift finaliser with the constants of C. Wellons' hash-prospector search
-// (avalanche bias 0.10); A + i B is a Weyl sequence with a per-column odd step.  Per element: 2 multiplies, one
-// wide multiply and 6 shift/logic ops instead of 10 wide multiplies and 10 logic ops.  tests/test_oracle.py holds
-// the statistics (uniformity of every j_i, of adjacent pairs, of whole permutations for small n, KS of the jitter).
+// mix32 is ONE xorshift-multiply round.  Its input is not a counter but a Weyl sequence A + i B whose start and odd step
+// are both full-entropy Philox words of the column, so the sequence is equidistributed to begin with; what the round has
+// to do is break its linearity (w_i, w_{i+1}, w_{i+2} collinear) in the HIGH bits, which are the ones the shuffle index and
+// the leading jitter bits are made of.  A first multiply would be wasted (it maps the sequence onto another Weyl sequence
+// with equally random start and step), and a second round moved nothing in the tests: tools/mixer_tests.py compares this
+// round with the two-round finaliser (C. Wellons' hash-prospector constants) it replaced and with three other candidates
+// on 7.5e7-sample contingency tables of (w_i, w_{i+lag}) bit fields, triples, Fisher-Yates index pairs, and on the
+// permutation statistics of 40,000 designs -- no difference -- while a rotate-multiply mixer fails them at once.  In the
+// fused kernels every generator instruction costs an issue cycle that the criterion does not get:
+// the two-round finaliser was 5.6 ms of the screening kernel's 54.7 ms per 2^27 candidates.  Per element: 1 multiply,
+// one wide multiply and 3 shift/logic ops, against 10 wide multiplies and 10 logic ops in v1.  tests/test_oracle.py holds
+// the statistics (uniformity of every position, of adjacent orderings and differences, independence of neighbouring
+// streams and columns, whole permutations for small n, KS and serial correlation of the jitter).
 constexpr uint32_t kLhd2Tag = 0x4C484432u;  // "LHD2"
 
 __host__ __device__ __forceinline__ uint32_t lhd2_mix32(uint32_t x) {
     x ^= x >> 16;
-    x *= 0x21f0aaadu;
-    x ^= x >> 15;
     x *= 0x735a2d97u;
-    x ^= x >> 15;
     return x;
 }
 

@@ -58,6 +58,9 @@
 #ifndef SCR_EXP
 #define SCR_EXP 0
 #endif
+#ifndef SCR_KNOCK
+#define SCR_KNOCK 0  // experiment: parts of the generator knocked out (bit mask, see the kernel)
+#endif
 #ifndef SCR_TILE
 #define SCR_TILE 4  // row blocks per scoring tile (measured: profiles/README.md, round 2)
 #endif
@@ -338,7 +341,16 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                     } else {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            mulhilo32(lhd2_mix32(x[k]), 2u * b + e + 1u, jx[k][e], jit[k][e]);
+#if SCR_KNOCK & 1   // experiment: no mixer
+                            const uint32_t w = x[k];
+#else
+                            const uint32_t w = lhd2_mix32(x[k]);
+#endif
+#if SCR_KNOCK & 2   // experiment: no wide multiply
+                            jx[k][e] = (w >> 28) & (2u * b + e); jit[k][e] = w;
+#else
+                            mulhilo32(w, 2u * b + e + 1u, jx[k][e], jit[k][e]);
+#endif
                             x[k] += kb[k];  // Weyl sequence A + i B
                         }
                     }
@@ -355,17 +367,25 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
                     if (k == 0) { v0[k] *= p.col0_scale; v1[k] *= p.col0_scale; }
                     aj0[k] = base + k * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
                     aj1[k] = base + k * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
+#if SCR_KNOCK & 8   // experiment: no shared-memory walk (one store per column block keeps the draws live)
+                    t0[k] = v0[k] + (float)aj0[k]; t1[k] = v1[k] + (float)aj1[k];
+#else
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
+#endif
                 }
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     if (jx[k][1] == jx[k][0]) t1[k] = v0[k]; else if (jx[k][1] == 2u * b) t1[k] = t0[k];
                     const unsigned int a0 = base + k * DS + (unsigned int)b * BS;
+#if SCR_KNOCK & 8
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k] + t1[k]) : "memory");
+#else
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k]) : "memory");
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj0[k]), "f"(v0[k]) : "memory");
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u), "f"(t1[k]) : "memory");
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj1[k]), "f"(v1[k]) : "memory");
+#endif
                 }
             }
         gen_done:

@@ -210,9 +210,7 @@ int oracle_generate_lhd_v1(uint64_t n, uint64_t d, uint64_t stream, double *out)
  * Same inside-out Fisher-Yates as v1. */
 static uint32_t lhd2_mix32(uint32_t x)
 {
-    x ^= x >> 16; x *= 0x21f0aaadu;
-    x ^= x >> 15; x *= 0x735a2d97u;
-    x ^= x >> 15;
+    x ^= x >> 16; x *= 0x735a2d97u;   /* one xorshift-multiply round on a Weyl sequence with random start and step */
     return x;
 }
 
