@@ -24,6 +24,19 @@
 #include <cstdlib>
 #include <cstdio>
 
+// Compile-time experiment switches (off in the product; profiles/README.md, round 2, has the measurements):
+//   CYC_EXP   1 no generation after the first round, 3 generation only, 7 / 8 two scoring warps per sub-partition with
+//             the third idle / generating three designs per round;  CYC_KNOCK  bit mask of generator parts knocked out;
+//   CYC_PROF  clock64 sums of the generation and scoring phases per warp, printed by CTA 0.
+// The variants that tried to OVERLAP the two phases (generation steps issued inside the scoring loop, a generation mutex per
+// sub-partition, a staggered start) were measured and removed again: commit 408d3ad has them.
+#ifndef CYC_EXP
+#define CYC_EXP 0
+#endif
+#ifndef CYC_KNOCK
+#define CYC_KNOCK 0
+#endif
+
 namespace mp {
 
 struct CyclicParams {
@@ -166,9 +179,6 @@ struct CycBlockDraw { uint32_t j0, j1; double v0, v1; };
 __device__ __forceinline__ CycBlockDraw cyc_draw_block_v2(uint32_t& x, uint32_t kb, uint32_t b, double c1, double c0, bool advance) {
     CycBlockDraw r;
     uint32_t jit0, jit1;
-#ifndef CYC_KNOCK
-#define CYC_KNOCK 0
-#endif
 #if CYC_KNOCK & 1   // no mixer
     const uint32_t w0 = x, w1 = x + kb;
 #else
@@ -244,72 +254,13 @@ __device__ __forceinline__ void cyc_generate_v2(unsigned int cand, uint32_t s_lo
     }
 }
 
-// EXPERIMENT (CYC_EXP): the same block steps as cyc_generate_v2, one at a time, so that the scoring loop can
-// issue them between its FP64 instructions.
-#ifndef CYC_EXP
-#define CYC_EXP 0
-#endif
-#ifndef CYC_STAGGER
-#define CYC_STAGGER 12000
-#endif
-struct CycNoHook { __device__ __forceinline__ void slot() {} __device__ __forceinline__ void handover() {} };
-
-template <int N, int D, int C>
-struct CycGenPipe {
-    static constexpr int NB = N / 2, H = (NB + 1) / 2;
-    static constexpr unsigned RB = Layout<N, D, C>::kRowBytes, DB = Layout<N, D, C>::kDimBytes;
-    uint32_t xp, pb, xs, sb;
-    unsigned int colp, cols, group_mask;
-    double c1, c0;
-    int g, next, limit;
-    __device__ __forceinline__ void init(unsigned int cand, uint32_t s_lo, uint32_t s_hi, double c1_, double c0_, int g_, unsigned int gm) {
-        c1 = c1_; c0 = c0_; g = g_; group_mask = gm; next = 0; limit = H;
-        xs = 0u; sb = 0u;
-        lhd2_column_key((uint32_t)g, s_lo, s_hi, xp, pb);
-        if (D == 3) {
-            lhd2_column_key(2u, s_lo, s_hi, xs, sb);
-            if (g) xs += (uint32_t)(2 * H) * sb;
-        }
-        colp = cand + (unsigned int)g * DB; cols = cand + 2u * DB;
-    }
-    __device__ __forceinline__ void step(int t) {
-        const bool sec = D == 3 && ((t < H) == (g == 0));
-        const CycBlockDraw P = cyc_draw_block_v2(xp, pb, (uint32_t)t, c1, c0, true);
-        CycBlockDraw S{};
-        if (D == 3) S = cyc_draw_block_v2(xs, sb, (uint32_t)t, c1, c0, sec);
-        const unsigned int a0 = (unsigned int)(2 * t) * RB;
-        double p0 = cyc_lds(colp + P.j0 * RB, true, 0.0), p1 = cyc_lds(colp + P.j1 * RB, true, 0.0);
-        double q0 = 0.0, q1 = 0.0;
-        if (D == 3) { q0 = cyc_lds(cols + S.j0 * RB, sec, 0.0); q1 = cyc_lds(cols + S.j1 * RB, sec, 0.0); }
-        if (P.j1 == P.j0) p1 = P.v0; else if (P.j1 == 2u * t) p1 = p0;
-        if (D == 3) { if (S.j1 == S.j0) q1 = S.v0; else if (S.j1 == 2u * t) q1 = q0; }
-        cyc_sts(colp + a0, p0, true);
-        cyc_sts(colp + P.j0 * RB, P.v0, true);
-        cyc_sts(colp + a0 + RB, p1, true);
-        cyc_sts(colp + P.j1 * RB, P.v1, true);
-        if (D == 3) {
-            cyc_sts(cols + a0, q0, sec);
-            cyc_sts(cols + S.j0 * RB, S.v0, sec);
-            cyc_sts(cols + a0 + RB, q1, sec);
-            cyc_sts(cols + S.j1 * RB, S.v1, sec);
-        }
-    }
-    __device__ __forceinline__ void slot() { if (next < limit) { step(next); ++next; } }
-    __device__ __forceinline__ void handover() {
-        while (next < H) { step(next); ++next; }
-        if (D == 3) __syncwarp(group_mask);
-        limit = NB;
-    }
-    __device__ __forceinline__ void finish() { while (next < NB) { step(next); ++next; } }
-};
-
 // One tile of the cyclic schedule: R rows against the lane's KP shifts.  The R + KP - 1 partner rows
 // are read once for all shifts (16 row loads per 60 pairs at R = 5, KP = 12).  Tiles whose partner
 // rows stay below N for both lanes (WRAP = false) address them as base + immediate; only the
 // upper tiles pay one add and one unsigned min per row for the wrap-around.
-template <int N, int D, int C, bool MAXPRO, bool SAFE, bool WRAP, int R, int KP, class Hook>
+template <int N, int D, int C, bool MAXPRO, bool SAFE, bool WRAP, int R, int KP>
 __device__ __forceinline__ void cyc_tile_window(const unsigned char* cand, unsigned i0_off, unsigned first_off,
-                                                const double (&xi)[R][D], RecipChain (&ch)[R], double (&mins)[R], double& acc, Hook& hook) {
+                                                const double (&xi)[R][D], RecipChain (&ch)[R], double (&mins)[R], double& acc) {
     constexpr unsigned RB = Layout<N, D, C>::kRowBytes;
     constexpr unsigned NB = N * RB;
     constexpr int W = R + KP - 1;
@@ -322,7 +273,6 @@ __device__ __forceinline__ void cyc_tile_window(const unsigned char* cand, unsig
     }
 #pragma unroll
     for (int c = 0; c < KP; ++c) {
-        if (c % 4 == 0) hook.slot();
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (MAXPRO) { if (SAFE) acc += 1.0 / cyc_maxpro_term<D>(xi[r], xj[r + c]); else ch[r].push(cyc_maxpro_term<D>(xi[r], xj[r + c])); }
@@ -339,8 +289,8 @@ __device__ __forceinline__ void cyc_tile_window(const unsigned char* cand, unsig
 // flush serves three tiles (36-39 terms) instead of one: 20 flushes per lane and candidate
 // instead of 50.  The n/2 diameters are split between the two lanes by ADDRESS (lane 0 rows
 // 0..12, lane 1 rows 13..24), not by predicate: 13 pair slots per lane instead of 25.
-template <int N, int D, int C, bool MAXPRO, bool SAFE = false, class Hook = CycNoHook>
-__device__ __forceinline__ double cyc_score(const unsigned char* cand, int g, Hook&& hook = Hook()) {
+template <int N, int D, int C, bool MAXPRO, bool SAFE = false>
+__device__ __forceinline__ double cyc_score(const unsigned char* cand, int g) {
     constexpr int R = 5, G = 2;
     constexpr int kHalf = (N - 1) / 2;
     constexpr int kPerLane = kHalf / G;
@@ -371,13 +321,12 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g, Ho
         double xi[R][D];
 #pragma unroll
         for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xi[r], cand, i0_off + r * RB);
-        cyc_tile_window<N, D, C, MAXPRO, SAFE, false, R, kPerLane>(cand, i0_off, first_off, xi, ch, mins, acc, hook);
+        cyc_tile_window<N, D, C, MAXPRO, SAFE, false, R, kPerLane>(cand, i0_off, first_off, xi, ch, mins, acc);
         if (t % kFlushEvery == kFlushEvery - 1) flush_all();
     }
     // diameters {i, i + N/2} (even N), i < N/2: lane 0 takes i = 0 .. kDiam-1, lane 1 the rest.  The
     // rows are addressed per lane, so both lanes run the same instructions (no divergence); when
     // N/2 is odd lane 1's last slot is a repeat of row 0 that is not pushed.
-    hook.handover();
     if (N % 2 == 0) {
         constexpr int H = N / 2;
 #pragma unroll
@@ -403,7 +352,7 @@ __device__ __forceinline__ double cyc_score(const unsigned char* cand, int g, Ho
         double xi[R][D];
 #pragma unroll
         for (int r = 0; r < R; ++r) load_row_at<N, D, C>(xi[r], cand, i0_off + r * RB);
-        cyc_tile_window<N, D, C, MAXPRO, SAFE, true, R, kPerLane>(cand, i0_off, first_off, xi, ch, mins, acc, hook);
+        cyc_tile_window<N, D, C, MAXPRO, SAFE, true, R, kPerLane>(cand, i0_off, first_off, xi, ch, mins, acc);
         if ((t - kNoWrap) % kFlushEvery == kFlushEvery - 1) flush_all();
     }
     if ((kTiles - kNoWrap) % kFlushEvery != 0) flush_all();
@@ -494,27 +443,12 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
     const int tok_in = 1 + smsp * ring + q, tok_out = 1 + smsp * ring + (q + 1 == ring ? 0 : q + 1);
     if (in_ring && q == ring - 1) cyc_token_pass(tok_out);  // position 0 scores first
 
-#if CYC_EXP == 4 || CYC_EXP == 6
-    {   // experiment: staggered start of the warps of a sub-partition
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)q * CYC_STAGGER) {}
-    }
-#endif
-#if CYC_EXP == 5 || CYC_EXP == 6
-    __shared__ unsigned int gen_lock[4];
-    if (threadIdx.x < 4) gen_lock[threadIdx.x] = 0u;
-    __syncthreads();
-#endif
     for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
         const unsigned long long off = gcid + rnd * gstep;
         bool active = off < total;
         unsigned long long idx = p.lo + off;
 #ifdef CYC_PROF
         const long long pt0 = clock64();
-#endif
-#if CYC_EXP == 5 || CYC_EXP == 6
-        if (lane == 0) { while (atomicCAS(&gen_lock[smsp], 0u, 1u) != 0u) __nanosleep(64); }
-        __syncwarp();
 #endif
 #ifdef CYC_PROF
         const long long pt1 = clock64();
@@ -534,7 +468,7 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
 #pragma unroll 1
             for (int rep = 0; rep < 3; ++rep)
                 cyc_generate_v2<N, D, C>((unsigned int)__cvta_generic_to_shared(cand), s_lo + rep, s_hi, p.c1, p.c0, g, group_mask);
-        } else if (active && (CYC_EXP == 1 || CYC_EXP == 2) && rnd > 0) {
+        } else if (active && CYC_EXP == 1 && rnd > 0) {
             // experiment: no stand-alone generation after the first round
         } else if (active) {
             if (GEN == 2 && N % 2 == 0 && !MAXPRO) {
@@ -549,10 +483,6 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
             }
         }
         __syncwarp(group_mask);
-#if CYC_EXP == 5 || CYC_EXP == 6
-        __syncwarp();
-        if (lane == 0) atomicExch(&gen_lock[smsp], 0u);
-#endif
 #ifdef CYC_PROF
         __syncwarp();
         const long long pt2 = clock64();
@@ -564,12 +494,7 @@ __global__ void __launch_bounds__(2 * C, 1) search_cyclic_kernel(CyclicParams p)
             if (active && in_cube) s = cyc_score<N, D, C, MAXPRO, false>(cand, g);
             else if (active) s = cyc_score<N, D, C, MAXPRO, true>(cand, g);
         } else if (active) {
-#if CYC_EXP == 2
-            CycGenPipe<N, D, C> gp;
-            gp.init((unsigned int)__cvta_generic_to_shared(cand), s_lo, s_hi, p.c1, p.c0, g, group_mask);
-            s = cyc_score<N, D, C, MAXPRO, false, CycGenPipe<N, D, C>&>(cand, g, gp);
-            gp.finish();
-#elif CYC_EXP == 3
+#if CYC_EXP == 3
             s = *reinterpret_cast<const double*>(cand + (s_lo % 150u) * Layout<N, D, C>::kRowBytes);
 #elif CYC_EXP == 7 || CYC_EXP == 8
             if (q < 2) s = cyc_score<N, D, C, MAXPRO>(cand, g);
