@@ -317,6 +317,7 @@ def run_configs(which, rank, world, dev, peak_tflops, peak32_tflops, max_over_ra
                                               "incremental step: the 2(n-2) pairs of the two swapped rows, old and new")}
         if rank == 0:
             rec["value"] = rec["maximin"]["value"]
+            rec["roofline"] = rec["maximin"]["roofline"]
             rec["note"] = ("headline of this config = maximin (trajectory bit-exact against the oracle in the tests). "
                            "MaxPro at d=20 is numerically degenerate in the reference itself: every product of 20 squared "
                            "differences is far below eps=1e-12, so psi = 3.981 for every design and accept/reject is rounding "

@@ -318,11 +318,22 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                     raw_new = fmin(fmin(fin_all, fmin(g1, d12)), fmin(g2, d12));
                 }
                 if (lane == 0) dirty_n[0] = 0;  // for the next iteration's list
-                const double new_metric = sqrt(raw_new);
-                double diff = new_metric - cur_metric;
-                if (!p.minimize) diff *= -1.0;
-                const double p_acc = diff < 0.0 ? 1.0 : exp(-diff / temp);
-                const bool accept = u < p_acc;
+                // Most moves leave the smallest distance where it was: raw_new == raw_cur bit for bit.  Then
+                // new_metric == cur_metric, diff = +-0 and p = exp(-+0 / temp) is 1 for every temp > 0 (u < 1: accept)
+                // and NaN for temp == 0 (0/0: reject) -- the same decision without the sqrt, the divide and the exp,
+                // which are ~1,300 cycles of dependent latency on this one warp while fifteen others wait.
+                double new_metric;
+                bool accept;
+                if (raw_new == raw_cur) {
+                    new_metric = cur_metric;
+                    accept = temp != 0.0;
+                } else {
+                    new_metric = sqrt(raw_new);
+                    double diff = new_metric - cur_metric;
+                    if (!p.minimize) diff *= -1.0;
+                    const double p_acc = diff < 0.0 ? 1.0 : exp(-diff / temp);
+                    accept = u < p_acc;
+                }
                 if (accept && moved && lane == 0) {
                     double v1 = cur[c * ns + r1], v2 = cur[c * ns + r2];
                     cur[c * ns + r1] = v2; cur[c * ns + r2] = v1;  // anneal.rs:34-39
