@@ -254,7 +254,8 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     mp::count_launch();
     int cyc_cands = 0, scr_cands = 0;
     const bool want_screen = !(flags & MAXPRO_FLAG_FP64_ONLY) && ((flags & MAXPRO_FLAG_FP32_SCREEN) || hi - lo >= kScreenMinRange);
-    if (want_screen && mp::search_screen_supported(n, d, metric, &scr_cands) && mp::search_cyclic_supported(n, d, &cyc_cands)) {
+    const bool exact_cyclic = mp::search_cyclic_supported(n, d, &cyc_cands);
+    if (want_screen && mp::search_screen_supported(n, d, metric, &scr_cands) && (exact_cyclic || mp::search_small_supported(n, d))) {
         // stage 1: fp32 screening with a proven bound; every candidate that can still win goes to the survivor list
         mp::SearchLaunch L{};
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
@@ -267,16 +268,18 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
         if (const char* v = mp::cfg("MAXPRO_SCREEN_CAP")) { const long c = atol(v); if (c >= 1 && c < (long)kSurvivorCap) cap = (unsigned int)c; }  // tests: force the overflow path
         CUDA_TRY(mp::launch_search_screen(L, w.survivors, w.counter + 1, cap));
         mp::count_launch();
-        // stage 2: the exact fp64 kernel over the survivors (over lo..hi if the list overflowed), usual fold
+        // stage 2: the exact fp64 kernel of the shape over the survivors (over lo..hi if the list overflowed), usual fold
         mp::SearchLaunch E{};
         E.n = n; E.d = d; E.metric = metric; E.seed = seed; E.lo = lo; E.hi = hi; E.flags = flags;
         E.block_best = w.block_best; E.done_counter = w.counter; E.result = result;
-        E.group = 2; E.threads = 2 * cyc_cands;
         E.list = w.survivors; E.list_count = 0; E.list_count_dev = w.counter + 1; E.list_cap = cap;
-        unsigned long long want2 = (total + cyc_cands - 1) / cyc_cands;
-        E.grid = (int)(want2 < (unsigned long long)sms ? want2 : (unsigned long long)sms);
         E.stream = stream;
-        CUDA_TRY(mp::launch_search_cyclic(E));
+        unsigned long long per_cta;
+        if (exact_cyclic) { E.group = 2; E.threads = 2 * cyc_cands; per_cta = (unsigned long long)cyc_cands; }
+        else { mp::search_small_pick_config(n, d, &E.group, &E.threads); per_cta = (unsigned long long)(E.threads / E.group); }
+        unsigned long long want2 = (total + per_cta - 1) / per_cta;
+        E.grid = (int)(want2 < (unsigned long long)sms ? want2 : (unsigned long long)sms);
+        CUDA_TRY(exact_cyclic ? mp::launch_search_cyclic(E) : mp::launch_search_small(E));
         mp::count_launch();
         return MAXPRO_OK;
     }

@@ -79,6 +79,8 @@ struct ScreenBound {
 
 struct ScreenParams {
     int gen;                         // design stream version (philox.cuh)
+    int n;                           // points per design (the general kernel; the specialised one has it as a template parameter)
+    int jbits;                       // jitter bits kept by stage 1: y = i 2^jbits + (jit >> (32 - jbits)) < 2^24 (18 up to n = 64)
     unsigned long long seed, lo, hi;
     float col0_scale;                // exact power of two carried by column 0
     float eps_s;                     // eps in scaled units
@@ -291,6 +293,122 @@ __device__ __forceinline__ float screen_tile_min(unsigned int base, unsigned int
     return r;
 }
 
+// Generation of one candidate by one lane: the design stream's draws and shuffle (philox.cuh), values as exact
+// integer-valued floats (see the header).  NB, BS and DS are compile-time constants in the specialised kernel and run-time
+// values in the general one.  The D columns are independent Fisher-Yates chains (each step reads what an earlier step of the
+// SAME column wrote), so they are walked side by side: D loads in flight per step instead of one.
+template <int D, int GEN>
+__device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsigned int BS, unsigned int DS, uint32_t s_lo, uint32_t s_hi,
+                                                float col0_scale, int jbits) {
+    uint32_t kb[D], x[D];
+    if (GEN == 2) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)k, s_lo, s_hi, x[k], kb[k]);
+    }
+#pragma unroll 2
+    for (int b = 0; b < NB; ++b) {
+        uint32_t jx[D][2], jit[D][2];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (GEN == 1) {
+                const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+                jit[k][0] = w.x; jx[k][0] = __umulhi(w.y, 2u * b + 1u);
+                jit[k][1] = w.z; jx[k][1] = __umulhi(w.w, 2u * b + 2u);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+#if SCR_KNOCK & 1   // experiment: no mixer
+                    const uint32_t w = x[k];
+#else
+                    const uint32_t w = lhd2_mix32(x[k]);
+#endif
+#if SCR_KNOCK & 2   // experiment: no wide multiply
+                    jx[k][e] = (w >> 28) & (2u * b + e); jit[k][e] = w;
+#else
+                    mulhilo32(w, 2u * b + e + 1u, jx[k][e], jit[k][e]);
+#endif
+                    x[k] += kb[k];  // Weyl sequence A + i B
+                }
+            }
+        }
+        // both elements of the block in all D columns: loads first, then the stores in shuffle order.  What
+        // element 2b+1 would have read after the stores of element 2b is patched in from registers (it can
+        // only alias a[2b] or a[j0]).
+        float t0[D], t1[D], v0[D], v1[D];
+        unsigned int aj0[D], aj1[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            v0[k] = (float)(((2u * b) << jbits) | (jit[k][0] >> (32 - jbits)));
+            v1[k] = (float)(((2u * b + 1u) << jbits) | (jit[k][1] >> (32 - jbits)));
+            if (k == 0) { v0[k] *= col0_scale; v1[k] *= col0_scale; }
+            aj0[k] = base + k * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
+            aj1[k] = base + k * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
+#if SCR_KNOCK & 8   // experiment: no shared-memory walk (one store per column block keeps the draws live)
+            t0[k] = v0[k] + (float)aj0[k]; t1[k] = v1[k] + (float)aj1[k];
+#else
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
+#endif
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (jx[k][1] == jx[k][0]) t1[k] = v0[k]; else if (jx[k][1] == 2u * b) t1[k] = t0[k];
+            const unsigned int a0 = base + k * DS + (unsigned int)b * BS;
+#if SCR_KNOCK & 8
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k] + t1[k]) : "memory");
+#else
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj0[k]), "f"(v0[k]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u), "f"(t1[k]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj1[k]), "f"(v1[k]) : "memory");
+#endif
+        }
+    }
+}
+
+// Survivor test of one candidate against its CTA's running bound (see the header), and the update of that bound.
+// cta_thr holds bits of a non-negative double: MaxPro -- the smallest threshold W a candidate of this CTA implies;
+// maximin -- the largest lower bound of a candidate's squared minimum.  Called by every thread of the CTA (rnd == 0 has
+// a barrier: everybody's bound first, then the test against the best of them).
+template <bool MAXPRO>
+__device__ __forceinline__ void screen_survivors(const ScreenParams& p, unsigned long long* cta_thr, bool first_round, bool active,
+                                                 double s, unsigned long long idx) {
+    auto append = [&]() {
+        const unsigned int pos = atomicAdd(p.count, 1u);
+        if (pos < p.cap) p.list[pos] = idx;
+    };
+    const bool listed = SCR_EXP == 0 || (idx & 0xFFFFF) == 0;
+    if (MAXPRO) {
+        if (first_round) {
+            if (active) atomicMin(cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
+            __syncthreads();
+            const double thr = __longlong_as_double((long long)*cta_thr);
+            if (active && s <= thr && listed) append();
+        } else {
+            const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)cta_thr);
+            if (active && s <= thr && listed) {
+                append();
+                const double w = screen_threshold(s, p.bound);
+                if (w < thr) atomicMin(cta_thr, (unsigned long long)__double_as_longlong(w));
+            }
+        }
+    } else {
+        const double up = screen_mm_upper(s, p.bound), low = screen_mm_lower(s, p.bound);
+        if (first_round) {
+            if (active) atomicMax(cta_thr, (unsigned long long)__double_as_longlong(low));
+            __syncthreads();
+            const double thr = __longlong_as_double((long long)*cta_thr);
+            if (active && up >= thr && listed) append();
+        } else {
+            const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)cta_thr);
+            if (active && up >= thr && listed) {
+                append();
+                if (low > thr) atomicMax(cta_thr, (unsigned long long)__double_as_longlong(low));
+            }
+        }
+    }
+}
+
 // Shared-memory layout: rows in blocks of two, block m of dimension k of candidate c (= lane) at
 // ((k * NB + m) * C + c) * 8, the even row in the low half.  A block is one LDS.64, conflict-free across the warp.
 template <int N, int D, int C, int GEN, bool MAXPRO>
@@ -320,75 +438,8 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
         if (active) {
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
             const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
-            // ---- generation: the design stream's draws and shuffle (philox.cuh); values as exact integers (see header)
-            // The D columns are independent Fisher-Yates chains (each step reads what an earlier step of the SAME
-            // column wrote), so they are walked side by side: D loads in flight per step instead of one.
-            uint32_t kb[D], x[D];
-            if (SCR_EXP == 1 && rnd > 0) goto gen_done;  // experiment: scoring only
-            if (GEN == 2) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)k, s_lo, s_hi, x[k], kb[k]);
-            }
-#pragma unroll 2
-            for (int b = 0; b < NB; ++b) {
-                uint32_t jx[D][2], jit[D][2];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    if (GEN == 1) {
-                        const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
-                        jit[k][0] = w.x; jx[k][0] = __umulhi(w.y, 2u * b + 1u);
-                        jit[k][1] = w.z; jx[k][1] = __umulhi(w.w, 2u * b + 2u);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-#if SCR_KNOCK & 1   // experiment: no mixer
-                            const uint32_t w = x[k];
-#else
-                            const uint32_t w = lhd2_mix32(x[k]);
-#endif
-#if SCR_KNOCK & 2   // experiment: no wide multiply
-                            jx[k][e] = (w >> 28) & (2u * b + e); jit[k][e] = w;
-#else
-                            mulhilo32(w, 2u * b + e + 1u, jx[k][e], jit[k][e]);
-#endif
-                            x[k] += kb[k];  // Weyl sequence A + i B
-                        }
-                    }
-                }
-                // both elements of the block in all D columns: loads first, then the stores in shuffle order.  What
-                // element 2b+1 would have read after the stores of element 2b is patched in from registers (it can
-                // only alias a[2b] or a[j0]).
-                float t0[D], t1[D], v0[D], v1[D];
-                unsigned int aj0[D], aj1[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    v0[k] = (float)(((2u * b) << 18) | (jit[k][0] >> 14));
-                    v1[k] = (float)(((2u * b + 1u) << 18) | (jit[k][1] >> 14));
-                    if (k == 0) { v0[k] *= p.col0_scale; v1[k] *= p.col0_scale; }
-                    aj0[k] = base + k * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
-                    aj1[k] = base + k * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
-#if SCR_KNOCK & 8   // experiment: no shared-memory walk (one store per column block keeps the draws live)
-                    t0[k] = v0[k] + (float)aj0[k]; t1[k] = v1[k] + (float)aj1[k];
-#else
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
-#endif
-                }
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    if (jx[k][1] == jx[k][0]) t1[k] = v0[k]; else if (jx[k][1] == 2u * b) t1[k] = t0[k];
-                    const unsigned int a0 = base + k * DS + (unsigned int)b * BS;
-#if SCR_KNOCK & 8
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k] + t1[k]) : "memory");
-#else
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k]) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj0[k]), "f"(v0[k]) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u), "f"(t1[k]) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj1[k]), "f"(v1[k]) : "memory");
-#endif
-                }
-            }
-        gen_done:
+            if (!(SCR_EXP == 1 && rnd > 0))  // experiment 1: scoring only after the first round
+                screen_generate<D, GEN>(base, NB, BS, DS, s_lo, s_hi, p.col0_scale, 18);
             // ---- scoring: row blocks in tiles of kTile, the odd blocks out one by one (screen_tile above)
             constexpr int kTile = SCR_TILE;
             constexpr int kTiles = NB / kTile;
@@ -412,44 +463,209 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
             }
             if (p.debug_scores) p.debug_scores[off] = s;
         }
-        // ---- survivors
-        auto append = [&]() {
-            const unsigned int pos = atomicAdd(p.count, 1u);
-            if (pos < p.cap) p.list[pos] = idx;
-        };
-        const bool listed = SCR_EXP == 0 || (idx & 0xFFFFF) == 0;
-        if (MAXPRO) {
-            if (rnd == 0) {
-                // the CTA's first round: everybody's threshold first, then the test against the smallest of them
-                if (active) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
-                __syncthreads();
-                const double thr = __longlong_as_double((long long)cta_thr);
-                if (active && s <= thr && listed) append();
-            } else {
-                const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
-                if (active && s <= thr && listed) {
-                    append();
-                    const double w = screen_threshold(s, p.bound);
-                    if (w < thr) atomicMin(&cta_thr, (unsigned long long)__double_as_longlong(w));
-                }
-            }
-        } else {
-            // maximin: survive unless the candidate's upper bound is below the best lower bound seen (see the header)
-            const double up = screen_mm_upper(s, p.bound), low = screen_mm_lower(s, p.bound);
-            if (rnd == 0) {
-                if (active) atomicMax(&cta_thr, (unsigned long long)__double_as_longlong(low));
-                __syncthreads();
-                const double thr = __longlong_as_double((long long)cta_thr);
-                if (active && up >= thr && listed) append();
-            } else {
-                const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)&cta_thr);
-                if (active && up >= thr && listed) {
-                    append();
-                    if (low > thr) atomicMax(&cta_thr, (unsigned long long)__double_as_longlong(low));
-                }
-            }
-        }
+        screen_survivors<MAXPRO>(p, &cta_thr, rnd == 0, active, s, idx);
     }
+}
+
+// ---- the general kernel: any even n with 8 <= n <= 256 (18 jitter bits up to n = 64, one fewer per doubling), D as a template parameter --------------------------------------
+// Same two stages, same bound, same layout (block m of dimension k of candidate c at ((k NB + m) C + c) 8) with NB = n/2
+// and the candidates per CTA as run-time values, so the partner loops are real loops and the chain bookkeeping a
+// warp-uniform counter.  Blocks are walked in tiles of two.  Block b is paired with the SH blocks that follow it
+// cyclically -- SH = (NB-1)/2 for odd NB; for even NB SH = NB/2 - 1 plus the "diameter" block b + NB/2 for the blocks
+// of the lower half -- which covers every pair of blocks once.  In a tile {m, m+1}: step 0 pairs block m with block m+1
+// (registers) and block m+1 with block m+SH+1; steps 1 .. SH-1 pair both with block m+1+s.  Every row meets one term per
+// step, so one counter tells all of them when a reciprocal chain is full (six terms).
+template <int D, bool MAXPRO>
+struct RtTile {
+    unsigned int base, BS, DS;
+    f2 eps2;
+    __device__ __forceinline__ unsigned int block_off(unsigned int mm) const { const unsigned int o = mm * BS; return min(o, o - DS); }
+    __device__ __forceinline__ void load_block(f2 (&b)[D], unsigned int off) const {
+#pragma unroll
+        for (int k = 0; k < D; ++k) b[k] = lds2(base + k * DS + off);
+    }
+    // MaxPro: q^2 + eps of two pairs; maximin: their squared distances
+    __device__ __forceinline__ f2 term2(const f2 (&a)[D], const f2 (&b)[D]) const {
+        if (MAXPRO) {
+            f2 q = sub2(a[0], b[0]);
+#pragma unroll
+            for (int k = 1; k < D; ++k) q = mul2(q, sub2(a[k], b[k]));
+            return fma2(q, q, eps2);
+        }
+        const f2 d0 = sub2(a[0], b[0]);
+        f2 q = mul2(d0, d0);
+#pragma unroll
+        for (int k = 1; k < D; ++k) { const f2 dk = sub2(a[k], b[k]); q = fma2(dk, dk, q); }
+        return q;
+    }
+    // one block's two rows as broadcast pairs, and the term of the pair inside the block
+    __device__ __forceinline__ float rows_of(const f2 (&A)[D], f2 (&X)[2][D]) const {
+        float q_in = 1.0f, s_in = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float a0, a1;
+            unpk(A[k], a0, a1);
+            X[0][k] = pk(a0, a0); X[1][k] = pk(a1, a1);
+            q_in = k == 0 ? a0 - a1 : q_in * (a0 - a1);
+            s_in = fmaf(a0 - a1, a0 - a1, s_in);
+        }
+        float e0, e1;
+        unpk(eps2, e0, e1);
+        return MAXPRO ? fmaf(q_in, q_in, e0) : s_in;
+    }
+};
+
+// running result of a candidate: MaxPro -- sum of reciprocals (chains + directly inverted terms); maximin -- minimum
+template <bool MAXPRO>
+struct RtAcc {
+    f2 vsum;
+    float direct, mn;
+    __device__ __forceinline__ void reset() { vsum = pk(0.0f, 0.0f); direct = 0.0f; mn = CUDART_INF_F; }
+    __device__ __forceinline__ void single(float t) { if (MAXPRO) direct += rcp_approx(t); else mn = fminf(mn, t); }
+    __device__ __forceinline__ void single2(f2 t) { float lo, hi; unpk(t, lo, hi); if (MAXPRO) direct += rcp_approx(lo) + rcp_approx(hi); else mn = min3(mn, lo, hi); }
+    __device__ __forceinline__ float result() const { float v0, v1; unpk(vsum, v0, v1); return MAXPRO ? v0 + v1 + direct : mn; }
+};
+
+template <int D, int GEN, bool MAXPRO>
+__global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long cta_thr;
+    const int C = (int)blockDim.x, NB = p.n / 2;
+    const unsigned int BS = (unsigned int)C * 8u, DS = (unsigned int)NB * BS;
+    const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + threadIdx.x * 8u;
+    const bool odd = (NB & 1) != 0;
+    const int SH = odd ? (NB - 1) / 2 : NB / 2 - 1;  // >= 1 (n >= 8)
+    const unsigned int half = (unsigned int)(NB / 2);
+    constexpr int kChainTerms = 6;
+
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * C + threadIdx.x;
+    const unsigned long long gstep = (unsigned long long)gridDim.x * C;
+    const unsigned long long total = p.hi - p.lo;
+    const unsigned long long rounds = (total + gstep - 1) / gstep;
+    if (threadIdx.x == 0) cta_thr = MAXPRO ? 0x7FF0000000000000ull : 0ull;
+    __syncthreads();
+    RtTile<D, MAXPRO> T{base, BS, DS, pk(p.eps_s, p.eps_s)};
+
+    for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
+        const unsigned long long off = gtid + rnd * gstep;
+        const bool active = off < total;
+        const unsigned long long idx = p.lo + off;
+        double s = 0.0;
+        if (active) {
+            const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
+            screen_generate<D, GEN>(base, NB, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits);
+            double acc = 0.0;
+            float mn_all = CUDART_INF_F;
+#pragma unroll 1
+            for (int m = 0; m < NB; m += 2) {
+                RtAcc<MAXPRO> R;
+                R.reset();
+                if (m + 1 < NB) {
+                    // ---- a tile of two blocks
+                    f2 A0[D], A1[D], X[2][2][D];
+                    T.load_block(A0, (unsigned int)m * BS);
+                    T.load_block(A1, (unsigned int)(m + 1) * BS);
+                    R.single(T.rows_of(A0, X[0]));
+                    R.single(T.rows_of(A1, X[1]));
+                    Chain2 ch[2][2];
+                    int cnt = 0;
+                    auto feed = [&](int b, const f2 (&P)[D]) {  // one term for each of the two rows of block b (cnt is warp-uniform)
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const f2 pr = T.term2(X[b][r], P);
+                            if (!MAXPRO) { R.single2(pr); continue; }
+                            if (cnt == 0) ch[b][r].start(pr); else ch[b][r].push(pr);
+                        }
+                    };
+                    auto flush = [&]() {
+                        if (MAXPRO) R.vsum = add2(R.vsum, add2(add2(ch[0][0].value(), ch[0][1].value()), add2(ch[1][0].value(), ch[1][1].value())));
+                        cnt = 0;
+                    };
+                    {   // step 0
+                        f2 E[D];
+                        T.load_block(E, T.block_off((unsigned int)(m + 1 + SH)));
+                        feed(0, A1);
+                        feed(1, E);
+                        cnt = 1;
+                    }
+#pragma unroll 1
+                    for (int st = 1; st < SH; ++st) {
+                        if (cnt == kChainTerms) flush();
+                        f2 B[D];
+                        T.load_block(B, T.block_off((unsigned int)(m + 1 + st)));
+                        feed(0, B);
+                        feed(1, B);
+                        ++cnt;
+                    }
+                    flush();
+                    if (!odd) {  // even NB: the diameter partner of the blocks of the lower half
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            if ((unsigned int)(m + b) < half) {
+                                f2 Dm[D];
+                                T.load_block(Dm, ((unsigned int)(m + b) + half) * BS);
+                                R.single2(T.term2(X[b][0], Dm));
+                                R.single2(T.term2(X[b][1], Dm));
+                            }
+                        }
+                    }
+                } else {
+                    // ---- the odd block out (odd NB): block NB-1 against blocks 0 .. SH-1
+                    f2 A0[D], X[2][D];
+                    T.load_block(A0, (unsigned int)m * BS);
+                    R.single(T.rows_of(A0, X));
+                    Chain2 ch[2];
+                    int cnt = 0;
+#pragma unroll 1
+                    for (int st = 0; st < SH; ++st) {
+                        if (cnt == kChainTerms) {
+                            if (MAXPRO) R.vsum = add2(R.vsum, add2(ch[0].value(), ch[1].value()));
+                            cnt = 0;
+                        }
+                        f2 B[D];
+                        T.load_block(B, (unsigned int)st * BS);
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const f2 pr = T.term2(X[r], B);
+                            if (!MAXPRO) { R.single2(pr); continue; }
+                            if (cnt == 0) ch[r].start(pr); else ch[r].push(pr);
+                        }
+                        ++cnt;
+                    }
+                    if (MAXPRO) R.vsum = add2(R.vsum, add2(ch[0].value(), ch[1].value()));
+                }
+                if (MAXPRO) acc += (double)R.result(); else mn_all = fminf(mn_all, R.result());
+            }
+            s = MAXPRO ? acc : (double)mn_all;
+            if (p.debug_scores) p.debug_scores[off] = s;
+        }
+        screen_survivors<MAXPRO>(p, &cta_thr, rnd == 0, active, s, idx);
+    }
+}
+
+// candidates per CTA of the general kernel for a shape (0: the shape is not served)
+static int screen_rt_cands(unsigned long long n, unsigned long long d) {
+    if (n < 8 || n > 256 || (n & 1) != 0 || d < 1 || d > 8) return 0;
+    size_t c = kSmemBudget / (n * d * sizeof(float));
+    c = c / 32 * 32;
+    if (c > 512) c = 512;
+    return c >= 128 ? (int)c : 0;
+}
+
+template <int D>
+cudaError_t launch_screen_rt_d(const SearchLaunch& L, const ScreenParams& p, int cands) {
+    const size_t smem = (size_t)L.n * D * cands * sizeof(float);
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<L.grid, cands, smem, L.stream>>>(p);
+        return cudaGetLastError();
+    };
+    if (L.metric == 0) {
+        if constexpr (D >= 2 && D <= 4) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true>) : go(search_screen_rt_kernel<D, 2, true>);
+        else return cudaErrorInvalidValue;  // search_screen_supported keeps MaxPro to d = 2 .. 4
+    }
+    return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, false>) : go(search_screen_rt_kernel<D, 2, false>);
 }
 
 template <int N, int D, int C>
@@ -468,17 +684,36 @@ cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
 
 }  // namespace
 
+// Shapes with a screening kernel; *cands = candidates per CTA (= threads).  The specialised kernel serves n = 50,
+// d = 2 or 3; the general one any even n from 8 to 256 whose design fits shared memory 128 times (n d <= 454) -- for
+// maximin all of those (its bound is tight at any d: 1.7-3x the fp64 kernels on every shape measured), for MaxPro only
+// where the survivors stay few (tools/screen_sweep.py, profiles/r2q_screen_*.txt): d = 2 .. 4 up to n = 64 and d = 2, 3
+// up to n = 100 (1.2-2.1x).  Outside that the band W / S' is wide enough that the survivors swamp stage 2 (0.5-0.7x at
+// (30,5), (50,5), (100,4), (200,2)); at d = 1 the fp64 kernel is as fast; from d ~ 8 on eps dominates the terms and
+// rho(F) stops applying at all.
 bool search_screen_supported(unsigned long long n, unsigned long long d, int metric, int* cands) {
     int c = 0;
-    if ((metric == 0 || metric == 1) && n == 50 && d == 3) c = 384;
-    else if ((metric == 0 || metric == 1) && n == 50 && d == 2) c = 512;
+    if (metric == 0 || metric == 1) {
+        if (n == 50 && d == 3) c = 384;
+        else if (n == 50 && d == 2) c = 512;
+        else if (!cfg("MAXPRO_NO_SCREEN_RT") && (metric == 1 || (d >= 2 && d <= (n <= 64 ? 4u : 3u) && n <= 100))) c = screen_rt_cands(n, d);
+    }
     if (cands) *cands = c;
     return c != 0;
 }
 
 // Host: the constants of the bound for a shape (see the header comment).
+// jitter bits stage 1 keeps for a design of n points: the most that leaves y = i 2^jbits + ... below 2^24
+static int screen_jbits(unsigned long long n) {
+    int lg = 0;
+    while ((1ull << lg) < n) ++lg;
+    const int jb = 24 - lg;
+    return jb > 18 ? 18 : jb;  // 18 is what the specialised kernel is built for; more buys nothing
+}
+
 static ScreenBound screen_bound(unsigned long long n, unsigned long long d, float* col0_scale, float* eps_s) {
-    const double unit = (double)n * 262144.0;  // y = x * n * 2^18
+    const int jb = screen_jbits(n);
+    const double unit = ldexp((double)n, jb);  // y = x * n * 2^jbits
     // exact power of two on column 0 that puts G^2 eps next to 2^-20
     const double log2_g2eps = log2(kEps) + 2.0 * (double)d * log2(unit);
     const int a = (int)llround(0.5 * (log2_g2eps + 20.0));
@@ -488,7 +723,7 @@ static ScreenBound screen_bound(unsigned long long n, unsigned long long d, floa
     ScreenBound b;
     b.g2 = G * G;
     b.eps = (double)*eps_s / b.g2;
-    const double eta = ldexp(1.0, -18) / (double)n;
+    const double eta = ldexp(1.0, -jb) / (double)n;
     b.dq = (double)d * eta * pow(1.0 + eta, (double)d - 1.0);
     // gmin = min over q >= 0 of (q^2 + eps) / ((q + dq)^2 + eps), scanned on a log grid around sqrt(eps), 2 % margin
     double g = 1.0;
@@ -498,9 +733,9 @@ static ScreenBound screen_bound(unsigned long long n, unsigned long long d, floa
         if (r < g) g = r;
     }
     b.gmin = g * 0.98;
-    b.arith = ldexp(1.0, -18);
+    b.arith = ldexp(1.0, d <= 3 ? -18 : -17);  // (2d + 25) 2^-24 at most: products, fma, six chain pushes, reciprocal, sums
     b.tau = (4.0 * (double)d + 4.0) * ldexp(1.0, -52);
-    // maximin (see the header): units of u = n 2^18, no scaling
+    // maximin (see the header): units of u = n 2^jbits, no scaling
     b.mm_c1 = 2.0 * sqrt((double)d) * (1.0 + ldexp(1.0, -20));
     b.mm_c0 = (double)d;
     b.mm_arith = ((double)d + 1.0) * ldexp(1.0, -23);
@@ -512,6 +747,8 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
                                  double* debug_scores) {
     ScreenParams p;
     p.gen = stream_version();
+    p.n = (int)L.n;
+    p.jbits = screen_jbits(L.n);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s);
     if (L.metric != 0) p.col0_scale = 1.0f;  // maximin works in plain units
@@ -519,6 +756,18 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
     p.debug_scores = debug_scores;
     if (L.n == 50 && L.d == 3) return launch_screen_nd<50, 3, 384>(L, p);
     if (L.n == 50 && L.d == 2) return launch_screen_nd<50, 2, 512>(L, p);
+    const int cands = screen_rt_cands(L.n, L.d);
+    if (cands == 0 || cands != L.threads) return cudaErrorInvalidValue;
+    switch (L.d) {
+        case 1: return launch_screen_rt_d<1>(L, p, cands);
+        case 2: return launch_screen_rt_d<2>(L, p, cands);
+        case 3: return launch_screen_rt_d<3>(L, p, cands);
+        case 4: return launch_screen_rt_d<4>(L, p, cands);
+        case 5: return launch_screen_rt_d<5>(L, p, cands);
+        case 6: return launch_screen_rt_d<6>(L, p, cands);
+        case 7: return launch_screen_rt_d<7>(L, p, cands);
+        case 8: return launch_screen_rt_d<8>(L, p, cands);
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -38,6 +38,11 @@ struct SearchParams {
     unsigned long long seed, lo, hi;
     double c1, c0;        // 2^-32/n and 2^-33/n : v = (i + (jit+0.5)*2^-32)/n
     double n_pairs, inv_d;
+    // list mode (stage 2 of the two-stage search, search_screen.cu): score list[0..*list_count_dev) instead of lo..hi;
+    // a count above list_cap means stage 1 overflowed its list: the whole range is scored instead
+    const unsigned long long* list;
+    const unsigned int* list_count_dev;
+    unsigned int list_cap;
     BestRec* block_best;  // [gridDim.x]
     unsigned int* done_counter;
     BestRec* result;      // final {score, index}
@@ -236,7 +241,13 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
 
     const unsigned long long gcid = (unsigned long long)blockIdx.x * C + c;
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
-    const unsigned long long total = p.hi - p.lo;
+    const unsigned long long* list = p.list;
+    unsigned long long list_count = 0;
+    if (list) {
+        list_count = *p.list_count_dev;
+        if (list_count > p.list_cap) list = nullptr;
+    }
+    const unsigned long long total = list ? list_count : p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;  // same trip count for every thread
 
     // token ring of the warps sharing this warp's sub-partition: barrier 1 + smsp*ring + q is
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(512, 1) search_small_kernel(SearchParams p) {
     for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
         const unsigned long long off = gcid + rnd * gstep;
         const bool active = off < total;
-        const unsigned long long idx = p.lo + off;
+        const unsigned long long idx = list ? (active ? list[off] : 0ull) : p.lo + off;
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         if (active) {
@@ -373,6 +384,7 @@ cudaError_t launch_search_small(const SearchLaunch& L) {
     p.c0 = lhd_c0(p.gen, p.c1);
     p.n_pairs = (double)L.n * ((double)L.n - 1.0) / 2.0;
     p.inv_d = 1.0 / (double)L.d;
+    p.list = L.list; p.list_count_dev = L.list_count_dev; p.list_cap = L.list_cap;
     p.block_best = L.block_best; p.done_counter = L.done_counter; p.result = L.result;
     switch (L.d) {
         case 1: return launch_d<1>(L, p);

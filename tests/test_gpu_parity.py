@@ -687,6 +687,34 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
 
 
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
+@pytest.mark.parametrize("n,d", [(8, 1), (8, 3), (10, 2), (12, 4), (20, 3), (26, 5), (30, 5), (32, 2), (50, 4), (50, 5), (62, 3), (64, 2),
+                                 (50, 8), (40, 6), (24, 7), (100, 2), (100, 4), (128, 3), (200, 2), (66, 5)])
+def test_two_stage_search_general_shapes(n, d, metric, switches):
+    """The general screening kernel (any even n from 8 to 256 with n d <= 454; MaxPro at d = 2 .. 4, maximin up to d = 8): the two-stage
+    search returns the winner, score bits and tie-break of the fp64-only search.  Shapes it does not serve (MaxPro at
+    d > 4 here) take the fp64 kernel under every flag."""
+    s_ref, i_ref = oracle.search_range(n, d, metric, 11, 0, 20_000)
+    two = engine.search_range(n, d, metric, 11, 0, 20_000, flags=1)
+    assert two == engine.search_range(n, d, metric, 11, 0, 20_000, flags=2)
+    assert two[1] == i_ref and math.isclose(two[0], s_ref, rel_tol=REL)
+    for seed in range(3):
+        lo = seed * (1 << 35) + 17
+        exact = engine.search_range(n, d, metric, 500 + seed, lo, lo + (1 << 21), flags=2)
+        assert engine.search_range(n, d, metric, 500 + seed, lo, lo + (1 << 21), flags=1) == exact, (seed, exact)
+        assert engine.search_range(n, d, metric, 500 + seed, lo, lo + (1 << 21)) == exact      # MAXPRO_FLAG_DEFAULT
+    for lo, hi in ((5, 6), (5, 5 + 511), (0, 148 * 512 + 17)):
+        assert engine.search_range(n, d, metric, 3, lo, hi, flags=1) == engine.search_range(n, d, metric, 3, lo, hi, flags=2)
+    switches.set("MAXPRO_SCREEN_CAP", "3")   # survivor list overflows: stage 2 scores the whole range
+    assert engine.search_range(n, d, metric, 1001, 0, 1 << 19, flags=1) == engine.search_range(n, d, metric, 1001, 0, 1 << 19, flags=2)
+    switches.clear("MAXPRO_SCREEN_CAP")
+    _lib.set_stream_version(1)
+    try:
+        assert engine.search_range(n, d, metric, 9, 0, 1 << 19, flags=1) == engine.search_range(n, d, metric, 9, 0, 1 << 19, flags=2)
+    finally:
+        _lib.set_stream_version(2)
+
+
+@pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 @pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
 def test_two_stage_search_returns_the_exact_winner(n, d, metric, switches):
     """The two-stage search (fp32 screening with a proven bound + fp64 re-score of the survivors) must return what the
