@@ -658,14 +658,15 @@ def test_score_batch_psi_ties_go_to_later_index():
 
 # ---------------------------------------------------------------- two-stage search (fp32 screen + exact re-score)
 
-@pytest.mark.parametrize("n,d", [(50, 3), (50, 2)])
+@pytest.mark.parametrize("n,d", [(50, 3), (50, 2), (20, 3), (64, 4), (100, 2), (12, 2)])   # specialised and general kernel
 def test_screen_bound_and_survivors_against_oracle(n, d):
     """Stage 1 alone (maxpro_debug_screen): its fp32 sums against the oracle's S for every candidate of a range, and
     its survivor list against what the proven bound promises -- every candidate that can be the winner or tie with
     it is on the list; the list is a small fraction of the range."""
     seed, lo, hi = 42, 1000, 1000 + 40_000
     surv, count, sums = _lib.debug_screen(n, d, seed, lo, hi, want_sums=True)
-    assert count == len(surv) < (hi - lo) // 10
+    # a 40,000-candidate range is less than one round per CTA: the running bound is still loose, most of all at d = 4
+    assert count == len(surv) < (hi - lo) // (10 if n == 50 else 3)
     designs = oracle.generate_batch(n, d, seed, lo, hi - lo)
     S = np.array([oracle.maxpro_sum(x) for x in designs])
     rel = np.abs(sums - S) / S
