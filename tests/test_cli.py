@@ -83,3 +83,19 @@ def test_cli_pipeline_on_a_design_larger_than_shared_memory():
     assert vals["Annealed metric"] >= vals["Swapped metric"] >= vals["Original metric"]
     import oracle
     assert oracle.maximin_criterion(design) == vals["Annealed metric"]
+
+
+@pytest.mark.gpu
+def test_cli_gpus_flag_gives_the_one_device_result():
+    """--gpus N (engine-only flag; 0 = every device of the box): the search and the chains are spread over the devices
+    inside the C ABI (maxpro_set_devices), index blocks + host fold, so the printed design and metrics are those of
+    one device whatever N is.  Also with --anneal-chains, and through the two-stage search (100,000 candidates)."""
+    base = ("--iterations", "100000", "--samples", "50", "--ndims", "3", "--metric", "max-pro", "--seed", "5",
+            "--anneal-iterations", "300", "--anneal-chains", "64")
+    one = run(*base, "--gpus", "1")
+    every = run(*base, "--gpus", "0")
+    assert one.returncode == 0 and every.returncode == 0, (one.stderr, every.stderr)
+    assert one.stdout == every.stdout
+    assert "--gpus" in run("--help").stdout
+    r = run(*base, "--gpus", "999")
+    assert r.returncode != 0 and "device" in r.stderr.lower()
