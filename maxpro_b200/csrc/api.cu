@@ -175,7 +175,7 @@ __global__ void debug_pow_kernel(const double* x, const double* y, unsigned long
 constexpr size_t kMaxBlockRecs = 4096;
 constexpr unsigned long long kScreenMinRange = 1ull << 15;  // MAXPRO_FLAG_DEFAULT: ranges below this go straight to the fp64 kernel
 constexpr unsigned int kSurvivorCap = 1u << 20;  // 8 MB; a 2^28-candidate range leaves a few tens of thousands
-constexpr size_t kGenericChunkBytes = 128ull << 20;
+constexpr size_t kGenericChunkBytes = 48ull << 20;  // below a quarter of the block-cache limit: the chunk buffer is kept between calls
 
 unsigned long long generic_chunk(unsigned long long n, unsigned long long d) {
     unsigned long long per = n * d * sizeof(double);
@@ -252,14 +252,15 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
     }
     init_counter_kernel<<<1, 1, 0, stream>>>(w.counter);
     mp::count_launch();
-    int cyc_cands = 0, scr_cands = 0;
+    int cyc_cands = 0, scr_cands = 0, scr_threads = 0;
     const bool want_screen = !(flags & MAXPRO_FLAG_FP64_ONLY) && ((flags & MAXPRO_FLAG_FP32_SCREEN) || hi - lo >= kScreenMinRange);
     const bool exact_cyclic = mp::search_cyclic_supported(n, d, &cyc_cands);
-    if (want_screen && mp::search_screen_supported(n, d, metric, &scr_cands) && (exact_cyclic || mp::search_small_supported(n, d))) {
+    const bool exact_small = !exact_cyclic && mp::search_small_supported(n, d), exact_warp = !exact_cyclic && !exact_small && use_warp_kernel(n, d);
+    if (want_screen && mp::search_screen_supported(n, d, metric, &scr_cands, &scr_threads) && (exact_cyclic || exact_small || exact_warp)) {
         // stage 1: fp32 screening with a proven bound; every candidate that can still win goes to the survivor list
         mp::SearchLaunch L{};
         L.n = n; L.d = d; L.metric = metric; L.seed = seed; L.lo = lo; L.hi = hi; L.flags = flags;
-        L.threads = scr_cands; L.group = 1;
+        L.threads = scr_threads; L.group = scr_threads / scr_cands;
         unsigned long long total = hi - lo;
         unsigned long long want = (total + scr_cands - 1) / scr_cands;
         L.grid = (int)(want < (unsigned long long)sms ? want : (unsigned long long)sms);
@@ -274,12 +275,13 @@ int search_range_device_impl(uint64_t n, uint64_t d, int metric, uint64_t seed, 
         E.block_best = w.block_best; E.done_counter = w.counter; E.result = result;
         E.list = w.survivors; E.list_count = 0; E.list_count_dev = w.counter + 1; E.list_cap = cap;
         E.stream = stream;
-        unsigned long long per_cta;
+        unsigned long long per_cta, max_grid = (unsigned long long)sms;
         if (exact_cyclic) { E.group = 2; E.threads = 2 * cyc_cands; per_cta = (unsigned long long)cyc_cands; }
-        else { mp::search_small_pick_config(n, d, &E.group, &E.threads); per_cta = (unsigned long long)(E.threads / E.group); }
+        else if (exact_small) { mp::search_small_pick_config(n, d, &E.group, &E.threads); per_cta = (unsigned long long)(E.threads / E.group); }
+        else { E.group = 0; E.threads = 128; per_cta = 4; max_grid = (unsigned long long)mp::search_warp_grid(n, d, sms); }  // 4 candidates (warps) per CTA
         unsigned long long want2 = (total + per_cta - 1) / per_cta;
-        E.grid = (int)(want2 < (unsigned long long)sms ? want2 : (unsigned long long)sms);
-        CUDA_TRY(exact_cyclic ? mp::launch_search_cyclic(E) : mp::launch_search_small(E));
+        E.grid = (int)(want2 < max_grid ? want2 : max_grid);
+        CUDA_TRY(exact_cyclic ? mp::launch_search_cyclic(E) : exact_small ? mp::launch_search_small(E) : mp::launch_search_warp(E));
         mp::count_launch();
         return MAXPRO_OK;
     }
@@ -1021,10 +1023,10 @@ int maxpro_debug_screen(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, uint
                         uint64_t capacity, uint64_t* count, double* fp32_sums) {
     if (!count) return fail(MAXPRO_ERR_INVALID, "null pointer");
     if (hi < lo) return fail(MAXPRO_ERR_INVALID, "search range is inverted");
-    int sms = 0, cands = 0;
+    int sms = 0, cands = 0, threads = 0;
     if (int rc = ensure_device(&sms)) return rc;
-    if (!mp::search_screen_supported(n, d, MAXPRO_METRIC_MAXPRO, &cands))
-        return fail(MAXPRO_ERR_UNSUPPORTED, "the fp32 screening pass covers MaxPro at n = 50, d = 2 or 3");
+    if (!mp::search_screen_supported(n, d, MAXPRO_METRIC_MAXPRO, &cands, &threads))
+        return fail(MAXPRO_ERR_UNSUPPORTED, "no MaxPro screening kernel for this shape (csrc/search_screen.cu: search_screen_supported)");
     const uint64_t total = hi - lo;
     DevBuf dl, dc, ds;
     CUDA_TRY(dl.alloc((size_t)kSurvivorCap * sizeof(unsigned long long)));
@@ -1035,7 +1037,7 @@ int maxpro_debug_screen(uint64_t n, uint64_t d, uint64_t seed, uint64_t lo, uint
     mp::count_launch();
     mp::SearchLaunch L{};
     L.n = n; L.d = d; L.metric = MAXPRO_METRIC_MAXPRO; L.seed = seed; L.lo = lo; L.hi = hi;
-    L.threads = cands; L.group = 1; L.stream = st;
+    L.threads = threads; L.group = threads / cands; L.stream = st;
     const uint64_t want = (total + cands - 1) / cands;
     L.grid = (int)(want < (uint64_t)sms ? (want ? want : 1) : (uint64_t)sms);
     CUDA_TRY(mp::launch_search_screen(L, dl.as<unsigned long long>(), dc.as<unsigned int>() + 1, kSurvivorCap,

@@ -80,6 +80,7 @@ struct ScreenBound {
 struct ScreenParams {
     int gen;                         // design stream version (philox.cuh)
     int n;                           // points per design (the general kernel; the specialised one has it as a template parameter)
+    int group;                       // general kernel: lanes per candidate (1, or 2 = one role per half-warp)
     int jbits;                       // jitter bits kept by stage 1: y = i 2^jbits + (jit >> (32 - jbits)) < 2^24 (18 up to n = 64)
     unsigned long long seed, lo, hi;
     float col0_scale;                // exact power of two carried by column 0
@@ -299,11 +300,17 @@ __device__ __forceinline__ float screen_tile_min(unsigned int base, unsigned int
 // SAME column wrote), so they are walked side by side: D loads in flight per step instead of one.
 template <int D, int GEN>
 __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsigned int BS, unsigned int DS, uint32_t s_lo, uint32_t s_hi,
-                                                float col0_scale, int jbits) {
+                                                float col0_scale, int jbits, int k0 = 0, int kstep = 1, int dtot = D) {
+    // this lane's columns: k0, k0 + kstep, ... below dtot (all D of them when one lane builds the whole design; the
+    // general kernel with two lanes per candidate gives each lane every other column and masks the one that may be missing)
     uint32_t kb[D], x[D];
+    int kc[D];
+    bool on[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { kc[k] = k0 + k * kstep; on[k] = kc[k] < dtot; }
     if (GEN == 2) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)k, s_lo, s_hi, x[k], kb[k]);
+        for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)kc[k], s_lo, s_hi, x[k], kb[k]);
     }
 #pragma unroll 2
     for (int b = 0; b < NB; ++b) {
@@ -311,7 +318,7 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if (GEN == 1) {
-                const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)k, s_lo, s_hi, kKeyLhd0, kKeyLhd1);
+                const Philox4 w = philox4x32_10((uint32_t)b, (uint32_t)kc[k], s_lo, s_hi, kKeyLhd0, kKeyLhd1);
                 jit[k][0] = w.x; jx[k][0] = __umulhi(w.y, 2u * b + 1u);
                 jit[k][1] = w.z; jx[k][1] = __umulhi(w.w, 2u * b + 2u);
             } else {
@@ -340,20 +347,24 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
         for (int k = 0; k < D; ++k) {
             v0[k] = (float)(((2u * b) << jbits) | (jit[k][0] >> (32 - jbits)));
             v1[k] = (float)(((2u * b + 1u) << jbits) | (jit[k][1] >> (32 - jbits)));
-            if (k == 0) { v0[k] *= col0_scale; v1[k] *= col0_scale; }
-            aj0[k] = base + k * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
-            aj1[k] = base + k * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
+            if (kc[k] == 0) { v0[k] *= col0_scale; v1[k] *= col0_scale; }
+            aj0[k] = base + kc[k] * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
+            aj1[k] = base + kc[k] * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
 #if SCR_KNOCK & 8   // experiment: no shared-memory walk (one store per column block keeps the draws live)
             t0[k] = v0[k] + (float)aj0[k]; t1[k] = v1[k] + (float)aj1[k];
 #else
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
+            t0[k] = 0.0f; t1[k] = 0.0f;
+            if (on[k]) {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
+            }
 #endif
         }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if (jx[k][1] == jx[k][0]) t1[k] = v0[k]; else if (jx[k][1] == 2u * b) t1[k] = t0[k];
-            const unsigned int a0 = base + k * DS + (unsigned int)b * BS;
+            const unsigned int a0 = base + kc[k] * DS + (unsigned int)b * BS;
+            if (!on[k]) continue;
 #if SCR_KNOCK & 8
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k] + t1[k]) : "memory");
 #else
@@ -530,15 +541,22 @@ template <int D, int GEN, bool MAXPRO>
 __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long cta_thr;
-    const int C = (int)blockDim.x, NB = p.n / 2;
+    // Lanes per candidate G: 1, or 2 when fewer than 256 designs fit the shared memory of an SM (n d above ~220): the
+    // two lanes of a candidate sit in different half-warps (lanes 0-15 / 16-31 of the same 16 candidates), which is
+    // the unit a 64-bit shared-memory access is served in, so their block reads never collide.  Each lane builds every
+    // other column and scores every other tile; the partial results meet in one shuffle.
+    const int G = p.group;
+    const int lane = threadIdx.x & 31, per_warp = 32 / G;
+    const int c = (int)(threadIdx.x >> 5) * per_warp + lane % per_warp, g = lane / per_warp;
+    const int C = (int)blockDim.x / G, NB = p.n / 2;
     const unsigned int BS = (unsigned int)C * 8u, DS = (unsigned int)NB * BS;
-    const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + threadIdx.x * 8u;
+    const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + (unsigned int)c * 8u;
     const bool odd = (NB & 1) != 0;
     const int SH = odd ? (NB - 1) / 2 : NB / 2 - 1;  // >= 1 (n >= 8)
     const unsigned int half = (unsigned int)(NB / 2);
     constexpr int kChainTerms = 6;
 
-    const unsigned long long gtid = (unsigned long long)blockIdx.x * C + threadIdx.x;
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * C + c;
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
     const unsigned long long total = p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
@@ -553,11 +571,15 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
         double s = 0.0;
         if (active) {
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
-            screen_generate<D, GEN>(base, NB, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits);
+            if (G == 1) screen_generate<D, GEN>(base, NB, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits);
+            else screen_generate<(D + 1) / 2, GEN>(base, NB, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D);
+        }
+        if (G > 1) __syncwarp();  // the design is complete before either lane scores it
+        if (active) {
             double acc = 0.0;
             float mn_all = CUDART_INF_F;
 #pragma unroll 1
-            for (int m = 0; m < NB; m += 2) {
+            for (int m = 2 * g; m < NB; m += 2 * G) {
                 RtAcc<MAXPRO> R;
                 R.reset();
                 if (m + 1 < NB) {
@@ -637,28 +659,35 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
                 if (MAXPRO) acc += (double)R.result(); else mn_all = fminf(mn_all, R.result());
             }
             s = MAXPRO ? acc : (double)mn_all;
-            if (p.debug_scores) p.debug_scores[off] = s;
         }
-        screen_survivors<MAXPRO>(p, &cta_thr, rnd == 0, active, s, idx);
+        if (G > 1) {  // the two partial results of a candidate; also: both lanes are done reading before the design is overwritten
+            const double other = __shfl_xor_sync(0xffffffffu, s, 16);
+            s = MAXPRO ? ((g == 0) ? s + other : other + s) : fmin(s, other);
+        }
+        if (active && g == 0 && p.debug_scores) p.debug_scores[off] = s;
+        screen_survivors<MAXPRO>(p, &cta_thr, rnd == 0, active && g == 0, s, idx);
     }
 }
 
-// candidates per CTA of the general kernel for a shape (0: the shape is not served)
-static int screen_rt_cands(unsigned long long n, unsigned long long d) {
+// candidates per CTA of the general kernel for a shape (0: the shape is not served) and the lanes per candidate
+static int screen_rt_cands(unsigned long long n, unsigned long long d, int* group) {
+    if (group) *group = 1;
     if (n < 8 || n > 256 || (n & 1) != 0 || d < 1 || d > 8) return 0;
     size_t c = kSmemBudget / (n * d * sizeof(float));
-    c = c / 32 * 32;
-    if (c > 512) c = 512;
-    return c >= 128 ? (int)c : 0;
+    if (c >= 256) return (int)((c > 512 ? 512 : c) / 32 * 32);
+    c = c / 16 * 16;  // two lanes per candidate: 16 candidates per warp
+    if (group) *group = 2;
+    return c >= 64 ? (int)c : 0;
 }
 
 template <int D>
 cudaError_t launch_screen_rt_d(const SearchLaunch& L, const ScreenParams& p, int cands) {
     const size_t smem = (size_t)L.n * D * cands * sizeof(float);
+    const int threads = cands * p.group;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<L.grid, cands, smem, L.stream>>>(p);
+        kernel<<<L.grid, threads, smem, L.stream>>>(p);
         return cudaGetLastError();
     };
     if (L.metric == 0) {
@@ -684,21 +713,22 @@ cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
 
 }  // namespace
 
-// Shapes with a screening kernel; *cands = candidates per CTA (= threads).  The specialised kernel serves n = 50,
-// d = 2 or 3; the general one any even n from 8 to 256 whose design fits shared memory 128 times (n d <= 454) -- for
-// maximin all of those (its bound is tight at any d: 1.7-3x the fp64 kernels on every shape measured), for MaxPro only
-// where the survivors stay few (tools/screen_sweep.py, profiles/r2q_screen_*.txt): d = 2 .. 4 up to n = 64 and d = 2, 3
-// up to n = 100 (1.2-2.1x).  Outside that the band W / S' is wide enough that the survivors swamp stage 2 (0.5-0.7x at
-// (30,5), (50,5), (100,4), (200,2)); at d = 1 the fp64 kernel is as fast; from d ~ 8 on eps dominates the terms and
-// rho(F) stops applying at all.
-bool search_screen_supported(unsigned long long n, unsigned long long d, int metric, int* cands) {
-    int c = 0;
+// Shapes with a screening kernel; *cands = candidates per CTA, *threads = its block size.  The specialised kernel serves
+// n = 50, d = 2 or 3; the general one any even n from 8 to 256 whose design fits shared memory 64 times (n d <= 908,
+// d <= 8) -- for maximin all of those (its bound is tight at any d: 2-3.6x the fp64 kernels on every shape measured),
+// for MaxPro only where the survivors stay few (tools/screen_sweep.py, profiles/r2q_screen_*.txt, r2t_screen_*.txt):
+// d = 2 at any n, d = 3 up to n = 160, d = 4 up to n = 64 (1.3-2.1x).  Outside that the band W / S' is wide enough that
+// the survivors swamp stage 2 (0.5-0.7x at (30,5), (50,5), (100,4), (200,3), (256,3)); at d = 1 the fp64 kernel is as fast;
+// from d ~ 8 on eps dominates the terms and rho(F) stops applying at all.
+bool search_screen_supported(unsigned long long n, unsigned long long d, int metric, int* cands, int* threads) {
+    int c = 0, group = 1;
     if (metric == 0 || metric == 1) {
         if (n == 50 && d == 3) c = 384;
         else if (n == 50 && d == 2) c = 512;
-        else if (!cfg("MAXPRO_NO_SCREEN_RT") && (metric == 1 || (d >= 2 && d <= (n <= 64 ? 4u : 3u) && n <= 100))) c = screen_rt_cands(n, d);
+        else if (!cfg("MAXPRO_NO_SCREEN_RT") && (metric == 1 || d == 2 || (d == 3 && n <= 160) || (d == 4 && n <= 64))) c = screen_rt_cands(n, d, &group);
     }
     if (cands) *cands = c;
+    if (threads) *threads = c * group;
     return c != 0;
 }
 
@@ -748,6 +778,7 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
     ScreenParams p;
     p.gen = stream_version();
     p.n = (int)L.n;
+    p.group = 1;
     p.jbits = screen_jbits(L.n);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s);
@@ -756,8 +787,8 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
     p.debug_scores = debug_scores;
     if (L.n == 50 && L.d == 3) return launch_screen_nd<50, 3, 384>(L, p);
     if (L.n == 50 && L.d == 2) return launch_screen_nd<50, 2, 512>(L, p);
-    const int cands = screen_rt_cands(L.n, L.d);
-    if (cands == 0 || cands != L.threads) return cudaErrorInvalidValue;
+    const int cands = screen_rt_cands(L.n, L.d, &p.group);
+    if (cands == 0 || cands * p.group != L.threads) return cudaErrorInvalidValue;
     switch (L.d) {
         case 1: return launch_screen_rt_d<1>(L, p, cands);
         case 2: return launch_screen_rt_d<2>(L, p, cands);

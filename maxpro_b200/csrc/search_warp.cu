@@ -39,6 +39,11 @@ struct WarpParams {
     int n, d, ns;  // ns = row stride of the [k][i] layout: n + copied rows, even (16-byte loads), 2 or 10 mod 16 (the column walkers hit different banks)
     unsigned int cand_bytes;  // shared memory of one candidate slot
     unsigned long long seed, lo, hi;
+    // list mode (stage 2 of the two-stage search, search_screen.cu): score list[0..*list_count_dev) instead of lo..hi; a count
+    // above list_cap means stage 1 overflowed its list: the whole range is scored instead
+    const unsigned long long* list;
+    const unsigned int* list_count_dev;
+    unsigned int list_cap;
     double c1, c0, n_pairs, inv_d;
     BestRec* block_best;
     unsigned int* done_counter;
@@ -66,7 +71,15 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 4) search_warp_kernel(WarpPar
     lb.init(p.inv_d);
 
     const unsigned long long wstep = (unsigned long long)gridDim.x * (kWarpCtaThreads / 32);
-    for (unsigned long long idx = p.lo + (unsigned long long)blockIdx.x * (kWarpCtaThreads / 32) + warp; idx < p.hi; idx += wstep) {
+    const unsigned long long* list = p.list;
+    unsigned long long list_count = 0;
+    if (list) {
+        list_count = *p.list_count_dev;
+        if (list_count > p.list_cap) list = nullptr;
+    }
+    const unsigned long long total = list ? list_count : p.hi - p.lo;
+    for (unsigned long long off = (unsigned long long)blockIdx.x * (kWarpCtaThreads / 32) + warp; off < total; off += wstep) {
+        const unsigned long long idx = list ? list[off] : p.lo + off;
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         __syncwarp();  // previous candidate fully consumed
@@ -238,6 +251,7 @@ cudaError_t launch_search_warp(const SearchLaunch& L) {
     p.n = (int)L.n; p.d = (int)L.d; p.ns = (int)warp_row_stride(L.n);
     p.cand_bytes = warp_cand_bytes(L.n, L.d);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
+    p.list = L.list; p.list_count_dev = L.list_count_dev; p.list_cap = L.list_cap;
     p.gen = stream_version();
     p.c1 = ldexp(1.0 / (double)L.n, -32);
     p.c0 = lhd_c0(p.gen, p.c1);

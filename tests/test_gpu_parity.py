@@ -689,9 +689,10 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
 
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 @pytest.mark.parametrize("n,d", [(8, 1), (8, 3), (10, 2), (12, 4), (20, 3), (26, 5), (30, 5), (32, 2), (50, 4), (50, 5), (62, 3), (64, 2),
-                                 (50, 8), (40, 6), (24, 7), (100, 2), (100, 4), (128, 3), (200, 2), (66, 5)])
+                                 (50, 8), (40, 6), (24, 7), (100, 2), (100, 4), (128, 3), (200, 2), (66, 5),
+                                 (100, 5), (100, 8), (128, 7), (200, 4), (256, 3), (90, 1), (64, 8)])   # two lanes per candidate from n d ~ 220 up
 def test_two_stage_search_general_shapes(n, d, metric, switches):
-    """The general screening kernel (any even n from 8 to 256 with n d <= 454; MaxPro at d = 2 .. 4, maximin up to d = 8): the two-stage
+    """The general screening kernel (any even n from 8 to 256 with n d <= 908; MaxPro at d = 2 .. 4, maximin up to d = 8): the two-stage
     search returns the winner, score bits and tie-break of the fp64-only search.  Shapes it does not serve (MaxPro at
     d > 4 here) take the fp64 kernel under every flag."""
     s_ref, i_ref = oracle.search_range(n, d, metric, 11, 0, 20_000)

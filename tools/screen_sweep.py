@@ -4,7 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine
 shapes = [(10, 2), (20, 3), (30, 5), (40, 4), (50, 4), (50, 5), (64, 2), (64, 3), (50, 8), (64, 6), (32, 7)]
 if len(sys.argv) > 1 and sys.argv[1] == 'big':
-    shapes = [(80, 2), (80, 5), (100, 2), (100, 3), (100, 4), (128, 3), (150, 3), (200, 2), (256, 1)]
+    shapes = [(64, 4), (80, 2), (80, 5), (100, 2), (100, 3), (100, 4), (100, 5), (100, 8), (128, 3), (128, 6), (150, 3), (200, 2), (200, 4), (256, 1), (256, 3)]
+if len(sys.argv) > 1 and sys.argv[1] == 'mp':
+    shapes = [(80, 3), (100, 3), (128, 2), (128, 3), (150, 2), (150, 3), (200, 2), (200, 3), (256, 2), (256, 3)]
 if len(sys.argv) > 1 and sys.argv[1] == 'grid':
     shapes = [(n, d) for d in (1, 2, 3, 4) for n in (8, 12, 16, 24, 32, 48, 64)]
 for metric, name in ((METRIC_MAXPRO, "maxpro"), (METRIC_MAXIMIN, "maximin")):

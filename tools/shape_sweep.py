@@ -10,7 +10,7 @@ shapes = [(10, 2), (20, 3), (30, 5), (50, 2), (50, 3), (50, 4), (50, 8), (64, 6)
 for n, d in shapes:
     flops = ((3 * d + 3) if metric == METRIC_MAXPRO else (3 * d + 2)) * n * (n - 1) // 2
     N = max(2000, min(1 << 26, int(2e12 / flops)))  # ~0.1-0.2 s of work at 10-20 TFLOP/s
-    engine.search_range(n, d, metric, 42, 0, min(N, 20000))
+    engine.search_range(n, d, metric, 42, 0, min(N, 1 << 16))  # same path as the timed call (two-stage from 32,768 candidates up)
     t0 = time.perf_counter()
     s, i = engine.search_range(n, d, metric, 42, 0, N)
     dt = time.perf_counter() - t0
