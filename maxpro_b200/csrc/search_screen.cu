@@ -300,7 +300,8 @@ __device__ __forceinline__ float screen_tile_min(unsigned int base, unsigned int
 // SAME column wrote), so they are walked side by side: D loads in flight per step instead of one.
 template <int D, int GEN>
 __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsigned int BS, unsigned int DS, uint32_t s_lo, uint32_t s_hi,
-                                                float col0_scale, int jbits, int k0 = 0, int kstep = 1, int dtot = D) {
+                                                float col0_scale, int jbits, int k0 = 0, int kstep = 1, int dtot = D, bool single_last = false) {
+    // single_last: the design has an odd number of points -- the last block holds one element (its second half is never used)
     // this lane's columns: k0, k0 + kstep, ... below dtot (all D of them when one lane builds the whole design; the
     // general kernel with two lanes per candidate gives each lane every other column and masks the one that may be missing)
     uint32_t kb[D], x[D];
@@ -356,7 +357,7 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
             t0[k] = 0.0f; t1[k] = 0.0f;
             if (on[k]) {
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0[k]) : "r"(aj0[k]) : "memory");
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
+                if (!(single_last && b == NB - 1)) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1[k]) : "r"(aj1[k]) : "memory");
             }
 #endif
         }
@@ -370,6 +371,7 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
 #else
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(t0[k]) : "memory");
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj0[k]), "f"(v0[k]) : "memory");
+            if (single_last && b == NB - 1) continue;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u), "f"(t1[k]) : "memory");
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(aj1[k]), "f"(v1[k]) : "memory");
 #endif
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     }
 }
 
-// ---- the general kernel: any even n with 8 <= n <= 256 (18 jitter bits up to n = 64, one fewer per doubling), D as a template parameter --------------------------------------
+// ---- the general kernel: any n with 8 <= n <= 256 (18 jitter bits up to n = 64, one fewer per doubling), D as a template parameter --------------------------------------
 // Same two stages, same bound, same layout (block m of dimension k of candidate c at ((k NB + m) C + c) 8) with NB = n/2
 // and the candidates per CTA as run-time values, so the partner loops are real loops and the chain bookkeeping a
 // warp-uniform counter.  Blocks are walked in tiles of two.  Block b is paired with the SH blocks that follow it
@@ -488,9 +490,9 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
 // step, so one counter tells all of them when a reciprocal chain is full (six terms).
 template <int D, bool MAXPRO>
 struct RtTile {
-    unsigned int base, BS, DS;
+    unsigned int base, BS, DS, WR;  // DS: dimension stride (all stored blocks); WR: NB * BS, the wrap of the cyclic pairing
     f2 eps2;
-    __device__ __forceinline__ unsigned int block_off(unsigned int mm) const { const unsigned int o = mm * BS; return min(o, o - DS); }
+    __device__ __forceinline__ unsigned int block_off(unsigned int mm) const { const unsigned int o = mm * BS; return min(o, o - WR); }
     __device__ __forceinline__ void load_block(f2 (&b)[D], unsigned int off) const {
 #pragma unroll
         for (int k = 0; k < D; ++k) b[k] = lds2(base + k * DS + off);
@@ -548,8 +550,11 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
     const int G = p.group;
     const int lane = threadIdx.x & 31, per_warp = 32 / G;
     const int c = (int)(threadIdx.x >> 5) * per_warp + lane % per_warp, g = lane / per_warp;
-    const int C = (int)blockDim.x / G, NB = p.n / 2;
-    const unsigned int BS = (unsigned int)C * 8u, DS = (unsigned int)NB * BS;
+    // An odd number of points: the first n - 1 rows are paired block-wise as usual; the last row sits alone in one more
+    // block (low half) and meets every block in a pass of its own.
+    const bool n_odd = (p.n & 1) != 0;
+    const int C = (int)blockDim.x / G, NB = p.n / 2, NBS = NB + (n_odd ? 1 : 0);  // paired blocks, stored blocks
+    const unsigned int BS = (unsigned int)C * 8u, DS = (unsigned int)NBS * BS;
     const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + (unsigned int)c * 8u;
     const bool odd = (NB & 1) != 0;
     const int SH = odd ? (NB - 1) / 2 : NB / 2 - 1;  // >= 1 (n >= 8)
@@ -562,7 +567,7 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
     const unsigned long long rounds = (total + gstep - 1) / gstep;
     if (threadIdx.x == 0) cta_thr = MAXPRO ? 0x7FF0000000000000ull : 0ull;
     __syncthreads();
-    RtTile<D, MAXPRO> T{base, BS, DS, pk(p.eps_s, p.eps_s)};
+    RtTile<D, MAXPRO> T{base, BS, DS, (unsigned int)NB * BS, pk(p.eps_s, p.eps_s)};
 
     for (unsigned long long rnd = 0; rnd < rounds; ++rnd) {
         const unsigned long long off = gtid + rnd * gstep;
@@ -571,8 +576,8 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
         double s = 0.0;
         if (active) {
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
-            if (G == 1) screen_generate<D, GEN>(base, NB, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits);
-            else screen_generate<(D + 1) / 2, GEN>(base, NB, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D);
+            if (G == 1) screen_generate<D, GEN>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, 0, 1, D, n_odd);
+            else screen_generate<(D + 1) / 2, GEN>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D, n_odd);
         }
         if (G > 1) __syncwarp();  // the design is complete before either lane scores it
         if (active) {
@@ -658,6 +663,29 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
                 }
                 if (MAXPRO) acc += (double)R.result(); else mn_all = fminf(mn_all, R.result());
             }
+            if (n_odd) {
+                // ---- the last row (odd n) against every block; with two lanes per candidate each takes every other block
+                RtAcc<MAXPRO> R;
+                R.reset();
+                f2 AL[D], XL[D];
+                T.load_block(AL, (unsigned int)NB * BS);
+#pragma unroll
+                for (int k = 0; k < D; ++k) { float a0, a1; unpk(AL[k], a0, a1); XL[k] = pk(a0, a0); }
+                Chain2 chl;
+                int cnt = 0;
+#pragma unroll 1
+                for (int m = g; m < NB; m += G) {
+                    f2 B[D];
+                    T.load_block(B, (unsigned int)m * BS);
+                    const f2 pr = T.term2(XL, B);
+                    if (!MAXPRO) { R.single2(pr); continue; }
+                    if (cnt == kChainTerms) { R.vsum = add2(R.vsum, chl.value()); cnt = 0; }
+                    if (cnt == 0) chl.start(pr); else chl.push(pr);
+                    ++cnt;
+                }
+                if (MAXPRO && cnt > 0) R.vsum = add2(R.vsum, chl.value());
+                if (MAXPRO) acc += (double)R.result(); else mn_all = fminf(mn_all, R.result());
+            }
             s = MAXPRO ? acc : (double)mn_all;
         }
         if (G > 1) {  // the two partial results of a candidate; also: both lanes are done reading before the design is overwritten
@@ -672,8 +700,9 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
 // candidates per CTA of the general kernel for a shape (0: the shape is not served) and the lanes per candidate
 static int screen_rt_cands(unsigned long long n, unsigned long long d, int* group) {
     if (group) *group = 1;
-    if (n < 8 || n > 256 || (n & 1) != 0 || d < 1 || d > 8) return 0;
-    size_t c = kSmemBudget / (n * d * sizeof(float));
+    if (n < 8 || n > 256 || d < 1 || d > 8) return 0;
+    const unsigned long long rows = n + (n & 1);  // an odd design stores one more (unused) row
+    size_t c = kSmemBudget / (rows * d * sizeof(float));
     if (c >= 256) return (int)((c > 512 ? 512 : c) / 32 * 32);
     c = c / 16 * 16;  // two lanes per candidate: 16 candidates per warp
     if (group) *group = 2;
@@ -682,7 +711,7 @@ static int screen_rt_cands(unsigned long long n, unsigned long long d, int* grou
 
 template <int D>
 cudaError_t launch_screen_rt_d(const SearchLaunch& L, const ScreenParams& p, int cands) {
-    const size_t smem = (size_t)L.n * D * cands * sizeof(float);
+    const size_t smem = (size_t)(L.n + (L.n & 1)) * D * cands * sizeof(float);
     const int threads = cands * p.group;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -714,7 +743,7 @@ cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
 }  // namespace
 
 // Shapes with a screening kernel; *cands = candidates per CTA, *threads = its block size.  The specialised kernel serves
-// n = 50, d = 2 or 3; the general one any even n from 8 to 256 whose design fits shared memory 64 times (n d <= 908,
+// n = 50, d = 2 or 3; the general one any n from 8 to 256 whose design fits shared memory 64 times (n d <= 908,
 // d <= 8) -- for maximin all of those (its bound is tight at any d: 2-3.6x the fp64 kernels on every shape measured),
 // for MaxPro only where the survivors stay few (tools/screen_sweep.py, profiles/r2q_screen_*.txt, r2t_screen_*.txt):
 // d = 2 at any n, d = 3 up to n = 160, d = 4 up to n = 64 (1.3-2.1x).  Outside that the band W / S' is wide enough that

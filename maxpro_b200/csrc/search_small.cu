@@ -340,7 +340,9 @@ static cudaError_t launch_d(const SearchLaunch& L, const SearchParams& p) {
 bool search_small_supported(unsigned long long n, unsigned long long d) {
     unsigned long long min_cands = 64;
     if (const char* e = cfg("MAXPRO_SMALL_MIN_CANDS")) { int v = atoi(e); if (v >= 16 && v <= 512 && v % 16 == 0) min_cands = (unsigned long long)v; }
-    return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * min_cands + 32 * sizeof(BestRec) <= kSmemBudget;
+    // 256 bytes of slack: the kernel's static shared memory (block_publish_best) and the per-CTA reservation come out of the
+    // same 227 KB -- a design that fills the budget to the byte, (151,3), failed its launch with cudaErrorInvalidValue
+    return d >= 1 && d <= kSmallMaxD && n >= 2 && n * d * sizeof(double) * min_cands + 32 * sizeof(BestRec) + 256 <= kSmemBudget;
 }
 
 // Lanes per candidate and CTA size.  Two lanes per candidate whenever there are at least two

@@ -658,7 +658,7 @@ def test_score_batch_psi_ties_go_to_later_index():
 
 # ---------------------------------------------------------------- two-stage search (fp32 screen + exact re-score)
 
-@pytest.mark.parametrize("n,d", [(50, 3), (50, 2), (20, 3), (64, 4), (100, 2), (12, 2)])   # specialised and general kernel
+@pytest.mark.parametrize("n,d", [(50, 3), (50, 2), (20, 3), (64, 4), (100, 2), (12, 2), (51, 3), (25, 2)])   # specialised and general kernel
 def test_screen_bound_and_survivors_against_oracle(n, d):
     """Stage 1 alone (maxpro_debug_screen): its fp32 sums against the oracle's S for every candidate of a range, and
     its survivor list against what the proven bound promises -- every candidate that can be the winner or tie with
@@ -690,9 +690,11 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 @pytest.mark.parametrize("n,d", [(8, 1), (8, 3), (10, 2), (12, 4), (20, 3), (26, 5), (30, 5), (32, 2), (50, 4), (50, 5), (62, 3), (64, 2),
                                  (50, 8), (40, 6), (24, 7), (100, 2), (100, 4), (128, 3), (200, 2), (66, 5),
-                                 (100, 5), (100, 8), (128, 7), (200, 4), (256, 3), (90, 1), (64, 8)])   # two lanes per candidate from n d ~ 220 up
+                                 (100, 5), (100, 8), (128, 7), (200, 4), (256, 3), (90, 1), (64, 8),   # two lanes per candidate from n d ~ 220 up
+                                 (9, 2), (13, 1), (25, 3), (51, 3), (63, 4), (99, 5), (101, 2), (255, 2),   # odd n: the last row in a pass of its own
+                                 (151, 3)])   # 3,624 B per design: filled the thread-group kernel's shared-memory budget to the byte
 def test_two_stage_search_general_shapes(n, d, metric, switches):
-    """The general screening kernel (any even n from 8 to 256 with n d <= 908; MaxPro at d = 2 .. 4, maximin up to d = 8): the two-stage
+    """The general screening kernel (any n from 8 to 256 with n d <= 908; MaxPro at d = 2 .. 4, maximin up to d = 8): the two-stage
     search returns the winner, score bits and tie-break of the fp64-only search.  Shapes it does not serve (MaxPro at
     d > 4 here) take the fp64 kernel under every flag."""
     s_ref, i_ref = oracle.search_range(n, d, metric, 11, 0, 20_000)

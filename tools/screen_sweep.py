@@ -5,6 +5,8 @@ from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine
 shapes = [(10, 2), (20, 3), (30, 5), (40, 4), (50, 4), (50, 5), (64, 2), (64, 3), (50, 8), (64, 6), (32, 7)]
 if len(sys.argv) > 1 and sys.argv[1] == 'big':
     shapes = [(64, 4), (80, 2), (80, 5), (100, 2), (100, 3), (100, 4), (100, 5), (100, 8), (128, 3), (128, 6), (150, 3), (200, 2), (200, 4), (256, 1), (256, 3)]
+if len(sys.argv) > 1 and sys.argv[1] == 'odd':
+    shapes = [(9, 2), (25, 3), (51, 3), (63, 4), (101, 2), (151, 3), (255, 2), (99, 5)]
 if len(sys.argv) > 1 and sys.argv[1] == 'mp':
     shapes = [(80, 3), (100, 3), (128, 2), (128, 3), (150, 2), (150, 3), (200, 2), (200, 3), (256, 2), (256, 3)]
 if len(sys.argv) > 1 and sys.argv[1] == 'grid':
