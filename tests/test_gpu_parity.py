@@ -838,3 +838,14 @@ def test_reference_scripts_flow_through_import_maxpro():
     ordered = ref_named.order_design(b, "maxpro")                         # comparisons.py:99-104
     assert sorted(map(tuple, ordered)) == sorted(map(tuple, b))
     assert ref_named.build_lhd(10, 3, 100, "maximin", seed=12345) == ref_named.build_lhd(10, 3, 100, "maximin", seed=12345)
+
+
+def test_kernel_handover_shapes_launch_and_agree():
+    """tools/boundary_sweep.py: ~190 shapes within two points of every hand-over between the search kernels (thread-group /
+    warp / CTA double- and single-buffered / chunked; general screening kernel with one and two lanes) launch under
+    MAXPRO_FLAG_FP64_ONLY and under the default flags, and the returned score is the criterion of the regenerated winner.
+    (A design that filled the thread-group kernel's shared-memory budget to the byte used to fail its launch.)"""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "boundary_sweep.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "failures: 0" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
