@@ -328,11 +328,11 @@ static size_t anneal_smem_bytes_buffers(unsigned long long n, unsigned long long
 // Placement of a chain's design (see anneal_kernel): 0 shared memory, 1 jitter with the current design in
 // HBM scratch, 2 everything in HBM scratch.
 static bool anneal_all_in_hbm(unsigned long long n, unsigned long long d) {
-    return anneal_smem_bytes_buffers(n, d, 1) > kSmemBudget;
+    return anneal_smem_bytes_buffers(n, d, 1) > kSmemBudget - kSmemSlack;
 }
 static int anneal_place(unsigned long long n, unsigned long long d, int swap) {
     if (anneal_all_in_hbm(n, d)) return 2;
-    if (!swap && anneal_smem_bytes_buffers(n, d, 2) > kSmemBudget) return 1;
+    if (!swap && anneal_smem_bytes_buffers(n, d, 2) > kSmemBudget - kSmemSlack) return 1;
     return 0;
 }
 
@@ -354,7 +354,7 @@ size_t anneal_jitter_scratch_bytes(unsigned long long n, unsigned long long d, i
 // Every design the 16-bit row indices can address is supported: what does not fit shared memory is annealed out of HBM.
 bool anneal_supported(unsigned long long n, unsigned long long d, int swap) {
     return n >= 1 && d >= 1 && n < (1ull << 30) / (d ? d : 1) && n <= 65535 && d <= 65535 &&
-           anneal_smem_bytes(n, d, swap) <= kSmemBudget;  // the staged rows of a move (2 d doubles) stay in shared memory
+           anneal_smem_bytes(n, d, swap) <= kSmemBudget - kSmemSlack;  // the staged rows of a move (2 d doubles) stay in shared memory
 }
 
 static int round_up_32(unsigned long long v) { return (int)((v + 31) / 32 * 32); }

@@ -420,7 +420,7 @@ size_t anneal_maximin_smem_bytes(unsigned long long n, unsigned long long d) {
 
 bool anneal_maximin_supported(unsigned long long n, unsigned long long d, int metric, int swap) {
     if (const char* e = cfg("MAXPRO_NO_ANNEAL_MAXIMIN_INC")) if (atoi(e) != 0) return false;
-    return metric == 1 && swap != 0 && n >= 2 && n <= 65535 && d >= 1 && d <= 65535 && anneal_maximin_smem_bytes(n, d) <= kSmemBudget;
+    return metric == 1 && swap != 0 && n >= 2 && n <= 65535 && d >= 1 && d <= 65535 && anneal_maximin_smem_bytes(n, d) <= kSmemBudget - kSmemSlack;
 }
 
 cudaError_t launch_anneal_maximin(const AnnealLaunch& L, int plan_sms, unsigned int* plan_grid) {

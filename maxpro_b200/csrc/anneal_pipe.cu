@@ -407,7 +407,7 @@ size_t pipe_smem_bytes(unsigned long long n, unsigned long long d) {
 
 bool anneal_pipe_supported(unsigned long long n, unsigned long long d, int metric, int swap) {
     if (const char* e = cfg("MAXPRO_NO_ANNEAL_PIPE")) if (atoi(e) != 0) return false;
-    return metric == 0 && swap && n >= 4 && n <= 65535 && d >= 1 && d <= 65535 && pipe_smem_bytes(n, d) <= kSmemBudget;
+    return metric == 0 && swap && n >= 4 && n <= 65535 && d >= 1 && d <= 65535 && pipe_smem_bytes(n, d) <= kSmemBudget - kSmemSlack;
 }
 
 cudaError_t launch_anneal_pipe(const AnnealLaunch& L, int plan_sms, unsigned int* plan_grid) {

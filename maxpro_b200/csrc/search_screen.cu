@@ -702,7 +702,7 @@ static int screen_rt_cands(unsigned long long n, unsigned long long d, int* grou
     if (group) *group = 1;
     if (n < 8 || n > 256 || d < 1 || d > 8) return 0;
     const unsigned long long rows = n + (n & 1);  // an odd design stores one more (unused) row
-    size_t c = kSmemBudget / (rows * d * sizeof(float));
+    size_t c = (kSmemBudget - kSmemSlack) / (rows * d * sizeof(float));
     if (c >= 256) return (int)((c > 512 ? 512 : c) / 32 * 32);
     c = c / 16 * 16;  // two lanes per candidate: 16 candidates per warp
     if (group) *group = 2;

@@ -351,7 +351,7 @@ bool search_small_supported(unsigned long long n, unsigned long long d) {
 void search_small_pick_config(unsigned long long n, unsigned long long d, int* group, int* threads) {
     int G = d >= 2 ? 2 : 1;
     size_t per = (size_t)n * d * sizeof(double);
-    size_t cap = (kSmemBudget - 32 * sizeof(BestRec)) / per;
+    size_t cap = (kSmemBudget - 32 * sizeof(BestRec) - 256) / per;  // 256: the kernel's static shared memory (see search_small_supported)
     // Four lanes per candidate when shared memory leaves two lanes fewer than 10 warps (n*d above ~180
     // elements) and there are four or more columns -- except d = 5 (2+1+1+1 columns per lane: the
     // generation phase is as long as with two lanes, and the scoring tiles get smaller).  Measured,

@@ -29,4 +29,7 @@ for d in (5, 10, 20):
         n0 = target // d
         for n in range(n0 - 2, n0 + 3):
             probe(n, d)
+# designs whose size divides the 227 KB budget exactly (a design per CTA that fills it to the byte): 232,448 = 2^10 * 227
+for n, d in ((151, 1), (151, 2), (151, 3), (227, 1), (227, 2), (227, 4), (227, 8), (113, 2), (113, 4)):
+    probe(n, d)
 print("boundary sweep done, failures:", bad)
