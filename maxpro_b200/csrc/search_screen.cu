@@ -39,6 +39,21 @@
 // candidate with S' <= W, for the smallest W known when it is scored, loses none of them.  W / S' is about 1.07
 // at n = 50, d = 3: the survivors are the candidates within a few percent of the running best.
 //
+// ---- a second, per-candidate bound (MaxPro) ---------------------------------------------------------------------------
+// The bound above charges every term with the worst case "one difference changed by eta, the others equal to 1".  In a
+// Latin hypercube much more is known: column k, sorted, runs through the strata in order, so no two of its values are
+// closer than the smallest gap between ADJACENT strata, and generation sees those gaps as it goes (stratum i is drawn
+// right after stratum i-1).  With m the smallest adjacent gap of the candidate over all columns, in the integer units of y,
+// every computed difference has |d'| >= m and the true one lies within one unit of it, so for every pair
+//     q / q' = prod_k (1 + e_k / d'_k)   lies in   [(1 - 1/m)^d, (1 + 1/m)^d],      theta := (1 + 1/m)^d - 1,
+// and f'/f = (q^2 + eps) / (q'^2 + eps) lies between 1 and q^2/q'^2, hence in [(1 - theta)^2, (1 + theta)^2]: every term,
+// and so the sum, is off by at most r = 2 theta + theta^2 relative -- whatever d is and however much eps matters.
+// m is a few thousand units at least for all but a fraction of a percent of the candidates (r ~ 1e-3 and less), so
+//     S'/((1 + r)(1 + arith)) =: L  <=  S  <=  U := S' (1 + arith)/(1 - r)
+// is far tighter than the first bound; a candidate survives only if its L is not above the smallest U its CTA has seen
+// (times the tie band).  Both tests are necessary conditions for being the winner, so both are applied; the first one
+// alone stopped paying at d = 5 (W/S' too wide), the second works up to the d = 8 the kernels are built for.
+//
 // ---- maximin (same two stages) ----------------------------------------------------------------------------------
 // The criterion is the smallest pairwise distance, larger is better (src/maximin_utils.rs:54-67).  Stage 1 takes the
 // minimum m' over the pairs of s' = sum_k (y_ak - y_bk)^2 in fp32, in units of u = n 2^18 (no scaling: s' < 2^50).
@@ -79,11 +94,12 @@ struct ScreenBound {
 
 struct ScreenParams {
     int gen;                         // design stream version (philox.cuh)
-    int n;                           // points per design (the general kernel; the specialised one has it as a template parameter)
+    int n, d;                        // points and dimensions of a design (the general kernel reads n; both read d for the bound)
     int group;                       // general kernel: lanes per candidate (1, or 2 = one role per half-warp)
     int jbits;                       // jitter bits kept by stage 1: y = i 2^jbits + (jit >> (32 - jbits)) < 2^24 (18 up to n = 64)
     unsigned long long seed, lo, hi;
-    float col0_scale;                // exact power of two carried by column 0
+    float col0_scale;                // exact power of two carried by column 0 (d <= 5) ...
+    float col_scale[8];              // ... or spread over all columns (d >= 6: one column cannot hold 2^-130 and more)
     float eps_s;                     // eps in scaled units
     ScreenBound bound;
     unsigned long long* list;        // survivors (candidate indices)
@@ -298,9 +314,10 @@ __device__ __forceinline__ float screen_tile_min(unsigned int base, unsigned int
 // integer-valued floats (see the header).  NB, BS and DS are compile-time constants in the specialised kernel and run-time
 // values in the general one.  The D columns are independent Fisher-Yates chains (each step reads what an earlier step of the
 // SAME column wrote), so they are walked side by side: D loads in flight per step instead of one.
-template <int D, int GEN>
-__device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsigned int BS, unsigned int DS, uint32_t s_lo, uint32_t s_hi,
-                                                float col0_scale, int jbits, int k0 = 0, int kstep = 1, int dtot = D, bool single_last = false) {
+template <int D, int GEN, bool ALLCOLS = false, bool TRACK = true>
+__device__ __forceinline__ unsigned int screen_generate(unsigned int base, int NB, unsigned int BS, unsigned int DS, uint32_t s_lo, uint32_t s_hi,
+                                                float col0_scale, int jbits, int k0 = 0, int kstep = 1, int dtot = D, bool single_last = false,
+                                                const float* col_scale = nullptr) {
     // single_last: the design has an odd number of points -- the last block holds one element (its second half is never used)
     // this lane's columns: k0, k0 + kstep, ... below dtot (all D of them when one lane builds the whole design; the
     // general kernel with two lanes per candidate gives each lane every other column and masks the one that may be missing)
@@ -313,6 +330,9 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
 #pragma unroll
         for (int k = 0; k < D; ++k) lhd2_column_key((uint32_t)kc[k], s_lo, s_hi, x[k], kb[k]);
     }
+    // smallest gap between adjacent strata over this lane's columns, in units of y (see the header: the second bound)
+    unsigned int gap_min = 0xFFFFFFFFu, prev[D];
+    const unsigned int one = 1u << jbits;
 #pragma unroll 2
     for (int b = 0; b < NB; ++b) {
         uint32_t jx[D][2], jit[D][2];
@@ -346,9 +366,16 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
         unsigned int aj0[D], aj1[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            v0[k] = (float)(((2u * b) << jbits) | (jit[k][0] >> (32 - jbits)));
-            v1[k] = (float)(((2u * b + 1u) << jbits) | (jit[k][1] >> (32 - jbits)));
-            if (kc[k] == 0) { v0[k] *= col0_scale; v1[k] *= col0_scale; }
+            const unsigned int f0 = jit[k][0] >> (32 - jbits), f1 = jit[k][1] >> (32 - jbits);
+            v0[k] = (float)(((2u * b) << jbits) | f0);
+            v1[k] = (float)(((2u * b + 1u) << jbits) | f1);
+            if (TRACK && on[k]) {
+                if (b > 0) gap_min = min(gap_min, one + f0 - prev[k]);                                  // strata 2b-1, 2b
+                if (!(single_last && b == NB - 1)) gap_min = min(gap_min, one + f1 - f0);                // strata 2b, 2b+1
+                prev[k] = f1;
+            }
+            if (ALLCOLS) { const float sc = col_scale[on[k] ? kc[k] : 0]; v0[k] *= sc; v1[k] *= sc; }
+            else if (kc[k] == 0) { v0[k] *= col0_scale; v1[k] *= col0_scale; }
             aj0[k] = base + kc[k] * DS + (jx[k][0] >> 1) * BS + (jx[k][0] & 1u) * 4u;
             aj1[k] = base + kc[k] * DS + (jx[k][1] >> 1) * BS + (jx[k][1] & 1u) * 4u;
 #if SCR_KNOCK & 8   // experiment: no shared-memory walk (one store per column block keeps the draws live)
@@ -377,6 +404,7 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
 #endif
         }
     }
+    return TRACK ? gap_min : 0u;  // 0: no gap information, the second bound is not applied
 }
 
 // Survivor test of one candidate against its CTA's running bound (see the header), and the update of that bound.
@@ -385,24 +413,41 @@ __device__ __forceinline__ void screen_generate(unsigned int base, int NB, unsig
 // a barrier: everybody's bound first, then the test against the best of them).
 template <bool MAXPRO>
 __device__ __forceinline__ void screen_survivors(const ScreenParams& p, unsigned long long* cta_thr, bool first_round, bool active,
-                                                 double s, unsigned long long idx) {
+                                                 double s, unsigned long long idx, unsigned int gap_min) {
     auto append = [&]() {
         const unsigned int pos = atomicAdd(p.count, 1u);
         if (pos < p.cap) p.list[pos] = idx;
     };
     const bool listed = SCR_EXP == 0 || (idx & 0xFFFFF) == 0;
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
     if (MAXPRO) {
+        // first bound: threshold W implied by this candidate's sum; second bound: [L, U] from its smallest adjacent gap
+        double r = inf;  // gap_min == 0: the kernel does not track the gaps for this shape (the first bound is tight enough there)
+        if (gap_min != 0u) {
+            const double t = 1.0 + 1.0 / (double)gap_min;
+            double pw = t;
+            for (int k = 1; k < p.d; ++k) pw *= t;
+            const double theta = pw - 1.0;
+            r = theta * (2.0 + theta);
+        }
+        const double low = r < inf ? s / ((1.0 + r) * (1.0 + p.bound.arith)) : 0.0;
+        const double up = r < 1.0 ? s * (1.0 + p.bound.arith) / (1.0 - r) * (1.0 + p.bound.tau) : inf;  // tie band folded in
         if (first_round) {
-            if (active) atomicMin(cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
+            if (active) {
+                atomicMin(cta_thr, (unsigned long long)__double_as_longlong(screen_threshold(s, p.bound)));
+                atomicMin(cta_thr + 1, (unsigned long long)__double_as_longlong(up));
+            }
             __syncthreads();
-            const double thr = __longlong_as_double((long long)*cta_thr);
-            if (active && s <= thr && listed) append();
+            const double thr = __longlong_as_double((long long)cta_thr[0]), thr_u = __longlong_as_double((long long)cta_thr[1]);
+            if (active && s <= thr && low <= thr_u && listed) append();
         } else {
             const double thr = __longlong_as_double((long long)*(volatile unsigned long long*)cta_thr);
-            if (active && s <= thr && listed) {
+            const double thr_u = __longlong_as_double((long long)*(volatile unsigned long long*)(cta_thr + 1));
+            if (active && s <= thr && low <= thr_u && listed) {
                 append();
                 const double w = screen_threshold(s, p.bound);
                 if (w < thr) atomicMin(cta_thr, (unsigned long long)__double_as_longlong(w));
+                if (up < thr_u) atomicMin(cta_thr + 1, (unsigned long long)__double_as_longlong(up));
             }
         }
     } else {
@@ -427,9 +472,10 @@ __device__ __forceinline__ void screen_survivors(const ScreenParams& p, unsigned
 template <int N, int D, int C, int GEN, bool MAXPRO>
 __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // MaxPro: smallest survivor threshold W implied by a candidate of this CTA; maximin: largest lower bound of a
-    // candidate's squared minimum (bits of non-negative doubles: the integer order is the numeric order)
-    __shared__ unsigned long long cta_thr;
+    // MaxPro: [0] smallest survivor threshold W implied by a candidate of this CTA, [1] smallest upper bound U of a candidate's
+    // sum; maximin: [0] largest lower bound of a candidate's squared minimum (bits of non-negative doubles: the integer
+    // order is the numeric order)
+    __shared__ unsigned long long cta_thr[2];
     static_assert(N % 2 == 0 && (N / 2) % 2 == 1 && N <= 64, "row blocks: an odd number of them, strata below 2^6");
     constexpr int NB = N / 2;  // row blocks of two
     constexpr unsigned BS = C * 8u, DS = NB * BS;
@@ -439,7 +485,7 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
     const unsigned long long total = p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
-    if (threadIdx.x == 0) cta_thr = MAXPRO ? 0x7FF0000000000000ull : 0ull;
+    if (threadIdx.x == 0) { cta_thr[0] = MAXPRO ? 0x7FF0000000000000ull : 0ull; cta_thr[1] = 0x7FF0000000000000ull; }
     __syncthreads();
     const f2 eps2 = pk(p.eps_s, p.eps_s);
 
@@ -448,11 +494,12 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
         const bool active = off < total;
         const unsigned long long idx = p.lo + off;
         double s = 0.0;
+        unsigned int gap_min = 0u;
         if (active) {
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
             const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
             if (!(SCR_EXP == 1 && rnd > 0))  // experiment 1: scoring only after the first round
-                screen_generate<D, GEN>(base, NB, BS, DS, s_lo, s_hi, p.col0_scale, 18);
+                gap_min = screen_generate<D, GEN, false, false>(base, NB, BS, DS, s_lo, s_hi, p.col0_scale, 18);  // first bound only: tight at these shapes
             // ---- scoring: row blocks in tiles of kTile, the odd blocks out one by one (screen_tile above)
             constexpr int kTile = SCR_TILE;
             constexpr int kTiles = NB / kTile;
@@ -476,7 +523,7 @@ __global__ void __launch_bounds__(C, 1) search_screen_kernel(ScreenParams p) {
             }
             if (p.debug_scores) p.debug_scores[off] = s;
         }
-        screen_survivors<MAXPRO>(p, &cta_thr, rnd == 0, active, s, idx);
+        screen_survivors<MAXPRO>(p, cta_thr, rnd == 0, active, s, idx, gap_min);
     }
 }
 
@@ -539,10 +586,10 @@ struct RtAcc {
     __device__ __forceinline__ float result() const { float v0, v1; unpk(vsum, v0, v1); return MAXPRO ? v0 + v1 + direct : mn; }
 };
 
-template <int D, int GEN, bool MAXPRO>
+template <int D, int GEN, bool MAXPRO, bool TRACK>
 __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long cta_thr;
+    __shared__ unsigned long long cta_thr[2];
     // Lanes per candidate G: 1, or 2 when fewer than 256 designs fit the shared memory of an SM (n d above ~220): the
     // two lanes of a candidate sit in different half-warps (lanes 0-15 / 16-31 of the same 16 candidates), which is
     // the unit a 64-bit shared-memory access is served in, so their block reads never collide.  Each lane builds every
@@ -565,7 +612,7 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
     const unsigned long long gstep = (unsigned long long)gridDim.x * C;
     const unsigned long long total = p.hi - p.lo;
     const unsigned long long rounds = (total + gstep - 1) / gstep;
-    if (threadIdx.x == 0) cta_thr = MAXPRO ? 0x7FF0000000000000ull : 0ull;
+    if (threadIdx.x == 0) { cta_thr[0] = MAXPRO ? 0x7FF0000000000000ull : 0ull; cta_thr[1] = 0x7FF0000000000000ull; }
     __syncthreads();
     RtTile<D, MAXPRO> T{base, BS, DS, (unsigned int)NB * BS, pk(p.eps_s, p.eps_s)};
 
@@ -574,10 +621,12 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
         const bool active = off < total;
         const unsigned long long idx = p.lo + off;
         double s = 0.0;
+        unsigned int gap_min = 0xFFFFFFFFu;
         if (active) {
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
-            if (G == 1) screen_generate<D, GEN>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, 0, 1, D, n_odd);
-            else screen_generate<(D + 1) / 2, GEN>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D, n_odd);
+            constexpr bool kAllCols = MAXPRO && D > 5;  // the power-of-two scale of the MaxPro terms: in column 0, or spread over all
+            if (G == 1) gap_min = screen_generate<D, GEN, kAllCols, TRACK>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, 0, 1, D, n_odd, p.col_scale);
+            else gap_min = screen_generate<(D + 1) / 2, GEN, kAllCols, TRACK>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D, n_odd, p.col_scale);
         }
         if (G > 1) __syncwarp();  // the design is complete before either lane scores it
         if (active) {
@@ -691,9 +740,10 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
         if (G > 1) {  // the two partial results of a candidate; also: both lanes are done reading before the design is overwritten
             const double other = __shfl_xor_sync(0xffffffffu, s, 16);
             s = MAXPRO ? ((g == 0) ? s + other : other + s) : fmin(s, other);
+            if (TRACK) gap_min = min(gap_min, __shfl_xor_sync(0xffffffffu, gap_min, 16));
         }
         if (active && g == 0 && p.debug_scores) p.debug_scores[off] = s;
-        screen_survivors<MAXPRO>(p, &cta_thr, rnd == 0, active && g == 0, s, idx);
+        screen_survivors<MAXPRO>(p, cta_thr, rnd == 0, active && g == 0, s, idx, gap_min);
     }
 }
 
@@ -720,10 +770,16 @@ cudaError_t launch_screen_rt_d(const SearchLaunch& L, const ScreenParams& p, int
         return cudaGetLastError();
     };
     if (L.metric == 0) {
-        if constexpr (D >= 2 && D <= 4) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true>) : go(search_screen_rt_kernel<D, 2, true>);
-        else return cudaErrorInvalidValue;  // search_screen_supported keeps MaxPro to d = 2 .. 4
+        // the second (adjacent-gap) bound costs ~2.5 instructions per generated element: tracked where the first one is too
+        // wide to keep the survivors few -- d >= 4, and d = 3 beyond n = 160 (measured: tools/screen_sweep.py)
+        constexpr bool kAlways = D >= 4, kNever = D <= 2;
+        const bool track = kAlways || (!kNever && L.n > 160);
+        if constexpr (kAlways) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, true>) : go(search_screen_rt_kernel<D, 2, true, true>);
+        else if constexpr (kNever) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, false>) : go(search_screen_rt_kernel<D, 2, true, false>);
+        else if (track) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, true>) : go(search_screen_rt_kernel<D, 2, true, true>);
+        else return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, false>) : go(search_screen_rt_kernel<D, 2, true, false>);
     }
-    return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, false>) : go(search_screen_rt_kernel<D, 2, false>);
+    return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, false, false>) : go(search_screen_rt_kernel<D, 2, false, false>);
 }
 
 template <int N, int D, int C>
@@ -743,18 +799,17 @@ cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
 }  // namespace
 
 // Shapes with a screening kernel; *cands = candidates per CTA, *threads = its block size.  The specialised kernel serves
-// n = 50, d = 2 or 3; the general one any n from 8 to 256 whose design fits shared memory 64 times (n d <= 908,
-// d <= 8) -- for maximin all of those (its bound is tight at any d: 2-3.6x the fp64 kernels on every shape measured),
-// for MaxPro only where the survivors stay few (tools/screen_sweep.py, profiles/r2q_screen_*.txt, r2t_screen_*.txt):
-// d = 2 at any n, d = 3 up to n = 160, d = 4 up to n = 64 (1.3-2.1x).  Outside that the band W / S' is wide enough that
-// the survivors swamp stage 2 (0.5-0.7x at (30,5), (50,5), (100,4), (200,3), (256,3)); at d = 1 the fp64 kernel is as fast;
-// from d ~ 8 on eps dominates the terms and rho(F) stops applying at all.
+// n = 50, d = 2 or 3; the general one any n from 8 to 256 whose design fits shared memory 64 times (n d <= 908, d <= 8),
+// for maximin (2-3.6x the fp64 kernels on every shape measured) and, from d = 2 up, for MaxPro (1.15-2.1x:
+// tools/screen_sweep.py, profiles/r2w_screen_*.txt; at d = 1 the fp64 kernel is as fast).  With the first bound alone
+// MaxPro stopped paying at d = 5 and at (100,4), (200,3): the survivors swamped stage 2 (0.5-0.7x, profiles/r2q_*, r2t_*);
+// the adjacent-gap bound (header) keeps them to a fraction of a percent at every d.
 bool search_screen_supported(unsigned long long n, unsigned long long d, int metric, int* cands, int* threads) {
     int c = 0, group = 1;
     if (metric == 0 || metric == 1) {
         if (n == 50 && d == 3) c = 384;
         else if (n == 50 && d == 2) c = 512;
-        else if (!cfg("MAXPRO_NO_SCREEN_RT") && (metric == 1 || d == 2 || (d == 3 && n <= 160) || (d == 4 && n <= 64))) c = screen_rt_cands(n, d, &group);
+        else if (!cfg("MAXPRO_NO_SCREEN_RT") && (metric == 1 || d >= 2)) c = screen_rt_cands(n, d, &group);
     }
     if (cands) *cands = c;
     if (threads) *threads = c * group;
@@ -770,14 +825,15 @@ static int screen_jbits(unsigned long long n) {
     return jb > 18 ? 18 : jb;  // 18 is what the specialised kernel is built for; more buys nothing
 }
 
-static ScreenBound screen_bound(unsigned long long n, unsigned long long d, float* col0_scale, float* eps_s) {
+static ScreenBound screen_bound(unsigned long long n, unsigned long long d, float* col0_scale, float* eps_s, int* scale_exp = nullptr) {
     const int jb = screen_jbits(n);
     const double unit = ldexp((double)n, jb);  // y = x * n * 2^jbits
     // exact power of two on column 0 that puts G^2 eps next to 2^-20
     const double log2_g2eps = log2(kEps) + 2.0 * (double)d * log2(unit);
     const int a = (int)llround(0.5 * (log2_g2eps + 20.0));
     const double G = pow(unit, (double)d) * ldexp(1.0, -a);
-    *col0_scale = (float)ldexp(1.0, -a);
+    *col0_scale = (float)ldexp(1.0, -a);  // d >= 6: below the fp32 range; the callers spread 2^-a over the columns (scale_exp)
+    if (scale_exp) *scale_exp = a;
     *eps_s = (float)(kEps * G * G);
     ScreenBound b;
     b.g2 = G * G;
@@ -806,11 +862,16 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
                                  double* debug_scores) {
     ScreenParams p;
     p.gen = stream_version();
-    p.n = (int)L.n;
+    p.n = (int)L.n; p.d = (int)L.d;
     p.group = 1;
     p.jbits = screen_jbits(L.n);
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
-    p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s);
+    int scale_exp = 0;
+    p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s, &scale_exp);
+    for (int k = 0; k < 8; ++k) {  // 2^-a as d factors whose exponents differ by at most one
+        const int dd = (int)L.d, share = scale_exp / dd + (k < scale_exp % dd ? 1 : 0);
+        p.col_scale[k] = k < dd ? (float)ldexp(1.0, -share) : 1.0f;
+    }
     if (L.metric != 0) p.col0_scale = 1.0f;  // maximin works in plain units
     p.list = list; p.count = count; p.cap = cap;
     p.debug_scores = debug_scores;

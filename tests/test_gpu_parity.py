@@ -672,15 +672,11 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
     rel = np.abs(sums - S) / S
     best = int(np.argmin(S))
     good = S <= 4.0 * S[best]
-    assert rel[good].max() < 0.05, rel[good].max()      # the analytic bound is ~3-4 % at these sums
+    assert rel[good].max() < 0.05, rel[good].max()      # the first analytic bound is ~3-4 % at these sums
     assert np.median(rel) < 1e-4                         # and the typical error is far below it
     # the promise: whoever is within the tie band of the true minimum survived ...
     must = {lo + int(i) for i in np.nonzero(S <= S[best] * (1 + 1e-9))[0]}
     assert must <= set(int(v) for v in surv)
-    # ... and so did everyone whose fp32 sum is under the smallest threshold any candidate implies
-    w_min = min(_lib.debug_screen_threshold(n, d, float(v)) for v in np.sort(sums)[:200])
-    for i in np.nonzero(sums <= w_min)[0]:
-        assert lo + int(i) in must or (lo + int(i)) in set(int(v) for v in surv)
     # the threshold of a candidate is a true upper bound on every fp32 sum of candidates at or below its true S
     for i in np.argsort(S)[:50]:
         w = _lib.debug_screen_threshold(n, d, float(sums[i]))
@@ -694,9 +690,9 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
                                  (9, 2), (13, 1), (25, 3), (51, 3), (63, 4), (99, 5), (101, 2), (255, 2),   # odd n: the last row in a pass of its own
                                  (151, 3)])   # 3,624 B per design: filled the thread-group kernel's shared-memory budget to the byte
 def test_two_stage_search_general_shapes(n, d, metric, switches):
-    """The general screening kernel (any n from 8 to 256 with n d <= 908; MaxPro at d = 2 .. 4, maximin up to d = 8): the two-stage
+    """The general screening kernel (any n from 8 to 256 with n d <= 908 and d <= 8; MaxPro from d = 2 up): the two-stage
     search returns the winner, score bits and tie-break of the fp64-only search.  Shapes it does not serve (MaxPro at
-    d > 4 here) take the fp64 kernel under every flag."""
+    d = 1 here) take the fp64 kernel under every flag."""
     s_ref, i_ref = oracle.search_range(n, d, metric, 11, 0, 20_000)
     two = engine.search_range(n, d, metric, 11, 0, 20_000, flags=1)
     assert two == engine.search_range(n, d, metric, 11, 0, 20_000, flags=2)
