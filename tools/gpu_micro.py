@@ -43,8 +43,8 @@ if mode == "screen":
     total = 1 << 26
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         for (n, d) in ((50, 3), (50, 2)):
-            ms0 = dev_search(n, d, metric, total)
-            ms1 = dev_search(n, d, metric, total, flags=1)
+            ms0 = dev_search(n, d, metric, total, flags=2)   # MAXPRO_FLAG_FP64_ONLY
+            ms1 = dev_search(n, d, metric, total, flags=1)   # two-stage
             print(f"n={n} d={d} metric={metric}: exact {total/ms0/1e6:.3f} Gcand/s | fp32 screen + fp64 rescore {total/ms1/1e6:.3f} Gcand/s", flush=True)
     sys.exit(0)
 
