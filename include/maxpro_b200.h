@@ -54,7 +54,7 @@ typedef enum {
 } maxpro_metric;
 
 /* flags for maxpro_search_range_device / maxpro_search_range_ex / maxpro_build_lhd_ex.
- * Two-stage search (small designs: any n from 8 to 256 with n*d <= 908 and d <= 8; MaxPro from d = 2 up --
+ * Two-stage search (small designs: any n from 8 to 256 with n*d up to ~1700 and d <= 10; MaxPro from d = 2 up --
  * csrc/search_screen.cu: search_screen_supported): an fp32 screening pass with a proven error bound keeps every
  * candidate that can still be the winner or tie with it, the exact fp64 kernel re-scores those.  Same winner,
  * same score and same tie rule as the fp64-only search (csrc/search_screen.cu derives the bound; the parity tests

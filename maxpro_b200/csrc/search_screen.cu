@@ -99,7 +99,7 @@ struct ScreenParams {
     int jbits;                       // jitter bits kept by stage 1: y = i 2^jbits + (jit >> (32 - jbits)) < 2^24 (18 up to n = 64)
     unsigned long long seed, lo, hi;
     float col0_scale;                // exact power of two carried by column 0 (d <= 5) ...
-    float col_scale[8];              // ... or spread over all columns (d >= 6: one column cannot hold 2^-130 and more)
+    float col_scale[10];             // ... or spread over all columns (d >= 6: one column cannot hold 2^-130 and more)
     float eps_s;                     // eps in scaled units
     ScreenBound bound;
     unsigned long long* list;        // survivors (candidate indices)
@@ -586,14 +586,16 @@ struct RtAcc {
     __device__ __forceinline__ float result() const { float v0, v1; unpk(vsum, v0, v1); return MAXPRO ? v0 + v1 + direct : mn; }
 };
 
-template <int D, int GEN, bool MAXPRO, bool TRACK>
-__global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p) {
+template <int D, int GEN, bool MAXPRO, bool TRACK, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) search_screen_rt_kernel(ScreenParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long cta_thr[2];
-    // Lanes per candidate G: 1, or 2 when fewer than 256 designs fit the shared memory of an SM (n d above ~220): the
-    // two lanes of a candidate sit in different half-warps (lanes 0-15 / 16-31 of the same 16 candidates), which is
-    // the unit a 64-bit shared-memory access is served in, so their block reads never collide.  Each lane builds every
-    // other column and scores every other tile; the partial results meet in one shuffle.
+    // Lanes per candidate G: 1 while 256 designs fit the shared memory of an SM (n d up to ~220), 2 while 128 do, else 4.
+    // The lanes of a candidate sit in different parts of the warp (G = 2: lanes 0-15 / 16-31 of the same 16 candidates;
+    // G = 4: quarter-warps of the same 8).  A 64-bit shared-memory access is served per half-warp, so with G = 2 the
+    // two roles never collide; with G = 4 the two roles of a half-warp always read blocks two apart, and the block
+    // stride carries 32 bytes of padding that puts those into the two halves of the banks.  Each lane builds every
+    // G-th column and scores every G-th tile; the partial results meet in one or two shuffles.
     const int G = p.group;
     const int lane = threadIdx.x & 31, per_warp = 32 / G;
     const int c = (int)(threadIdx.x >> 5) * per_warp + lane % per_warp, g = lane / per_warp;
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
     // block (low half) and meets every block in a pass of its own.
     const bool n_odd = (p.n & 1) != 0;
     const int C = (int)blockDim.x / G, NB = p.n / 2, NBS = NB + (n_odd ? 1 : 0);  // paired blocks, stored blocks
-    const unsigned int BS = (unsigned int)C * 8u, DS = (unsigned int)NBS * BS;
+    const unsigned int BS = (unsigned int)C * 8u + (G == 4 ? 32u : 0u), DS = (unsigned int)NBS * BS;
     const unsigned int base = (unsigned int)__cvta_generic_to_shared(smem_raw) + (unsigned int)c * 8u;
     const bool odd = (NB & 1) != 0;
     const int SH = odd ? (NB - 1) / 2 : NB / 2 - 1;  // >= 1 (n >= 8)
@@ -626,7 +628,8 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
             const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
             constexpr bool kAllCols = MAXPRO && D > 5;  // the power-of-two scale of the MaxPro terms: in column 0, or spread over all
             if (G == 1) gap_min = screen_generate<D, GEN, kAllCols, TRACK>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, 0, 1, D, n_odd, p.col_scale);
-            else gap_min = screen_generate<(D + 1) / 2, GEN, kAllCols, TRACK>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D, n_odd, p.col_scale);
+            else if (G == 2) gap_min = screen_generate<(D + 1) / 2, GEN, kAllCols, TRACK>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 2, D, n_odd, p.col_scale);
+            else gap_min = screen_generate<(D + 3) / 4, GEN, kAllCols, TRACK>(base, NBS, BS, DS, (uint32_t)stream, (uint32_t)(stream >> 32), p.col0_scale, p.jbits, g, 4, D, n_odd, p.col_scale);
         }
         if (G > 1) __syncwarp();  // the design is complete before either lane scores it
         if (active) {
@@ -737,10 +740,12 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
             }
             s = MAXPRO ? acc : (double)mn_all;
         }
-        if (G > 1) {  // the two partial results of a candidate; also: both lanes are done reading before the design is overwritten
-            const double other = __shfl_xor_sync(0xffffffffu, s, 16);
-            s = MAXPRO ? ((g == 0) ? s + other : other + s) : fmin(s, other);
-            if (TRACK) gap_min = min(gap_min, __shfl_xor_sync(0xffffffffu, gap_min, 16));
+        // the partial results of a candidate's lanes (role 0 ends up with the whole); also: every lane is done reading
+        // before the design is overwritten
+        for (int w = 16; w >= 32 / G && G > 1; w >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, s, w);
+            s = MAXPRO ? s + other : fmin(s, other);
+            if (TRACK) gap_min = min(gap_min, __shfl_xor_sync(0xffffffffu, gap_min, w));
         }
         if (active && g == 0 && p.debug_scores) p.debug_scores[off] = s;
         screen_survivors<MAXPRO>(p, cta_thr, rnd == 0, active && g == 0, s, idx, gap_min);
@@ -750,19 +755,32 @@ __global__ void __launch_bounds__(512, 1) search_screen_rt_kernel(ScreenParams p
 // candidates per CTA of the general kernel for a shape (0: the shape is not served) and the lanes per candidate
 static int screen_rt_cands(unsigned long long n, unsigned long long d, int* group) {
     if (group) *group = 1;
-    if (n < 8 || n > 256 || d < 1 || d > 8) return 0;
+    if (n < 8 || n > 256 || d < 1 || d > 10) return 0;
     const unsigned long long rows = n + (n & 1);  // an odd design stores one more (unused) row
     size_t c = (kSmemBudget - kSmemSlack) / (rows * d * sizeof(float));
-    if (c >= 256) return (int)((c > 512 ? 512 : c) / 32 * 32);
-    c = c / 16 * 16;  // two lanes per candidate: 16 candidates per warp
-    if (group) *group = 2;
-    return c >= 64 ? (int)c : 0;
+    if (c >= 256 && d <= 8) return (int)((c > 512 ? 512 : c) / 32 * 32);
+    if (c >= 128 && d <= 8) {  // two lanes per candidate: 16 candidates per warp
+        if (group) *group = 2;
+        return (int)(c / 16 * 16);
+    }
+    // four lanes per candidate, 8 candidates per warp, 32 bytes of padding per row block; d = 9, 10: at most 256 threads
+    // (the kernel needs more than 128 registers there)
+    const size_t per_block_row = (kSmemBudget - kSmemSlack) / (d * (rows / 2));  // bytes one row block of all candidates may take
+    if (per_block_row < 32 + 8 * 32) return 0;
+    c = (per_block_row - 32) / 8 / 8 * 8;
+    if (c > 120) c = 120;
+    if (d > 8 && c > 64) c = 64;
+    if (group) *group = 4;
+    return c >= 32 ? (int)c : 0;
 }
 
 template <int D>
 cudaError_t launch_screen_rt_d(const SearchLaunch& L, const ScreenParams& p, int cands) {
-    const size_t smem = (size_t)(L.n + (L.n & 1)) * D * cands * sizeof(float);
+    const size_t nbs = (size_t)(L.n + (L.n & 1)) / 2;
+    const size_t smem = (size_t)D * nbs * ((size_t)cands * 8 + (p.group == 4 ? 32 : 0));
     const int threads = cands * p.group;
+    constexpr int kMaxT = D <= 8 ? 512 : 256;
+    if (threads > kMaxT) return cudaErrorInvalidValue;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -774,12 +792,12 @@ cudaError_t launch_screen_rt_d(const SearchLaunch& L, const ScreenParams& p, int
         // wide to keep the survivors few -- d >= 4, and d = 3 beyond n = 160 (measured: tools/screen_sweep.py)
         constexpr bool kAlways = D >= 4, kNever = D <= 2;
         const bool track = kAlways || (!kNever && L.n > 160);
-        if constexpr (kAlways) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, true>) : go(search_screen_rt_kernel<D, 2, true, true>);
-        else if constexpr (kNever) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, false>) : go(search_screen_rt_kernel<D, 2, true, false>);
-        else if (track) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, true>) : go(search_screen_rt_kernel<D, 2, true, true>);
-        else return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, false>) : go(search_screen_rt_kernel<D, 2, true, false>);
+        if constexpr (kAlways) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, true, kMaxT>) : go(search_screen_rt_kernel<D, 2, true, true, kMaxT>);
+        else if constexpr (kNever) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, false, kMaxT>) : go(search_screen_rt_kernel<D, 2, true, false, kMaxT>);
+        else if (track) return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, true, kMaxT>) : go(search_screen_rt_kernel<D, 2, true, true, kMaxT>);
+        else return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, true, false, kMaxT>) : go(search_screen_rt_kernel<D, 2, true, false, kMaxT>);
     }
-    return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, false, false>) : go(search_screen_rt_kernel<D, 2, false, false>);
+    return p.gen == 1 ? go(search_screen_rt_kernel<D, 1, false, false, kMaxT>) : go(search_screen_rt_kernel<D, 2, false, false, kMaxT>);
 }
 
 template <int N, int D, int C>
@@ -799,7 +817,7 @@ cudaError_t launch_screen_nd(const SearchLaunch& L, const ScreenParams& p) {
 }  // namespace
 
 // Shapes with a screening kernel; *cands = candidates per CTA, *threads = its block size.  The specialised kernel serves
-// n = 50, d = 2 or 3; the general one any n from 8 to 256 whose design fits shared memory 64 times (n d <= 908, d <= 8),
+// n = 50, d = 2 or 3; the general one any n from 8 to 256 whose design fits shared memory 32 times (n d <= ~1700, d <= 10),
 // for maximin (2-3.6x the fp64 kernels on every shape measured) and, from d = 2 up, for MaxPro (1.15-2.1x:
 // tools/screen_sweep.py, profiles/r2w_screen_*.txt; at d = 1 the fp64 kernel is as fast).  With the first bound alone
 // MaxPro stopped paying at d = 5 and at (100,4), (200,3): the survivors swamped stage 2 (0.5-0.7x, profiles/r2q_*, r2t_*);
@@ -868,7 +886,7 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
     p.seed = L.seed; p.lo = L.lo; p.hi = L.hi;
     int scale_exp = 0;
     p.bound = screen_bound(L.n, L.d, &p.col0_scale, &p.eps_s, &scale_exp);
-    for (int k = 0; k < 8; ++k) {  // 2^-a as d factors whose exponents differ by at most one
+    for (int k = 0; k < 10; ++k) {  // 2^-a as d factors whose exponents differ by at most one
         const int dd = (int)L.d, share = scale_exp / dd + (k < scale_exp % dd ? 1 : 0);
         p.col_scale[k] = k < dd ? (float)ldexp(1.0, -share) : 1.0f;
     }
@@ -888,6 +906,8 @@ cudaError_t launch_search_screen(const SearchLaunch& L, unsigned long long* list
         case 6: return launch_screen_rt_d<6>(L, p, cands);
         case 7: return launch_screen_rt_d<7>(L, p, cands);
         case 8: return launch_screen_rt_d<8>(L, p, cands);
+        case 9: return launch_screen_rt_d<9>(L, p, cands);
+        case 10: return launch_screen_rt_d<10>(L, p, cands);
     }
     return cudaErrorInvalidValue;
 }

@@ -688,9 +688,10 @@ def test_screen_bound_and_survivors_against_oracle(n, d):
                                  (50, 8), (40, 6), (24, 7), (100, 2), (100, 4), (128, 3), (200, 2), (66, 5),
                                  (100, 5), (100, 8), (128, 7), (200, 4), (256, 3), (90, 1), (64, 8),   # two lanes per candidate from n d ~ 220 up
                                  (9, 2), (13, 1), (25, 3), (51, 3), (63, 4), (99, 5), (101, 2), (255, 2),   # odd n: the last row in a pass of its own
-                                 (151, 3)])   # 3,624 B per design: filled the thread-group kernel's shared-memory budget to the byte
+                                 (151, 3),   # 3,624 B per design: filled the thread-group kernel's shared-memory budget to the byte
+                                 (100, 10), (128, 8), (200, 6), (256, 4), (90, 9), (101, 9), (40, 10), (16, 9)])   # four lanes per candidate; d = 9, 10
 def test_two_stage_search_general_shapes(n, d, metric, switches):
-    """The general screening kernel (any n from 8 to 256 with n d <= 908 and d <= 8; MaxPro from d = 2 up): the two-stage
+    """The general screening kernel (any n from 8 to 256 with n d up to ~1700 and d <= 10; MaxPro from d = 2 up): the two-stage
     search returns the winner, score bits and tie-break of the fp64-only search.  Shapes it does not serve (MaxPro at
     d = 1 here) take the fp64 kernel under every flag."""
     s_ref, i_ref = oracle.search_range(n, d, metric, 11, 0, 20_000)
