@@ -607,7 +607,15 @@ def main():
                                 "sample": f"{sample} candidates (n=50, d=3, MaxPro) in {dt:.1f} s, OpenMP over candidates, "
                                           f"{host_info()['cpu_model']}"}
     if not args.no_configs:
-        recs = run_configs(set(CONFIG_NAMES), rank, world, dev, peak_tflops, peak32_tflops, max_over_ranks, barrier)
+        # the headline line must survive a failing config: one config at a time, an error string in its place
+        recs = {}
+        for name in CONFIG_NAMES:
+            try:
+                recs.update(run_configs({name}, rank, world, dev, peak_tflops, peak32_tflops, max_over_ranks, barrier))
+            except Exception as exc:  # noqa: BLE001 -- reported, not swallowed
+                if world > 1:
+                    raise  # a rank that skips a collective would hang the others: fail loudly under torchrun
+                recs[name] = {"error": f"{type(exc).__name__}: {exc}"}
         line["configs"] = recs
     if rank == 0:
         emit(line)
