@@ -1,4 +1,5 @@
-// K1+K2 fused, TWO-STAGE search for the headline shapes (n = 50, d = 2 or 3; both metrics): an fp32 screening
+// K1+K2 fused, TWO-STAGE search for small designs, both metrics (a kernel specialised for the headline shapes n = 50,
+// d = 2 or 3, and a general one for any n from 8 to 256 with d up to 10 further down): an fp32 screening
 // pass with a PROVEN error bound, then the exact fp64 kernel on the survivors.  The result is the result of the
 // exact search -- same winner under the reference's fold (src/lib.rs:85-97, criterion after powf, later index on
 // ties), same score -- at about twice its rate.
@@ -12,8 +13,8 @@
 //            CTA; the threshold is wide enough that the true winner -- and every candidate whose criterion can
 //            tie with it -- is certain to be below it (the bound is derived below).  Survivors are appended to a
 //            list in HBM (8 bytes each; a few hundred per CTA for 2^28 candidates).
-//   stage 2  search_cyclic.cu in list mode regenerates the survivors, scores them in fp64 and folds them exactly
-//            as the full fp64 search would.  If the list overflows, stage 2 scores the whole range instead.
+//   stage 2  the fp64 kernel of the shape (search_cyclic.cu, search_small.cu, search_warp.cu) in list mode regenerates
+//            the survivors, scores them in fp64 and folds them exactly as the full fp64 search would.  If the list overflows, stage 2 scores the whole range instead.
 //
 // ---- fp32 arithmetic with exact differences ----------------------------------------------------------------
 // A coordinate of the design stream is x = (i + (jit + 1/2) 2^-32) / n.  Stage 1 keeps y = i 2^18 + (jit >> 14), an
