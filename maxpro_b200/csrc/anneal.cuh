@@ -28,6 +28,7 @@ struct AnnealParams {
     double* cur_global;         // anneal.cu, jitter moves on designs that fit shared memory only once: [grid][d][ns] scratch
     const double* rowmin0;      // anneal_maximin.cu: nearest-neighbour squared distance of every row of the start design
     const unsigned short* rowarg0;  //               and the neighbour that attains it
+    const double* qparams;      // anneal_maximin.cu, screened kernel: colmin[d], quantisation step s, 1/s, usable flag
 };
 
 // Per-CTA fold of the chains' global bests.  The chains of a launch are grid-strided over the CTAs, and the caller

@@ -511,7 +511,7 @@ int anneal_scratch(uint64_t n, uint64_t d, int metric, int swap, uint64_t n_chai
     CUDA_TRY(mp::anneal_plan_grid(L, sms, grid));
     const size_t nd = n * d;
     sc->design = nd * sizeof(double);
-    sc->raw = (2 * n + 2) * sizeof(double);  // raw0, then the nearest-neighbour table: n doubles, n 16-bit indices
+    sc->raw = (2 * n + 2 + d + 4) * sizeof(double);  // raw0, the nearest-neighbour table (n doubles, n 16-bit indices), d + 3 quantisation parameters
     sc->best = (size_t)*grid * 2 * nd * sizeof(double);
     sc->metrics = n_chains * sizeof(double);
     sc->improved = n_chains * sizeof(unsigned int);
@@ -548,6 +548,7 @@ int anneal_one(const double* design, uint64_t n, uint64_t d, uint64_t n_iteratio
     L.grid = grid; L.best_design = db.as<double>(); L.cta_chain = dcc.as<unsigned long long>(); L.cta_buf = dcb.as<int>();
     L.best_metric = dm.as<double>(); L.improved = di.as<unsigned int>(); L.raw0 = dr.as<double>(); L.stream = st;
     L.rowmin0 = dr.as<double>() + 1; L.rowarg0 = reinterpret_cast<unsigned short*>(dr.as<double>() + 1 + n);
+    L.qparams = dr.as<double>() + 2 * n + 2;
     L.cur_scratch = dcur.as<double>();
     CUDA_TRY(mp::launch_anneal(L));
     std::vector<double> metrics(n_chains);
