@@ -1145,10 +1145,16 @@ bool anneal_maximin_supported(unsigned long long n, unsigned long long d, int me
     return metric == 1 && swap != 0 && n >= 2 && n <= 65535 && d >= 1 && d <= 65535 && anneal_maximin_smem_bytes(n, d) <= kSmemBudget - kSmemSlack;
 }
 
-// the row pass screened on the 8-bit copy (default) or evaluated in full (MAXPRO_NO_ANNEAL_MAXIMIN_SCREEN=1, or no room for the copy)
+// The row pass screened on the 8-bit copy or evaluated in full.  The screened step replaces ~3 n d T FP64 operations by
+// ~n (d/4) T integer ones plus a fixed ~3,000 cycles of lists, barriers and exact items, so it pays on wide designs only
+// (one B200, 148 chains, us per step: (1000,20) 5.84 -> 4.27, (600,16) 4.37 -> 3.86, (500,20) 3.92 -> 3.54; (1000,10)
+// 4.29 -> 4.40, (300,33) 4.17 -> 4.10, (700,5) 3.3 -> 4.6, (200,4) 2.3 -> 3.5 -- tools/anneal_maximin_ab.py).  MAXPRO_ANNEAL_MAXIMIN_SCREEN=1 forces it on every
+// shape that has room for the copy (the parity tests do), =0 switches it off.
 static bool anneal_maximin_screened(unsigned long long n, unsigned long long d) {
+    if (d > 16384 || anneal_maximin_screen_smem_bytes(n, d) > kSmemBudget - kSmemSlack) return false;
     if (const char* e = cfg("MAXPRO_NO_ANNEAL_MAXIMIN_SCREEN")) if (atoi(e) != 0) return false;
-    return d <= 16384 && anneal_maximin_screen_smem_bytes(n, d) <= kSmemBudget - kSmemSlack;
+    if (const char* e = cfg("MAXPRO_ANNEAL_MAXIMIN_SCREEN")) return atoi(e) != 0;
+    return d >= 16 && n >= 500;
 }
 
 cudaError_t launch_anneal_maximin(const AnnealLaunch& L, int plan_sms, unsigned int* plan_grid) {

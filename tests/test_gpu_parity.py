@@ -372,6 +372,11 @@ def test_anneal_maximin_swap_incremental_matches_oracle(n, d, iters, minimize, s
     got, best, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
     assert np.array_equal(got, ref) and best == ref_best
     assert best == oracle.maximin_criterion(got)  # the returned design is the global best of the chain
+    for screen in ("1", "0"):  # the row pass screened on the 8-bit copy (default for wide designs) and evaluated in full
+        switches.set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", screen)
+        got1, best1, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
+        assert np.array_equal(got1, ref) and best1 == ref_best
+    switches.clear("MAXPRO_ANNEAL_MAXIMIN_SCREEN")
     switches.set("MAXPRO_NO_ANNEAL_MAXIMIN_INC", "1")
     got2, best2, _ = engine.anneal_lhd(x, iters, 0.05, 0.995, METRIC_MAXIMIN, minimize, 17, True, n_chains=1)
     assert np.array_equal(got2, ref) and best2 == ref_best
@@ -386,6 +391,53 @@ def test_anneal_maximin_swap_incremental_grid_design_and_chains(r_golden):
     ref_chain = [r[1] for r in refs].index(ref_best)
     assert chain == ref_chain and best == ref_best
     assert np.array_equal(got, refs[ref_chain][0])
+
+
+def _hard_design(kind, n, d, rng):
+    x = oracle.generate_lhd(n, d, 77)
+    if kind == "wide_column":      # one column 1e4 times wider than the others: the 8-bit copy resolves only that column
+        x[:, 0] *= 1.0e4
+    elif kind == "offset":         # far from the origin, outside the unit cube
+        x = x * 3.0 + 1.0e3
+    elif kind == "duplicates":     # few distinct values per column: exact ties and coincident points
+        x = np.floor(x * 4.0) / 4.0
+    elif kind == "clustered":      # all points within 1e-6 of each other in every column but one
+        x[:, 1:] = 0.5 + (x[:, 1:] - 0.5) * 1.0e-6
+    elif kind == "constant":       # a constant column and a two-valued one
+        x[:, 0] = 0.25
+        x[:, d - 1] = (np.arange(n) % 2) * 0.5
+    elif kind == "tiny":           # ranges of 1e-20
+        x = x * 1.0e-20
+    return np.ascontiguousarray(x)
+
+
+@pytest.mark.parametrize("kind", ["wide_column", "offset", "duplicates", "clustered", "constant", "tiny"])
+@pytest.mark.parametrize("n,d,iters,minimize", [(150, 6, 700, False), (64, 3, 900, True), (300, 20, 300, False)])
+def test_anneal_maximin_swap_screened_hard_designs(kind, n, d, iters, minimize, switches):
+    """The screened step (anneal_maximin.cu: integer distances on an 8-bit copy decide which distances are evaluated) must
+    follow the oracle on designs that quantise badly -- where its lists overflow it hands the step to the exact pass --
+    and the kernel with the exact row pass (MAXPRO_NO_ANNEAL_MAXIMIN_SCREEN=1) must agree."""
+    x = _hard_design(kind, n, d, np.random.default_rng(1))
+    ref, ref_best = oracle.anneal_lhd(x, iters, 0.05, 0.99, METRIC_MAXIMIN, minimize, 23, True)
+    switches.set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", "1")  # on every shape, not only the wide ones it is the default for
+    got, best, _ = engine.anneal_lhd(x, iters, 0.05, 0.99, METRIC_MAXIMIN, minimize, 23, True, n_chains=1)
+    assert np.array_equal(got, ref) and best == ref_best
+    switches.set("MAXPRO_NO_ANNEAL_MAXIMIN_SCREEN", "1")
+    got2, best2, _ = engine.anneal_lhd(x, iters, 0.05, 0.99, METRIC_MAXIMIN, minimize, 23, True, n_chains=1)
+    assert np.array_equal(got2, ref) and best2 == ref_best
+
+
+@pytest.mark.parametrize("threads", [32, 96, 160, 512])
+def test_anneal_maximin_swap_screened_thread_counts(threads, switches):
+    """Odd warp counts (the evaluating threads are the upper half of the block) and one warp for the whole chain."""
+    x = oracle.generate_lhd(220, 7, 5)
+    ref, ref_best = oracle.anneal_lhd(x, 600, 0.05, 0.99, METRIC_MAXIMIN, False, 3, True)
+    switches.set("MAXPRO_ANNEAL_THREADS", str(threads))
+    switches.set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", "1")
+    got, best, _ = engine.anneal_lhd(x, 600, 0.05, 0.99, METRIC_MAXIMIN, False, 3, True, n_chains=3)
+    refs = [oracle.anneal_lhd(x, 600, 0.05, 0.99, METRIC_MAXIMIN, False, 3 + c, True) for c in range(3)]
+    ref_best = max(r[1] for r in refs)
+    assert best == ref_best and np.array_equal(got, refs[[r[1] for r in refs].index(ref_best)][0])
 
 
 @pytest.mark.parametrize("n,d", [(4, 1), (5, 2), (7, 3), (33, 1), (51, 7), (97, 2)])

@@ -9,7 +9,6 @@ import oracle
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
-if len(sys.argv) > 4:
-    _lib.debug_set("MAXPRO_NO_ANNEAL_MAXIMIN_SCREEN", "1")
+_lib.debug_set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", "0" if len(sys.argv) > 4 else "1")
 x = oracle.generate_lhd(n, d, 42)
 print(engine.anneal_lhd(x, steps, 0.01, 0.99, METRIC_MAXIMIN, False, 43, True, n_chains=148)[1:])
