@@ -537,8 +537,11 @@ __device__ __forceinline__ int screen_row_pass(const unsigned int* qb, const uns
 #pragma unroll
                 for (int w = 0; w < DW; ++w) { c0 = __dp4a(x0[w], tw[w], c0); c1 = __dp4a(x1[w], tw[w], c1); }
                 const int v0 = nj0 - 2 * (int)c0, v1 = nj1 - 2 * (int)c1;
-                warp_push(ok0 && v0 <= thrm, (unsigned int)j0 | ((unsigned int)t << 16), wl, cnt, lane);
-                warp_push(ok1 && v1 <= thrm, (unsigned int)j1 | ((unsigned int)t << 16), wl, cnt, lane);
+                const bool p0 = ok0 && v0 <= thrm, p1 = ok1 && v1 <= thrm;
+                if (__any_sync(0xffffffffu, p0 || p1)) {
+                    warp_push(p0, (unsigned int)j0 | ((unsigned int)t << 16), wl, cnt, lane);
+                    warp_push(p1, (unsigned int)j1 | ((unsigned int)t << 16), wl, cnt, lane);
+                }
                 const unsigned int tn = t == 0 ? tn0 : tn1;
                 dmin0 = min(dmin0, (unsigned int)v0 + tn); dmin1 = min(dmin1, (unsigned int)v1 + tn);
             }
@@ -559,8 +562,10 @@ __device__ __forceinline__ int screen_row_pass(const unsigned int* qb, const uns
                 allmin = vb < allmin ? vb : allmin;
                 chk1 = dmin1 <= th;
             }
-            warp_push(chk0, (unsigned int)j0 | (kSlotCheck << 16), wl, cnt, lane);
-            warp_push(chk1, (unsigned int)j1 | (kSlotCheck << 16), wl, cnt, lane);
+            if (__any_sync(0xffffffffu, chk0 || chk1)) {
+                warp_push(chk0, (unsigned int)j0 | (kSlotCheck << 16), wl, cnt, lane);
+                warp_push(chk1, (unsigned int)j1 | (kSlotCheck << 16), wl, cnt, lane);
+            }
 #pragma unroll 1
             for (int t = 2; t < n_targets; ++t) {  // the dirty row meets itself here (D = 0): its item stands for its distances to the moved rows
                 unsigned int tw[DW > 0 ? DW : 1];
@@ -569,8 +574,11 @@ __device__ __forceinline__ int screen_row_pass(const unsigned int* qb, const uns
                 unsigned int c0 = 0u, c1 = 0u;
 #pragma unroll
                 for (int w = 0; w < DW; ++w) { c0 = __dp4a(x0[w], tw[w], c0); c1 = __dp4a(x1[w], tw[w], c1); }
-                warp_push(ok0 && nj0 - 2 * (int)c0 <= thrm, (unsigned int)j0 | ((unsigned int)t << 16), wl, cnt, lane);
-                warp_push(ok1 && nj1 - 2 * (int)c1 <= thrm, (unsigned int)j1 | ((unsigned int)t << 16), wl, cnt, lane);
+                const bool p0 = ok0 && nj0 - 2 * (int)c0 <= thrm, p1 = ok1 && nj1 - 2 * (int)c1 <= thrm;
+                if (__any_sync(0xffffffffu, p0 || p1)) {
+                    warp_push(p0, (unsigned int)j0 | ((unsigned int)t << 16), wl, cnt, lane);
+                    warp_push(p1, (unsigned int)j1 | ((unsigned int)t << 16), wl, cnt, lane);
+                }
             }
         }
     } else {
@@ -841,7 +849,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_screen_kernel(AnnealParams
                 AMX_T(1)
                 const int nd_rows = dirty_n[0];
                 if (warp == last_warp) {
-                    // the pair (r1, r2) itself: its squares summed in the reference's order
+                    // the pair (r1, r2) itself: its squares summed in the reference's order (the last warp has the fewest rows)
                     double s12 = sqk[0];
 #pragma unroll 4
                     for (int k = 1; k < d; ++k) s12 = __dadd_rn(s12, sqk[k]);
@@ -859,62 +867,58 @@ __global__ void __launch_bounds__(512) anneal_maximin_screen_kernel(AnnealParams
                     unsigned long long allmin = kInfBits;
                     const int cnt = screen_row_pass<DW>(qb, nrm, tqw, n, dw, dwp, ns, r1, r2, 2 + nd_rows, tgt, tnrm[0], tnrm[1], rm, ra, tq, rm_new, ra_new, tq_new,
                                                         items + warp * kWarpItems, allmin);
-                    {   // block minimum of the clean rows' old minima (two REDUX.MIN on the bit pattern)
-                        const unsigned int hi = (unsigned int)(allmin >> 32), lo = (unsigned int)allmin;
-                        const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
-                        const unsigned int mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
-                        if (lane == 0) {
-                            wmin[warp] = ((unsigned long long)mhi << 32) | mlo;
-                            wcnt[warp] = cnt;
-                            if (cnt > kWarpItems) wcnt[16] = 1;
+                    // ---- the distances this warp listed, in full and at once (no barrier: the list is the warp's own): two lanes per
+                    //      item -- a clean row's item (and a dirty row meeting itself) stands for the distances to BOTH moved rows,
+                    //      one each; every other item is one distance (the odd lane idles).  One code path for all items.
+                    __syncwarp();
+                    {
+                        const int e = warp * kWarpItems + (lane >> 1), h = lane & 1;
+                        const bool live = (lane >> 1) < min(cnt, kWarpItems);
+                        const unsigned int it = live ? items[e] : 0xFFFFFFFFu;
+                        const int j = (int)(it & 0xFFFFu);
+                        const unsigned int sl = it >> 16;
+                        const int trow = live && sl >= 2u && sl != kSlotCheck ? dirty[sl - 2u] : -1;
+                        const bool both = live && (sl == kSlotCheck || trow == j);
+                        double v = CUDART_INF;
+                        if (live && (both || h == 0)) {
+                            const bool mv = both || sl < 2u;  // against a moved row (staged) or against a dirty row (in place)
+                            const double* a = mv ? rowsx + (both ? (unsigned int)h : sl) : cur + trow;
+                            v = sqdist_chain(a, mv ? 2 : ns, cur, ns, j, d);
                         }
+                        const double vo = __shfl_xor_sync(0xffffffffu, v, 1);
+                        {   // the warp's share of the step's criterion: its clean rows' old minima and every distance it evaluated
+                            const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+                            const unsigned long long m = vb < allmin ? vb : allmin;
+                            const unsigned int hi = (unsigned int)(m >> 32), lo = (unsigned int)m;
+                            const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
+                            const unsigned int mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+                            if (lane == 0) {
+                                wmin[warp] = ((unsigned long long)mhi << 32) | mlo;
+                                if (cnt > kWarpItems) wcnt[16] = 1;
+                            }
+                        }
+                        if (h == 0 && lane < 2 * kWarpItems) {
+                            const double vm = both && vo < v ? vo : v;
+                            const int arg = both ? (vo < v ? r2 : r1) : j;
+                            if (live && sl == kSlotCheck) {  // the only item of its row: decided here
+                                if (vm < rm[j]) { rm_new[j] = vm; ra_new[j] = (unsigned short)arg; tq_new[j] = screen_threshold(vm, inv_s_f, K_f); }
+                            } else if (live) {
+                                iarg[e] = (unsigned short)arg;
+                            } else {
+                                items[e] = 0xFFFFFFFFu;
+                            }
+                            ival[e] = vm;
+                        }
+#if AMX_PROFILE
+                        if (lane == 0) wcnt[warp] = cnt;
+#endif
                     }
                     AMX_T(2)
                     __syncthreads();
                     AMX_T(3)
                     exact = wcnt[16] != 0;
                     if (!exact) {
-                        // ---- the listed (row, target) distances in full: two threads per list slot, from the last thread down -- a
-                        //      clean row's item (and a dirty row meeting itself) stands for the distances to BOTH moved rows, one each;
-                        //      every other item is one distance (the odd thread idles).  One code path for all: the evaluating warps
-                        //      run it once.
-                        const int q = (int)blockDim.x - 1 - (int)threadIdx.x, e = q >> 1, h = q & 1;
-                        if ((q >> 5) < ((nwarps + 1) >> 1)) {  // the warps that hold the 2 * n_slots evaluating threads (whole warps: they vote)
-                            const bool live = e < n_slots && (e & (kWarpItems - 1)) < wcnt[e / kWarpItems];
-                            const unsigned int it = live ? items[e] : 0xFFFFFFFFu;
-                            const int j = (int)(it & 0xFFFFu);
-                            const unsigned int sl = it >> 16;
-                            const int trow = live && sl >= 2u && sl != kSlotCheck ? dirty[sl - 2u] : -1;
-                            const bool both = live && (sl == kSlotCheck || trow == j);
-                            double v = CUDART_INF;
-                            if (live && (both || h == 0)) {
-                                const bool mv = both || sl < 2u;  // against a moved row (staged) or against a dirty row (in place)
-                                const double* a = mv ? rowsx + (both ? (unsigned int)h : sl) : cur + trow;
-                                v = sqdist_chain(a, mv ? 2 : ns, cur, ns, j, d);
-                            }
-                            const double vo = __shfl_xor_sync(0xffffffffu, v, 1);
-                            {   // this warp's smallest distance, for the step's criterion
-                                const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
-                                const unsigned int hi = (unsigned int)(vb >> 32), lo = (unsigned int)vb;
-                                const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
-                                const unsigned int mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
-                                if (lane == 31) emin[last_warp - warp] = ((unsigned long long)mhi << 32) | mlo;
-                            }
-                            if (h == 0) {
-                                const double vm = both && vo < v ? vo : v;
-                                const int arg = both ? (vo < v ? r2 : r1) : j;
-                                if (live && sl == kSlotCheck) {  // the only item of its row: decided here
-                                    if (vm < rm[j]) { rm_new[j] = vm; ra_new[j] = (unsigned short)arg; tq_new[j] = screen_threshold(vm, inv_s_f, K_f); }
-                                } else if (live) {
-                                    iarg[e] = (unsigned short)arg;
-                                } else if (e < n_slots) {
-                                    items[e] = 0xFFFFFFFFu;
-                                }
-                                if (e < n_slots) ival[e] = vm;
-                            }
-                        }
                         AMX_T(4)
-                        __syncthreads();
                         AMX_T(5)
                         d12 = sqk[d];
                         if (warp == 0) {
