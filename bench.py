@@ -314,7 +314,10 @@ def run_configs(which, rank, world, dev, peak_tflops, peak32_tflops, max_over_ra
                              "check": {"never worse than the input (anneal.rs:92-94,142)": bool(never_worse),
                                        "returned design re-scored by the CPU oracle": bool(abs(rescored - best) <= 1e-9 * abs(best))},
                              "roofline": roof(rate, 4 * (n - 2) * per_pair,
-                                              "incremental step: the 2(n-2) pairs of the two swapped rows, old and new")}
+                                              "incremental step: the 2(n-2) pairs of the two swapped rows, old and new"
+                                              + ("; the kernel screens these pairs on an 8-bit copy of the design (IDP.4A) and evaluates "
+                                                 "in fp64 only the ~14 per step that can attain a minimum, so the FP64 pipe is ~10 % busy (ncu) -- "
+                                                 "the figure is the exact step's work per second, not pipe utilisation" if metric == METRIC_MAXIMIN else ""))}
         if rank == 0:
             rec["value"] = rec["maximin"]["value"]
             rec["roofline"] = rec["maximin"]["roofline"]
