@@ -71,14 +71,16 @@ __device__ __forceinline__ void cta_walk_columns(double* xs, const unsigned shor
     for (int k = first; k < d; k += step) fy_walk_column(xs + k * ns, jst + k * ns, n);
 }
 
-template <bool MAXPRO>
-__global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p) {
+// THREADS: 128 while four CTAs fit one SM; a design that leaves room for two (one) CTAs gets 256 (512) threads -- the same
+// 16 warps per SM: one CTA of four warps is one warp per sub-partition, and that does not fill the FP64 pipe.
+template <bool MAXPRO, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) search_cta_kernel(CtaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, d = p.d, ns = p.ns;
     double* xs = reinterpret_cast<double*>(smem_raw);                         // [d][ns]
     unsigned short* jst = reinterpret_cast<unsigned short*>(xs + (size_t)d * ns);  // [d][ns]
-    double* red = reinterpret_cast<double*>(smem_raw + (((size_t)d * ns * 10 + 15) / 16) * 16);  // [4] warp partials
-    __shared__ BestRec warp_best[4];
+    double* red = reinterpret_cast<double*>(smem_raw + (((size_t)d * ns * 10 + 15) / 16) * 16);  // [THREADS / 32] warp partials
+    __shared__ BestRec warp_best[THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles = (n + kTileRows - 1) / kTileRows;
     const int chunk = cta_dim_chunk(d);
@@ -90,9 +92,9 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         __syncthreads();  // previous candidate fully consumed
-        cta_stage_candidate(p.gen, xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, kCtaThreads);
+        cta_stage_candidate(p.gen, xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, THREADS);
         __syncthreads();
-        cta_walk_columns(xs, jst, n, d, ns, tid, kCtaThreads);
+        cta_walk_columns(xs, jst, n, d, ns, tid, THREADS);
         __syncthreads();
 
         // ---- scoring: items (row tile, column block) dealt round-robin to the warps
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
             while (t < tiles && jb >= nblk) { jb -= nblk; ++t; nblk = (n - t * kTileRows + kJB - 1) / kJB; }
             if (t >= tiles) break;
             cta_score_item_any<MAXPRO>(chunk, xs, n, d, ns, t * kTileRows, t * kTileRows + jb * kJB, lane, st);
-            jb += kCtaThreads / 32;
+            jb += THREADS / 32;
         }
         if (MAXPRO) st.flush();
         const double acc = st.acc, mn = st.mn;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) search_cta_kernel(CtaParams p)
         if (tid == 0) {
             double s = red[0];
 #pragma unroll
-            for (int w = 1; w < 4; ++w) s = MAXPRO ? s + red[w] : fmin(s, red[w]);
+            for (int w = 1; w < THREADS / 32; ++w) s = MAXPRO ? s + red[w] : fmin(s, red[w]);
             if (!MAXPRO) s = sqrt(s);
             lb.offer(s, idx, p.n_pairs, p.inv_d);
         }
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
 
 static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) {
     unsigned long long ns = cta_row_stride(n);
-    return (size_t)(((d * ns * 10 + 15) / 16) * 16 + 4 * sizeof(double));
+    return (size_t)(((d * ns * 10 + 15) / 16) * 16 + 16 * sizeof(double));
 }
 
 static size_t cta_pipe_smem_bytes(unsigned long long n, unsigned long long d) {
@@ -219,6 +221,17 @@ static bool cta_use_pipe(unsigned long long n, unsigned long long d) {
     return 2 * (cta_pipe_smem_bytes(n, d) + 2048) <= kSmemBudget;
 }
 
+// CTAs of the single-buffer kernel per SM: 4 x 128 threads, 2 x 256 or 1 x 512 (MAXPRO_CTA_THREADS forces a block size)
+static int cta_per_sm(unsigned long long n, unsigned long long d) {
+    int per_sm = (int)(kSmemBudget / (cta_smem_bytes(n, d) + 1024));
+    per_sm = per_sm >= 4 ? 4 : (per_sm >= 2 ? 2 : 1);
+    if (const char* e = cfg("MAXPRO_CTA_THREADS")) {
+        const int t = atoi(e);
+        if ((t == 128 || t == 256 || t == 512) && 512 / t <= per_sm) per_sm = 512 / t;
+    }
+    return per_sm;
+}
+
 bool search_cta_supported(unsigned long long n, unsigned long long d) {
     return n >= 2 && n <= 65535 && d >= 1 && cta_smem_bytes(n, d) + 256 <= kSmemBudget;  // 256: static shared memory
 }
@@ -230,11 +243,7 @@ int search_cta_grid(unsigned long long n, unsigned long long d, int sms) {
         if (per_sm < 1) per_sm = 1;
         return sms * per_sm;
     }
-    size_t smem = cta_smem_bytes(n, d) + 1024;
-    int per_sm = (int)(kSmemBudget / smem);
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
-    return sms * per_sm;
+    return sms * cta_per_sm(n, d);
 }
 
 cudaError_t launch_search_cta(const SearchLaunch& L) {
@@ -261,16 +270,20 @@ cudaError_t launch_search_cta(const SearchLaunch& L) {
         }
         return cudaGetLastError();
     }
-    size_t smem = cta_smem_bytes(L.n, L.d);
+    const size_t smem = cta_smem_bytes(L.n, L.d);
+    const int per_sm = cta_per_sm(L.n, L.d);
+    e = cudaSuccess;
+    auto go = [&](auto kernel, int threads) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return;
+        kernel<<<L.grid, threads, smem, L.stream>>>(p);
+    };
     if (L.metric == 0) {
-        e = cudaFuncSetAttribute(search_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        search_cta_kernel<true><<<L.grid, kCtaThreads, smem, L.stream>>>(p);
+        if (per_sm >= 4) go(search_cta_kernel<true, 128>, 128); else if (per_sm == 2) go(search_cta_kernel<true, 256>, 256); else go(search_cta_kernel<true, 512>, 512);
     } else {
-        e = cudaFuncSetAttribute(search_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        search_cta_kernel<false><<<L.grid, kCtaThreads, smem, L.stream>>>(p);
+        if (per_sm >= 4) go(search_cta_kernel<false, 128>, 128); else if (per_sm == 2) go(search_cta_kernel<false, 256>, 256); else go(search_cta_kernel<false, 512>, 512);
     }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
