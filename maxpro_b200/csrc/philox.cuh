@@ -180,6 +180,38 @@ __device__ __forceinline__ void fy_walk_column(double* a, const unsigned short* 
     }
 }
 
+#ifdef __CUDACC__
+// The same walk for the v2 stream with nothing staged: the walking lane draws index and value of the next eight steps
+// itself (lhd2_element + lhd2_value, independent of the chain) and then does the eight dependent steps.
+__device__ __forceinline__ void fy_walk_column_v2(double* a, uint32_t ka, uint32_t kb, int n, double c1, double c0p) {
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint32_t j[8];
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            uint32_t jit;
+            lhd2_element(ka, kb, (uint32_t)(i + u), j[u], jit);
+            v[u] = lhd2_value((uint32_t)(i + u), jit, c1, c0p);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double t = a[j[u]];  // j <= i + u: when j == i + u the value read is unspecified and overwritten below
+            a[i + u] = t;
+            a[j[u]] = v[u];
+        }
+    }
+    for (; i < n; ++i) {
+        uint32_t j, jit;
+        lhd2_element(ka, kb, (uint32_t)i, j, jit);
+        const double v = lhd2_value((uint32_t)i, jit, c1, c0p);
+        const double t = a[j];
+        a[i] = t;
+        a[j] = v;
+    }
+}
+#endif
+
 // (w * bound) >> 32 : multiply-shift map of a 32-bit word onto [0, bound).
 __host__ __device__ __forceinline__ uint32_t mulhi_bound(uint32_t w, uint32_t bound) {
     return (uint32_t)(((uint64_t)w * (uint64_t)bound) >> 32);

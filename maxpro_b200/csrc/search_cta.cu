@@ -24,6 +24,7 @@
 #include "tile_score.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace mp {
 
@@ -73,13 +74,16 @@ __device__ __forceinline__ void cta_walk_columns(double* xs, const unsigned shor
 
 // THREADS: 128 while four CTAs fit one SM; a design that leaves room for two (one) CTAs gets 256 (512) threads -- the same
 // 16 warps per SM: one CTA of four warps is one warp per sub-partition, and that does not fill the FP64 pipe.
-template <bool MAXPRO, int THREADS>
+// COMPACT (stream v2 only): no side array -- the lane that walks a column draws index and value of every step itself (a
+// handful of integer operations and one DFMA per step, hidden behind the walk's dependent shared-memory round trip), so a
+// design takes 8 bytes per element instead of 10 and designs up to 227 KB stay on this kernel instead of going through HBM.
+template <bool MAXPRO, int THREADS, bool COMPACT>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS) search_cta_kernel(CtaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, d = p.d, ns = p.ns;
     double* xs = reinterpret_cast<double*>(smem_raw);                         // [d][ns]
-    unsigned short* jst = reinterpret_cast<unsigned short*>(xs + (size_t)d * ns);  // [d][ns]
-    double* red = reinterpret_cast<double*>(smem_raw + (((size_t)d * ns * 10 + 15) / 16) * 16);  // [THREADS / 32] warp partials
+    unsigned short* jst = reinterpret_cast<unsigned short*>(xs + (size_t)d * ns);  // [d][ns] (not COMPACT)
+    double* red = reinterpret_cast<double*>(smem_raw + (((size_t)d * ns * (COMPACT ? 8 : 10) + 15) / 16) * 16);  // [THREADS / 32] warp partials
     __shared__ BestRec warp_best[THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles = (n + kTileRows - 1) / kTileRows;
@@ -92,9 +96,17 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) search_cta_kernel(CtaP
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
         const uint32_t s_lo = (uint32_t)stream, s_hi = (uint32_t)(stream >> 32);
         __syncthreads();  // previous candidate fully consumed
-        cta_stage_candidate(p.gen, xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, THREADS);
-        __syncthreads();
-        cta_walk_columns(xs, jst, n, d, ns, tid, THREADS);
+        if (COMPACT) {
+            for (int k = tid; k < d; k += THREADS) {
+                uint32_t ka, kb;
+                lhd2_column_key((uint32_t)k, s_lo, s_hi, ka, kb);
+                fy_walk_column_v2(xs + k * ns, ka, kb, n, p.c1, p.c0);
+            }
+        } else {
+            cta_stage_candidate(p.gen, xs, jst, n, d, ns, s_lo, s_hi, p.c1, p.c0, tid, THREADS);
+            __syncthreads();
+            cta_walk_columns(xs, jst, n, d, ns, tid, THREADS);
+        }
         __syncthreads();
 
         // ---- scoring: items (row tile, column block) dealt round-robin to the warps
@@ -204,10 +216,17 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
     block_publish_best<MAXPRO>(lb.best, lb.idx, warp_best, p.block_best, p.done_counter, p.result);
 }
 
-static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) {
+static size_t cta_smem_bytes_layout(unsigned long long n, unsigned long long d, bool compact) {
     unsigned long long ns = cta_row_stride(n);
-    return (size_t)(((d * ns * 10 + 15) / 16) * 16 + 16 * sizeof(double));
+    return (size_t)(((d * ns * (compact ? 8 : 10) + 15) / 16) * 16 + 16 * sizeof(double));
 }
+// the compact layout (stream v2) takes over where the design no longer fits beside its side array
+static bool cta_compact(unsigned long long n, unsigned long long d) {
+    if (stream_version() != 2) return false;
+    if (const char* e = cfg("MAXPRO_CTA_COMPACT")) return atoi(e) != 0;
+    return cta_smem_bytes_layout(n, d, false) + 256 > kSmemBudget;
+}
+static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) { return cta_smem_bytes_layout(n, d, cta_compact(n, d)); }
 
 static size_t cta_pipe_smem_bytes(unsigned long long n, unsigned long long d) {
     unsigned long long ns = cta_row_stride(n);
@@ -278,11 +297,15 @@ cudaError_t launch_search_cta(const SearchLaunch& L) {
         if (e != cudaSuccess) return;
         kernel<<<L.grid, threads, smem, L.stream>>>(p);
     };
-    if (L.metric == 0) {
-        if (per_sm >= 4) go(search_cta_kernel<true, 128>, 128); else if (per_sm == 2) go(search_cta_kernel<true, 256>, 256); else go(search_cta_kernel<true, 512>, 512);
-    } else {
-        if (per_sm >= 4) go(search_cta_kernel<false, 128>, 128); else if (per_sm == 2) go(search_cta_kernel<false, 256>, 256); else go(search_cta_kernel<false, 512>, 512);
-    }
+    auto pick = [&](auto mp_tag, auto compact_tag) {
+        constexpr bool MP = decltype(mp_tag)::value, CP = decltype(compact_tag)::value;
+        if (per_sm >= 4) go(search_cta_kernel<MP, 128, CP>, 128);
+        else if (per_sm == 2) go(search_cta_kernel<MP, 256, CP>, 256);
+        else go(search_cta_kernel<MP, 512, CP>, 512);
+    };
+    const bool compact = cta_compact(L.n, L.d);
+    if (L.metric == 0) { if (compact) pick(std::true_type{}, std::true_type{}); else pick(std::true_type{}, std::false_type{}); }
+    else { if (compact) pick(std::false_type{}, std::true_type{}); else pick(std::false_type{}, std::false_type{}); }
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -232,6 +232,36 @@ def test_search_cta_single_and_double_buffered(n, d, iters, pipe, switches):
         assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
 
 
+@pytest.mark.parametrize("threads", ["128", "256", "512"])
+@pytest.mark.parametrize("n,d,iters", [(500, 10, 1500), (66, 7, 2000), (9, 33, 700), (130, 20, 900), (257, 3, 1500)])
+def test_search_cta_compact_layout_and_block_sizes(n, d, iters, threads, switches):
+    """The single-buffer CTA kernel without its side array (MAXPRO_CTA_COMPACT=1: the walking lane draws index and value
+    of every Fisher-Yates step itself -- the layout designs between 182 and 227 KB take by default) and at every block
+    size (128 threads while four CTAs fit an SM, 256 / 512 when only two / one do): the oracle's winner."""
+    switches.set("MAXPRO_NO_WARP", "1")
+    switches.set("MAXPRO_CTA_PIPE", "0")
+    switches.set("MAXPRO_CTA_THREADS", threads)
+    seed = 13
+    for compact in ("1", "0"):
+        switches.set("MAXPRO_CTA_COMPACT", compact)
+        for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+            s_ref, i_ref = oracle.search_range(n, d, metric, seed, 3, 3 + iters)
+            s, i = engine.search_range(n, d, metric, seed, 3, 3 + iters)
+            assert i == i_ref
+            assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+
+
+def test_search_cta_compact_is_the_default_for_designs_that_fill_shared_memory():
+    """n=5000, d=5 is 200 KB of coordinates: with its 16-bit side array it would not fit one SM and went through HBM chunks."""
+    n, d, seed = 5000, 5, 21
+    for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
+        s_ref, i_ref = oracle.search_range(n, d, metric, seed, 0, 300)
+        design, s, i = engine.build_lhd(n, d, 300, metric, seed)
+        assert i == i_ref
+        assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+        assert np.array_equal(design, oracle.generate_lhd(n, d, seed + i))
+
+
 @pytest.mark.parametrize("n,d", [(100, 5), (128, 8), (150, 3), (200, 4), (31, 9), (64, 9), (101, 10)])
 @pytest.mark.parametrize("metric", [METRIC_MAXPRO, METRIC_MAXIMIN])
 def test_search_warp_path_winner(n, d, metric):
