@@ -141,6 +141,15 @@ __device__ __forceinline__ void maximin_row_pass(const double* cur, const double
     }
 }
 
+// minimum of the per-warp slots of one block minimum (bit patterns of non-negative doubles): a load per lane, two REDUX.MIN
+__device__ __forceinline__ unsigned long long block_min_bits(const unsigned long long* slots, int nwarps, int lane) {
+    const unsigned long long m = lane < nwarps ? slots[lane] : 0x7FF0000000000000ull;
+    const unsigned int hi = (unsigned int)(m >> 32), lo = (unsigned int)m;
+    const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned int mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
 __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p) {
     extern __shared__ __align__(16) double smem_d[];
     const int n = (int)p.n, d = (int)p.d, nd = n * d;
@@ -150,8 +159,9 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
     double* rmin0 = cur + dns;                                // [2][ns]: committed / tentative row minima
     double* rowsx = rmin0 + 2 * ns;                           // [d][2]: the two moved rows AFTER the move
     double* sqk = rowsx + 2 * d;                              // [d] squared differences of the pair (r1, r2), then [d] = their sum
-    unsigned long long* lmin = reinterpret_cast<unsigned long long*>(sqk + d + 1);  // [3 + kMaxDirty] block minima (bit patterns)
-    Decision* dec = reinterpret_cast<Decision*>(lmin + 3 + kMaxDirty);
+    // per-warp minima (bit patterns), [slot][16 warps]: slot 0 clean rows, 1 row r1, 2 row r2, 3 + q dirty row q of the chunk
+    unsigned long long* lmin = reinterpret_cast<unsigned long long*>(sqk + d + 1);  // [3 + kMaxDirty][16]
+    Decision* dec = reinterpret_cast<Decision*>(lmin + (3 + kMaxDirty) * 16);
     int* dirty_n = reinterpret_cast<int*>(dec + 1);           // dirty_n[0] = count, then the list
     int* dirty = dirty_n + 1;                                 // [n] worst case
     // aligned on the OFFSET: a pointer that went through an integer loses its address space, and everything behind it
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
     uint4* draws = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(smem_d) + draws_off);
     ushort4* mlog = reinterpret_cast<ushort4*>(draws + kDrawBatch);
     unsigned short* rarg0 = reinterpret_cast<unsigned short*>(mlog + kLogCap);  // [2][ns] their arguments
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)blockDim.x >> 5;
 
     __shared__ CtaBest cta_best;  // per-CTA fold of the chains' global bests (anneal.cuh)
     if (threadIdx.x == 0) cta_best_reset(&cta_best, p);
@@ -200,25 +210,24 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                 for (int q = threadIdx.x; q < kDrawBatch; q += blockDim.x) {
                     const unsigned long long tq = t + (unsigned long long)q;
                     const Philox4 w = philox4x32_10((uint32_t)tq, (uint32_t)(tq >> 32), 0u, kDomainSwap, key0, key1);
-                    draws[q] = make_uint4(w.x, w.y, w.z, w.w);
+                    // decoded once for all threads and steps of the batch -- anneal.rs:29-31: r1, r2, c; the accept draw stays raw
+                    draws[q] = make_uint4(mulhi_bound(w.x, (uint32_t)n), mulhi_bound(w.y, (uint32_t)n), mulhi_bound(w.z, (uint32_t)d), w.w);
                 }
                 __syncthreads();
             }
             const uint4 w = draws[slot];
-            const int r1 = (int)mulhi_bound(w.x, (uint32_t)n);  // anneal.rs:29
-            const int r2 = (int)mulhi_bound(w.y, (uint32_t)n);  // :30
-            const int c = (int)mulhi_bound(w.z, (uint32_t)d);   // :31
-            const double u = (double)w.w * 0x1p-32;
+            const int r1 = (int)w.x, r2 = (int)w.y, c = (int)w.z;
             const double* rm = rmin0 + sel * ns;
             const unsigned short* ra = rarg0 + sel * ns;
             double* rm_new = rmin0 + (sel ^ 1) * ns;
             unsigned short* ra_new = rarg0 + (sel ^ 1) * ns;
             const bool moved = r1 != r2;
 
-            // Block minima go through 64-bit atomicMin on the bit patterns (squared distances are >= +0,
-            // so the integer order is the numeric order): lmin[0] clean rows, [1] row r1, [2] row r2,
-            // [3 + q] the dirty rows of the current chunk.  Who attains a minimum is written afterwards
-            // by every warp whose partial equals it -- the decision needs the values only.
+            // Block minima on the bit patterns (squared distances are >= +0, so the integer order is the numeric
+            // order): every warp leaves its minimum in its own slot, and after the barrier every warp folds the (at most 16)
+            // slots of a minimum with two REDUX.MIN -- a 64-bit atomicMin on shared memory is a compare-and-swap loop
+            // (ATOMS.CAST.SPIN), 3 + dirty of them per warp on the same few addresses.  Who attains a minimum is written
+            // afterwards by every warp whose partial equals it -- the decision needs the values only.
             constexpr unsigned long long kInfBits = 0x7FF0000000000000ull;
             AMX_T(0)
             double fin_all = CUDART_INF, g1 = CUDART_INF, g2 = CUDART_INF, d12 = CUDART_INF;
@@ -236,7 +245,6 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                     const int a = ra[i];
                     if (i != r1 && i != r2 && (a == r1 || a == r2)) dirty[atomicAdd(dirty_n, 1)] = i;  // dirty_n was zeroed before the last barrier
                 }
-                if (threadIdx.x < 3 + kMaxDirty) lmin[threadIdx.x] = kInfBits;
                 __syncthreads();
                 AMX_T(1)
                 const int nd_rows = dirty_n[0];
@@ -252,11 +260,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                 MinArg all{CUDART_INF, 0}, m1{CUDART_INF, 0}, m2{CUDART_INF, 0};
                 for (int base = 0; base == 0 || base < nd_rows; base += kMaxDirty) {
                     const int cnt = min(kMaxDirty, nd_rows - base);
-                    if (base != 0) {  // more than kMaxDirty dirty rows: the previous chunk's minima have been read
-                        __syncthreads();
-                        if (threadIdx.x < kMaxDirty) lmin[3 + threadIdx.x] = kInfBits;
-                        __syncthreads();
-                    }
+                    if (base != 0) __syncthreads();  // more than kMaxDirty dirty rows: the previous chunk's minima have been read
                     MinArg dm[kMaxDirty];
 #pragma unroll
                     for (int q = 0; q < kMaxDirty; ++q) dm[q] = MinArg{CUDART_INF, 0};
@@ -278,16 +282,16 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                     if (first) {
                         all = warp_minarg(all); m1 = warp_minarg(m1); m2 = warp_minarg(m2);
                         if (lane == 0) {
-                            atomicMin(&lmin[0], (unsigned long long)__double_as_longlong(all.v));
-                            atomicMin(&lmin[1], (unsigned long long)__double_as_longlong(m1.v));
-                            atomicMin(&lmin[2], (unsigned long long)__double_as_longlong(m2.v));
+                            lmin[0 * 16 + warp] = (unsigned long long)__double_as_longlong(all.v);
+                            lmin[1 * 16 + warp] = (unsigned long long)__double_as_longlong(m1.v);
+                            lmin[2 * 16 + warp] = (unsigned long long)__double_as_longlong(m2.v);
                         }
                     }
 #pragma unroll
                     for (int q = 0; q < kMaxDirty; ++q) {
                         if (q < cnt) {
                             dm[q] = warp_minarg(dm[q]);
-                            if (lane == 0) atomicMin(&lmin[3 + q], (unsigned long long)__double_as_longlong(dm[q].v));
+                            if (lane == 0) lmin[(3 + q) * 16 + warp] = (unsigned long long)__double_as_longlong(dm[q].v);
                         }
                     }
                     AMX_T(3)
@@ -297,16 +301,16 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
 #pragma unroll
                     for (int q = 0; q < kMaxDirty; ++q) {
                         if (q < cnt) {
-                            const unsigned long long g = lmin[3 + q];
+                            const unsigned long long g = block_min_bits(lmin + (3 + q) * 16, nwarps, lane);
                             if (lane == 0 && (unsigned long long)__double_as_longlong(dm[q].v) == g) { rm_new[di[q]] = dm[q].v; ra_new[di[q]] = (unsigned short)dm[q].a; }
                             fin_all = fmin(fin_all, __longlong_as_double((long long)g));
                         }
                     }
                 }
                 // rows r1 and r2: the minimum over the other rows and the pair (r1, r2) itself
-                fin_all = fmin(fin_all, __longlong_as_double((long long)lmin[0]));
-                g1 = __longlong_as_double((long long)lmin[1]);
-                g2 = __longlong_as_double((long long)lmin[2]);
+                fin_all = fmin(fin_all, __longlong_as_double((long long)block_min_bits(lmin + 0 * 16, nwarps, lane)));
+                g1 = __longlong_as_double((long long)block_min_bits(lmin + 1 * 16, nwarps, lane));
+                g2 = __longlong_as_double((long long)block_min_bits(lmin + 2 * 16, nwarps, lane));
                 d12 = sqk[d];
                 if (lane == 0) {
                     if (!(d12 < g1) && m1.v == g1) ra_new[r1] = (unsigned short)m1.a;
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
                     new_metric = cur_metric;
                     accept = temp != 0.0;
                 } else {
+                    const double u = (double)w.w * 0x1p-32;  // anneal.rs:125
                     new_metric = sqrt(raw_new);
                     double diff = new_metric - cur_metric;
                     if (!p.minimize) diff *= -1.0;
@@ -1126,7 +1131,7 @@ __global__ void __launch_bounds__(256) anneal_rowmin0_kernel(const double* desig
 
 size_t anneal_maximin_smem_bytes(unsigned long long n, unsigned long long d) {
     const unsigned long long ns = (n + 1) & ~1ull;
-    size_t b = (size_t)(ns * d + 2 * ns + 2 * d + d + 1 + 3 + kMaxDirty) * sizeof(double);  // cur, rmin x2, rowsx, sqk, lmin
+    size_t b = (size_t)(ns * d + 2 * ns + 2 * d + d + 1 + (3 + kMaxDirty) * 16) * sizeof(double);  // cur, rmin x2, rowsx, sqk, lmin
     b += sizeof(Decision) + (size_t)(1 + n) * sizeof(int) + 16;      // dec, dirty list, alignment slack
     b += (size_t)kDrawBatch * sizeof(uint4) + (size_t)kLogCap * sizeof(ushort4);
     b += (size_t)2 * ns * sizeof(unsigned short);
