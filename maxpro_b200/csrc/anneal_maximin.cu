@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(512) anneal_maximin_swap_kernel(AnnealParams p
             // slots of a minimum with two REDUX.MIN -- a 64-bit atomicMin on shared memory is a compare-and-swap loop
             // (ATOMS.CAST.SPIN), 3 + dirty of them per warp on the same few addresses.  Who attains a minimum is written
             // afterwards by every warp whose partial equals it -- the decision needs the values only.
-            constexpr unsigned long long kInfBits = 0x7FF0000000000000ull;
             AMX_T(0)
             double fin_all = CUDART_INF, g1 = CUDART_INF, g2 = CUDART_INF, d12 = CUDART_INF;
             if (moved) {

@@ -28,7 +28,6 @@
 
 namespace mp {
 
-constexpr int kCtaThreads = 128;
 struct CtaParams {
     int gen;       // design stream version (philox.cuh)
     int n, d, ns;  // ns = row stride of the [k][i] layout (cta_row_stride)
