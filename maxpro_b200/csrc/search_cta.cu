@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) search_cta_kernel(CtaP
 // the four warps at a barrier (16% of all warp samples at n = 500, d = 10).
 constexpr int kPipeThreads = 256;
 
-template <bool MAXPRO>
+// COMPACT (stream v2): nothing is staged -- the walking warp draws index and value of every step itself (fy_walk_column_v2).
+template <bool MAXPRO, bool COMPACT>
 __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, d = p.d, ns = p.ns;
@@ -167,9 +168,17 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
     unsigned long long idx = p.lo + blockIdx.x;
     if (idx < p.hi) {  // prologue: the first candidate, nothing to overlap it with
         const unsigned long long stream = p.seed + idx;  // src/lib.rs:70
-        cta_stage_candidate(p.gen, xbase, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
-        __syncthreads();
-        cta_walk_columns(xbase, jst, n, d, ns, tid, kPipeThreads);
+        if (COMPACT) {
+            for (int k = tid; k < d; k += kPipeThreads) {
+                uint32_t ka, kb;
+                lhd2_column_key((uint32_t)k, (uint32_t)stream, (uint32_t)(stream >> 32), ka, kb);
+                fy_walk_column_v2(xbase + k * ns, ka, kb, n, p.c1, p.c0);
+            }
+        } else {
+            cta_stage_candidate(p.gen, xbase, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
+            __syncthreads();
+            cta_walk_columns(xbase, jst, n, d, ns, tid, kPipeThreads);
+        }
     }
     __syncthreads();  // the side array is rewritten at the top of the loop
     int cur = 0;
@@ -177,13 +186,24 @@ __global__ void __launch_bounds__(kPipeThreads, 2) search_cta_pipe_kernel(CtaPar
         const unsigned long long nidx = idx + gridDim.x;
         const bool has_next = nidx < p.hi;
         // the side array is free (the previous walk ended before the last barrier) and so is the other buffer
-        if (has_next) {
+        if (has_next && !COMPACT) {
             const unsigned long long stream = p.seed + nidx;
             cta_stage_candidate(p.gen, xbase + (cur ^ 1) * xstride, jst, n, d, ns, (uint32_t)stream, (uint32_t)(stream >> 32), p.c1, p.c0, tid, kPipeThreads);
         }
         if (tid == 0) next_item = 0;
         __syncthreads();  // staged values visible to the walker; buffer `cur` complete; counter armed
-        if (has_next && warp == kWarps - 1) cta_walk_columns(xbase + (cur ^ 1) * xstride, jst, n, d, ns, lane, 32);
+        if (has_next && warp == kWarps - 1) {
+            if (COMPACT) {
+                const unsigned long long stream = p.seed + nidx;
+                for (int k = lane; k < d; k += 32) {
+                    uint32_t ka, kb;
+                    lhd2_column_key((uint32_t)k, (uint32_t)stream, (uint32_t)(stream >> 32), ka, kb);
+                    fy_walk_column_v2(xbase + (cur ^ 1) * xstride + k * ns, ka, kb, n, p.c1, p.c0);
+                }
+            } else {
+                cta_walk_columns(xbase + (cur ^ 1) * xstride, jst, n, d, ns, lane, 32);
+            }
+        }
 
         // ---- scoring: items (row tile, column block) in tile-major order from the shared counter
         const double* xs = xbase + cur * xstride;
@@ -232,9 +252,14 @@ static bool cta_compact(unsigned long long n, unsigned long long d) {
 }
 static size_t cta_smem_bytes(unsigned long long n, unsigned long long d) { return cta_smem_bytes_layout(n, d, cta_compact(n, d)); }
 
+static bool cta_pipe_compact() {
+    if (stream_version() != 2) return false;
+    if (const char* e = cfg("MAXPRO_CTA_PIPE_COMPACT")) return atoi(e) != 0;
+    return true;
+}
 static size_t cta_pipe_smem_bytes(unsigned long long n, unsigned long long d) {
     unsigned long long ns = cta_row_stride(n);
-    return (size_t)(((d * ns * 18 + 15) / 16) * 16);
+    return (size_t)(((d * ns * (cta_pipe_compact() ? 16 : 18) + 15) / 16) * 16);
 }
 
 // The pipelined kernel pays for its second buffer with occupancy; it is used while two CTAs of
@@ -283,15 +308,16 @@ cudaError_t launch_search_cta(const SearchLaunch& L) {
     cudaError_t e;
     if (cta_use_pipe(L.n, L.d)) {
         const size_t psmem = cta_pipe_smem_bytes(L.n, L.d);
-        if (L.metric == 0) {
-            e = cudaFuncSetAttribute(search_cta_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-            if (e != cudaSuccess) return e;
-            search_cta_pipe_kernel<true><<<L.grid, kPipeThreads, psmem, L.stream>>>(p);
-        } else {
-            e = cudaFuncSetAttribute(search_cta_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-            if (e != cudaSuccess) return e;
-            search_cta_pipe_kernel<false><<<L.grid, kPipeThreads, psmem, L.stream>>>(p);
-        }
+        e = cudaSuccess;
+        auto gop = [&](auto kernel) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            if (e != cudaSuccess) return;
+            kernel<<<L.grid, kPipeThreads, psmem, L.stream>>>(p);
+        };
+        const bool pc = cta_pipe_compact();
+        if (L.metric == 0) { if (pc) gop(search_cta_pipe_kernel<true, true>); else gop(search_cta_pipe_kernel<true, false>); }
+        else { if (pc) gop(search_cta_pipe_kernel<false, true>); else gop(search_cta_pipe_kernel<false, false>); }
+        if (e != cudaSuccess) return e;
         return cudaGetLastError();
     }
     const size_t smem = cta_smem_bytes(L.n, L.d);

@@ -227,9 +227,12 @@ def test_search_cta_single_and_double_buffered(n, d, iters, pipe, switches):
     seed = 11
     for metric in (METRIC_MAXPRO, METRIC_MAXIMIN):
         s_ref, i_ref = oracle.search_range(n, d, metric, seed, 5, 5 + iters)
-        s, i = engine.search_range(n, d, metric, seed, 5, 5 + iters)
-        assert i == i_ref
-        assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
+        for staged in ("1", "0"):  # stream v2: the walking lanes draw every step themselves (default) or read what all threads staged
+            switches.set("MAXPRO_CTA_PIPE_COMPACT", staged)
+            switches.set("MAXPRO_CTA_COMPACT", staged)
+            s, i = engine.search_range(n, d, metric, seed, 5, 5 + iters)
+            assert i == i_ref
+            assert math.isclose(s, s_ref, rel_tol=REL) if metric == METRIC_MAXPRO else s == s_ref
 
 
 @pytest.mark.parametrize("threads", ["128", "256", "512"])

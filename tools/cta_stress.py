@@ -26,8 +26,9 @@ while time.time() < t_end:
     N = int(min(3000, max(40, 4e8 / (n * n * d))))
     lo = int(rng.integers(0, 1000))
     res = []
-    for pipe, th, cp in (("1", None, None), ("0", "128", "0"), ("0", "128", "1"), ("0", "256", "1"), ("0", "512", "1"), ("0", "512", "0")):
+    for pipe, th, cp in (("1", None, "1"), ("1", None, "0"), ("0", "128", "0"), ("0", "128", "1"), ("0", "256", "1"), ("0", "512", "1"), ("0", "512", "0")):
         _lib.debug_set("MAXPRO_CTA_PIPE", pipe); _lib.debug_set("MAXPRO_CTA_THREADS", th); _lib.debug_set("MAXPRO_CTA_COMPACT", cp)
+        _lib.debug_set("MAXPRO_CTA_PIPE_COMPACT", cp)
         try:
             res.append(engine.search_range(n, d, metric, seed, lo, lo + N))
         except Exception:

@@ -10,12 +10,12 @@ for n, d in zip(args[0::2], args[1::2]):
     flops = (3 * d + 3) * n * (n - 1) // 2
     N = max(2000, min(1 << 26, int(2e12 / flops)))
     out = []
-    variants = [("pipe", {"MAXPRO_CTA_PIPE": "1"})]
+    variants = [("pipe", {"MAXPRO_CTA_PIPE": "1", "MAXPRO_CTA_PIPE_COMPACT": "1"}), ("pipe staged", {"MAXPRO_CTA_PIPE": "1", "MAXPRO_CTA_PIPE_COMPACT": "0"})]
     for th in ("128", "256", "512"):
         for cp in ("0", "1"):
             variants.append((f"single t{th} c{cp}", {"MAXPRO_CTA_PIPE": "0", "MAXPRO_CTA_THREADS": th, "MAXPRO_CTA_COMPACT": cp}))
     for tag, sw in variants:
-        for k in ("MAXPRO_CTA_PIPE", "MAXPRO_CTA_THREADS", "MAXPRO_CTA_COMPACT"):
+        for k in ("MAXPRO_CTA_PIPE", "MAXPRO_CTA_PIPE_COMPACT", "MAXPRO_CTA_THREADS", "MAXPRO_CTA_COMPACT"):
             _lib.debug_set(k, sw.get(k))
         try:
             engine.search_range(n, d, METRIC_MAXPRO, 42, 0, min(N, 1 << 14))
