@@ -240,10 +240,10 @@ static size_t cta_smem_bytes_layout(unsigned long long n, unsigned long long d, 
     return (size_t)(((d * ns * (compact ? 8 : 10) + 15) / 16) * 16 + 16 * sizeof(double));
 }
 // The compact layout (stream v2) takes over where the design no longer fits beside its side array -- and on wide designs,
-// d >= 12, where it is simply faster: one lane per column walks, so d columns are generated side by side and the staging
-// phase with its barrier is gone.  Measured against the double-buffered kernel (tools/cta_variants.py, algorithmic TFLOP/s):
-// (100,32) 9.3 -> 12.2, (120,16) 9.9 -> 12.2, (150,20) 12.0 -> 13.9, (400,16) 15.3 -> 17.8, (500,20) 16.9 -> 18.4, (256,12)
-// 14.7 -> 15.2; at d = 10 and below the double-buffered kernel stays ahead ((500,10) 17.4 vs 17.0, (300,6) 13.4 vs 13.2).
+// d >= 12, where it is a little faster: one lane per column walks, so d columns are generated side by side and the staging
+// phase with its barrier is gone ((1000,20) 19.2 -> 20.1, (2000,10) 19.9 -> 20.2 algorithmic TFLOP/s; at d <= 10 the two
+// layouts are within 1 %, tools/cta_variants.py).  The double-buffered kernel, which stages nothing either under stream v2,
+// is taken whenever two of its CTAs fit one SM.
 static bool cta_wide(unsigned long long d) { return stream_version() == 2 && d >= 12; }
 static bool cta_compact(unsigned long long n, unsigned long long d) {
     if (stream_version() != 2) return false;
@@ -266,7 +266,6 @@ static size_t cta_pipe_smem_bytes(unsigned long long n, unsigned long long d) {
 // eight warps still fit one SM (the single-buffer kernel then runs four CTAs of four warps).
 static bool cta_use_pipe(unsigned long long n, unsigned long long d) {
     if (const char* e = cfg("MAXPRO_CTA_PIPE")) return atoi(e) != 0 && cta_pipe_smem_bytes(n, d) + 1024 <= kSmemBudget;
-    if (cta_wide(d)) return false;  // the single-buffer kernel in its compact layout (see cta_compact)
     return 2 * (cta_pipe_smem_bytes(n, d) + 2048) <= kSmemBudget;
 }
 
