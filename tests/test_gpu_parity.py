@@ -460,6 +460,23 @@ def test_anneal_maximin_swap_screened_hard_designs(kind, n, d, iters, minimize, 
     assert np.array_equal(got2, ref) and best2 == ref_best
 
 
+@pytest.mark.parametrize("bad", [float("nan"), float("inf"), 1.0e200])
+def test_anneal_maximin_swap_screened_unquantisable_design(bad, switches):
+    """A design the 8-bit copy cannot represent (a non-finite entry, a range beyond 1e30): the screened kernel must notice
+    and do every step with its exact pass -- same result as the kernel that has no screening at all."""
+    x = oracle.generate_lhd(520, 16, 9)
+    x[7, 3] = bad
+    switches.set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", "1")
+    a = engine.anneal_lhd(x, 150, 0.05, 0.99, METRIC_MAXIMIN, False, 4, True, n_chains=2)
+    switches.set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", "0")
+    b = engine.anneal_lhd(x, 150, 0.05, 0.99, METRIC_MAXIMIN, False, 4, True, n_chains=2)
+    assert np.array_equal(a[0], b[0], equal_nan=True) and a[2] == b[2]
+    assert a[1] == b[1] or (math.isnan(a[1]) and math.isnan(b[1]))
+    if math.isfinite(bad):
+        ref, ref_best = oracle.anneal_lhd(x, 150, 0.05, 0.99, METRIC_MAXIMIN, False, 4 + a[2], True)
+        assert np.array_equal(a[0], ref) and a[1] == ref_best
+
+
 @pytest.mark.parametrize("threads", [32, 96, 160, 512])
 def test_anneal_maximin_swap_screened_thread_counts(threads, switches):
     """Odd warp counts (the evaluating threads are the upper half of the block) and one warp for the whole chain."""
