@@ -74,7 +74,10 @@ MAXPRO_API const char *maxpro_version(void);
  * by any reference test, so the engine defines its own): 2 = LHD-mix v2, the default --
  * one Philox4x32-10 call per column for the key, a 32-bit multiply-xorshift mixer per element; 1 = LHD-Philox
  * v1, the stream of the first release (one Philox call per two elements).  Process-wide.  Every kernel, the
- * winner regeneration and the CPU oracle implement both; a seed names different designs under the two. */
+ * winner regeneration and the CPU oracle implement both; a seed names different designs under the two.
+ * Set it BEFORE asking for workspace sizes: which kernel serves a shape can depend on the stream (under v2 the
+ * CTA-per-candidate search keeps designs up to 227 KB on chip, under v1 up to 182 KB), and a device-side call whose
+ * workspace was sized under the other version is refused with MAXPRO_ERR_INVALID rather than served. */
 MAXPRO_API int maxpro_set_stream_version(int version);
 MAXPRO_API int maxpro_get_stream_version(int *version);
 MAXPRO_API int maxpro_device_count(int *count);
