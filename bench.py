@@ -562,8 +562,9 @@ def main():
         score_e2e = {"value": nb / best_t, "unit": "supplied designs scored/s (n=50, d=3, MaxPro)", "designs": nb,
                      "h2d_bytes_per_call": int(designs.nbytes), "d2h_bytes_per_call": nb * 8 + 16,
                      "h2d_gb_per_s": designs.nbytes / best_t / 1e9,
-                     "note": "maxpro_score_batch with pageable host buffers, best of 3: bound by the host-to-device copy, "
-                             "not by the kernel (1.07e9 designs/s device-resident, profiles/)"}
+                     "note": "maxpro_score_batch with pageable host buffers, best of 3: bound by the host-to-device copy (staged through "
+                             "pinned buffers by several host threads, ~2x a plain cudaMemcpy), not by the kernel (1.07e9 designs/s "
+                             "device-resident, profiles/)"}
 
     traffic, traffic_src = newest_profile_traffic()
     line = {

@@ -115,6 +115,79 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// Large host inputs (maxpro_score_batch).  A cudaMemcpy from pageable memory goes through the driver's own staging at
+// 8-11 GB/s, one host thread copying; the kernel behind it needs a hundredth of that time.  So: chunks of kStageChunk bytes
+// are copied by several host threads into two pinned staging buffers (kept per calling thread, released with the device
+// cache) and each chunk is sent with cudaMemcpyAsync while the next one is being staged.  Memory that is already pinned or
+// managed, and anything small, takes the plain copy.  MAXPRO_H2D_STAGED=0 switches the staging off (tests, measurements).
+constexpr size_t kStageChunk = 16u << 20;
+struct HostStaging {
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ready = false;
+    cudaError_t init() {
+        if (ready) return cudaSuccess;
+        for (int i = 0; i < 2; ++i) {
+            cudaError_t e = cudaHostAlloc(&buf[i], kStageChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) { release(); return e; }
+        }
+        ready = true;
+        return cudaSuccess;
+    }
+    void release() {
+        for (int i = 0; i < 2; ++i) {
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            if (buf[i]) cudaFreeHost(buf[i]);
+            ev[i] = nullptr; buf[i] = nullptr;
+        }
+        ready = false;
+    }
+    ~HostStaging() { release(); }
+};
+thread_local HostStaging g_staging;
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes, unsigned int nthreads) {
+    if (nthreads <= 1 || bytes < (4u << 20)) { std::memcpy(dst, src, bytes); return; }
+    const size_t part = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> workers;
+    for (unsigned int t = 1; t < nthreads; ++t) {
+        const size_t off = (size_t)t * part;
+        if (off >= bytes) break;
+        const size_t len = std::min(part, bytes - off);
+        workers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    std::memcpy(dst, src, std::min(part, bytes));
+    for (auto& w : workers) w.join();
+}
+
+cudaError_t h2d_large(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    bool staged = bytes >= 4 * kStageChunk;
+    if (const char* e = mp::cfg("MAXPRO_H2D_STAGED")) staged = atoi(e) != 0 && bytes > kStageChunk;
+    if (staged) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) { if (attr.type != cudaMemoryTypeUnregistered) staged = false; }
+        else cudaGetLastError();
+    }
+    if (staged && g_staging.init() != cudaSuccess) { cudaGetLastError(); staged = false; }
+    if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    unsigned int nthreads = std::thread::hardware_concurrency() / 2;
+    nthreads = nthreads < 1 ? 1 : (nthreads > 8 ? 8 : nthreads);
+    size_t off = 0;
+    for (int c = 0; off < bytes; ++c) {
+        const int b = c & 1;
+        const size_t len = std::min(kStageChunk, bytes - off);
+        // the buffer's last transfer is done (a never-recorded event is complete; a call that failed half-way may have left one pending)
+        if (cudaError_t e = cudaEventSynchronize(g_staging.ev[b]); e != cudaSuccess) return e;
+        parallel_memcpy(g_staging.buf[b], static_cast<const char*>(src) + off, len, nthreads);
+        cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst) + off, g_staging.buf[b], len, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(g_staging.ev[b], st);
+        if (e != cudaSuccess) return e;
+        off += len;
+    }
+    return cudaSuccess;
+}
+
 int sm_count_cached[64];
 
 int ensure_device(int* sms = nullptr) {
@@ -612,6 +685,7 @@ uint64_t maxpro_kernel_launch_count(void) { return mp::g_launches.load(std::memo
 int maxpro_release_device_cache(uint64_t* bytes) {
     const uint64_t released = g_cache.cached_bytes;
     g_cache.drop_all();
+    g_staging.release();  // the pinned staging buffers of maxpro_score_batch (host memory: not counted in *bytes)
     if (bytes) *bytes = released;
     return MAXPRO_OK;
 }
@@ -749,7 +823,7 @@ int maxpro_score_batch(const double* designs, uint64_t b, uint64_t n, uint64_t d
     CUDA_TRY(dr.alloc(sizeof(BestRec)));
     CUDA_TRY(dw.alloc(ws_bytes));
     cudaStream_t st = cudaStreamPerThread;
-    CUDA_TRY(cudaMemcpyAsync(dd.p, designs, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h2d_large(dd.p, designs, bytes, st));
     if (int rc = score_batch_device_impl(dd.as<double>(), b, n, d, metric, ds.as<double>(), dr.p, dw.p, ws_bytes, st)) return rc;
     BestRec rec;
     if (scores) CUDA_TRY(cudaMemcpyAsync(scores, ds.p, b * sizeof(double), cudaMemcpyDeviceToHost, st));

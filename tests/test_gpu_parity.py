@@ -339,6 +339,23 @@ def test_search_full_size_properties():
     assert s == math.inf and i == 2 ** 64 - 1
 
 
+def test_score_batch_large_host_input_staged_copy(switches):
+    """Inputs of 64 MB and more reach the device through pinned staging buffers filled by several host threads
+    (api.cu: h2d_large); scores and argbest must be those of the plain copy, for a batch that is not a multiple of the chunk."""
+    rng = np.random.default_rng(5)
+    b, n, d = 70_001, 50, 3  # 84 MB: five 16 MB chunks and a ragged one
+    designs = rng.random((b, n, d))
+    designs[41_234] = designs[9]  # a duplicated design: the later index wins the tie only if both copies arrive intact
+    got, arg = engine.score_batch(designs, METRIC_MAXPRO)
+    switches.set("MAXPRO_H2D_STAGED", "0")
+    ref, ref_arg = engine.score_batch(designs, METRIC_MAXPRO)
+    assert np.array_equal(got, ref) and arg == ref_arg
+    assert got[41_234] == got[9]
+    sub = rng.integers(0, b, 64)
+    want, _ = oracle.score_batch(designs[sub], oracle.MAXPRO)
+    assert rel_err(got[sub], want) < REL
+
+
 # ---------------------------------------------------------------- annealer (K3)
 
 @pytest.mark.parametrize("metric,minimize", [(METRIC_MAXPRO, True), (METRIC_MAXIMIN, False)])
