@@ -240,6 +240,19 @@ def run_configs(which, rank, world, dev, peak_tflops, peak32_tflops, max_over_ra
             for key in ("Original metric", "Swapped metric", "Annealed metric"):
                 if ln.startswith(key + ":"):
                     metrics[key] = float(ln.split(":", 1)[1])
+        # what any process pays before its first kernel: a bare cudaFree(0) in a fresh process (tools/micro/ctx.cu, built by
+        # __graft_entry__.build()) -- the floor of the CLI's wall time on this box
+        ctx_s = None
+        ctx_bin = os.path.join(ROOT, "tools", "micro", "ctx")
+        if os.path.exists(ctx_bin):
+            try:
+                vals = []
+                for _ in range(2):
+                    pr = subprocess.run([ctx_bin], capture_output=True, text=True, env=env)
+                    vals.append(float(pr.stdout.split(":")[1].split()[0]) * 1e-3)
+                ctx_s = min(vals)
+            except Exception:  # noqa: BLE001 -- the probe is informational
+                ctx_s = None
         N = 1 << 26
         (_, s, i), t = _best_of(lambda: engine.build_lhd(n, d, N, METRIC_MAXPRO, 42), 2)
         flops = (3 * d + 3) * n * (n - 1) // 2 + 2
@@ -248,6 +261,7 @@ def run_configs(which, rank, world, dev, peak_tflops, peak32_tflops, max_over_ra
         out["C1"] = {"workload": "CLI --iterations 100000 --samples 50 --ndims 2 --metric max-pro --seed 42 "
                                  "(search + 20,000 swap + 80,000 jitter annealing steps, process start included)",
                      "value": wall, "unit": "s (CLI wall, best of 2)", "cli_rc": r.returncode, "cli_metrics": metrics,
+                     "cuda_context_s": ctx_s,  # a bare cudaFree(0) in a fresh process on this box: the floor of any GPU CLI call
                      "check": {"annealed <= swapped <= original": ok},
                      "search_rate": {"value": N / t, "unit": "candidates/s", "candidates": N},
                      "roofline": roof(N / t, flops, "n=50, d=2 MaxPro search at 2^26 candidates through build_lhd "
