@@ -23,6 +23,7 @@
 // Draws, Metropolis rule, global best and the move log are those of anneal.cu.
 #include "anneal.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #ifndef AMX_PROFILE
@@ -1189,9 +1190,6 @@ cudaError_t launch_anneal_maximin(const AnnealLaunch& L, int plan_sms, unsigned 
     p.cta_chain = L.cta_chain; p.cta_buf = L.cta_buf;
     p.rowmin0 = L.rowmin0; p.rowarg0 = L.rowarg0; p.qparams = L.qparams;
     const size_t smem = screened ? anneal_maximin_screen_smem_bytes(L.n, L.d) : anneal_maximin_smem_bytes(L.n, L.d);
-    int threads = (int)((L.n + 31) / 32 * 32);
-    if (threads > 512) threads = 512;
-    if (const char* e = cfg("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     void (*kernel)(AnnealParams) = anneal_maximin_swap_kernel;
     if (screened) {
         switch ((L.d + 3) / 4) {  // words per quantised row: in registers up to eight
@@ -1208,6 +1206,34 @@ cudaError_t launch_anneal_maximin(const AnnealLaunch& L, int plan_sms, unsigned 
     }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // Threads per chain.  One chain alone is fastest with one row per thread (up to 512 threads).  Many chains are not: a step
+    // is barrier intervals of dependent shared-memory latency, which several small CTAs on one SM overlap and one large CTA
+    // does not -- (500,10), 4,736 chains: 5.4e7 chain-steps/s with 512 threads, 8.1e7 with 256, 9.0e7 with 128; (300,6) 6.7e7
+    // with 320, 1.98e8 with 64 (tools/anneal_many_chains.py).  So: the block size that puts the most CTAs on an SM, among
+    // the CTAs the chains can fill, with at most six rows per thread; the larger block on a tie.
+    int sms = plan_sms;
+    if (sms <= 0) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    }
+    int threads = (int)((L.n + 31) / 32 * 32);
+    if (threads > 512) threads = 512;
+    if (const char* env = cfg("MAXPRO_ANNEAL_THREADS")) {
+        const int v = atoi(env);
+        if (v >= 32 && v <= 512 && v % 32 == 0) threads = v;
+    } else if (L.n_chains > (unsigned long long)sms) {
+        const unsigned long long needed = (L.n_chains + sms - 1) / sms;  // CTAs per SM the chains can fill
+        const int t_max = threads;
+        long long best_ctas = -1;
+        for (int t = t_max; t >= 32; t -= 32) {
+            if ((long long)t * 6 < (long long)L.n && t != t_max) break;  // more than six rows per thread
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, t, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+            const long long ctas = (long long)std::min<unsigned long long>((unsigned long long)per_sm, needed);
+            if (ctas > best_ctas) { best_ctas = ctas; threads = t; }  // ">": the larger block on a tie (t descends)
+        }
+    }
     if (plan_grid) return anneal_resident_grid(kernel, threads, smem, plan_sms, L.n_chains, 1ull << 20, plan_grid);
     if (L.grid == 0 || L.grid > L.n_chains) return cudaErrorInvalidValue;
     kernel<<<L.grid, threads, smem, L.stream>>>(p);
