@@ -26,6 +26,8 @@
 // Draws: Philox key = chain stream (seed + chain), ctr = {t_lo, t_hi, block, domain}.
 #include "anneal.cuh"
 
+#include <algorithm>
+
 #include <cstdlib>
 #include <type_traits>
 
@@ -398,9 +400,30 @@ static cudaError_t launch_anneal_impl(const AnnealLaunch& L, int plan_sms, unsig
     if (const char* e = cfg("MAXPRO_ANNEAL_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) threads = v; }
     const unsigned long long cap = place != 0 ? kHbmGrid : (1ull << 20);  // HBM placements: one scratch buffer per CTA
     cudaError_t e = cudaSuccess;
+    // Many maximin chains (more chains than SMs, designs in shared memory): the block size that keeps the most threads
+    // resident among the CTAs the chains can fill, the smaller block on a tie -- several small CTAs overlap their barriers and
+    // Metropolis steps where one large CTA waits: 20,000 jitter chains of (50,3) 1.5e8 -> 2.9e8 chain-steps/s, (300,6)
+    // 0.93e7 -> 1.23e7 (tools/anneal_many_chains_jit.py).  A minimum does not depend on the order it is taken in, so the
+    // trajectory is the same at every block size; the MaxPro sums are not order-free and keep their block size.
+    int sms = plan_sms;
+    if (sms <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); sms = 0; }
+    }
+    const bool pick_threads = L.metric != 0 && place == 0 && sms > 0 && L.n_chains > (unsigned long long)sms && !cfg("MAXPRO_ANNEAL_THREADS");
     auto go = [&](auto kernel) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return;
+        if (pick_threads) {
+            const unsigned long long needed = (L.n_chains + sms - 1) / sms;
+            long long best_used = -1;
+            for (int t = threads; t >= 32; t -= 32) {
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, t, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+                const long long used = (long long)std::min<unsigned long long>((unsigned long long)per_sm, needed) * t;
+                if (used >= best_used) { best_used = used; threads = t; }
+            }
+        }
         if (plan_grid) { e = anneal_resident_grid(kernel, threads, smem, plan_sms, L.n_chains, cap, plan_grid); return; }
         if (L.grid == 0 || L.grid > L.n_chains || L.grid > cap) { e = cudaErrorInvalidValue; return; }
         kernel<<<L.grid, threads, smem, L.stream>>>(p);
