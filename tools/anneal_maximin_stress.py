@@ -28,9 +28,11 @@ while time.time() < t_end:
         x[:, 1:] = 0.5 + (x[:, 1:] - 0.5) * 1e-5
     x = np.ascontiguousarray(x)
     steps = int(rng.integers(50, 1500))
+    if rng.integers(0, 3) == 0:
+        steps = int(rng.integers(20, 400))
     t0 = float(rng.choice([1e-300, 1e-3, 0.05, 1.0]))
     minimize = bool(rng.integers(0, 2))
-    chains = int(rng.choice([1, 1, 3, 150]))
+    chains = int(rng.choice([1, 1, 3, 150, 600, 3000]))  # more chains than SMs: the launch picks smaller blocks
     seed = int(rng.integers(0, 1 << 40))
     _lib.debug_set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", "1")
     a = engine.anneal_lhd(x, steps, t0, 0.99, METRIC_MAXIMIN, minimize, seed, True, n_chains=chains)
@@ -38,6 +40,11 @@ while time.time() < t_end:
     b = engine.anneal_lhd(x, steps, t0, 0.99, METRIC_MAXIMIN, minimize, seed, True, n_chains=chains)
     _lib.debug_set("MAXPRO_ANNEAL_MAXIMIN_SCREEN", None)
     runs += 1
+    if chains > 1 and steps <= 400:  # the winning chain alone (one row per thread) must end where it ended among many
+        c = engine.anneal_lhd(x, steps, t0, 0.99, METRIC_MAXIMIN, minimize, seed + a[2], True, n_chains=1)
+        if not (np.array_equal(a[0], c[0]) and a[1] == c[1]):
+            bad += 1
+            print(f"REPLAY MISMATCH n={n} d={d} kind={kind} steps={steps} t0={t0} minimize={minimize} chains={chains} seed={seed}", flush=True)
     if not (np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2]):
         bad += 1
         print(f"MISMATCH n={n} d={d} kind={kind} steps={steps} t0={t0} minimize={minimize} chains={chains} seed={seed}", flush=True)
